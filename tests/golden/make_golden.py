@@ -1,0 +1,94 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_probe).
+
+Run in the build container only (needs /root/reference to have built oracle/_ref):
+    make -C oracle ref && python tests/golden/make_golden.py
+Each fixture holds the input reads and every artefact ref_probe dumps for them, so the oracle and the
+CUDA path can be pinned against reference output on machines without /root/reference.
+"""
+import gzip
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from spades_b200.packing import longest_valid, revcomp, synthetic_reads  # noqa: E402
+
+PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+REF = "/root/reference"
+
+
+def ecoli_reads():
+    reads = []
+    for f in ("ecoli_1K_1.fq.gz", "ecoli_1K_2.fq.gz"):
+        lines = gzip.open(os.path.join(REF, "src/projects/spades/test_dataset", f), "rt").read().split("\n")
+        for i in range(1, len(lines), 4):
+            s = longest_valid(lines[i].strip().upper())
+            if s:
+                reads.append(s)
+    return reads
+
+
+def loops_reads():
+    rng = np.random.default_rng(5)
+    g = "".join("ACGT"[i] for i in rng.integers(0, 4, 500))
+    gg = g + g
+    reads = [gg[i:i + 120] for i in range(0, 500, 7)]
+    x = "".join("ACGT"[i] for i in rng.integers(0, 4, 200))
+    h = x + revcomp(x)
+    hh = h + h
+    reads += [hh[i:i + 150] for i in range(0, 400, 5)]
+    return reads
+
+
+# the six literal-read cases of src/test/debruijn/construction_test.cpp:30-64 (k=5) with their etalon edges
+GTEST_CASES = {
+    "SimpleThread": (["ACAAACCACCA"], ["ACAAACCACCA"]),
+    "SimpleThread2": (["ACAAACCACCC", "AAACCACCCAC"], ["ACAAACCACCCAC"]),
+    "SplitThread": (["ACAAACCACCA", "ACAAACAACCC"], ["ACAAAC", "CAAACCACCA", "CAAACAACCC"]),
+    "SplitThread2": (["ACAAACCACCA", "ACAAACAACCA"], ["AACCACCA", "ACAAAC", "CAAACCA", "CAAACAACCA"]),
+    "Buldge": (["ACAAAACACCA", "ACAAACCACCA"], ["ACAAAACACCA", "ACAAACCACCA"]),
+    "CondenseSimple": (["CGAAACCAC", "CGAAAACAC", "AACCACACC", "AAACACACC"], ["CGAAAACACAC", "CACACC", "CGAAACCACAC"]),
+}
+
+
+def run_probe(mode, reads, k, B, T=2):
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        open(rf, "w").write("\n".join(reads) + "\n")
+        out = os.path.join(d, "out")
+        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        res = {}
+        for f in os.listdir(out):
+            p = os.path.join(out, f)
+            if os.path.isfile(p):
+                res[f.replace(".", "_")] = np.frombuffer(open(p, "rb").read(), dtype=np.uint8)
+        return res
+
+
+def save(name, mode, reads, k, B):
+    res = run_probe(mode, reads, k, B)
+    res["reads"] = np.frombuffer("\n".join(reads).encode(), dtype=np.uint8)
+    res["k"] = np.array([k]); res["B"] = np.array([B]); res["mode"] = np.frombuffer(mode.encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
+    print(name, {a: len(b) for a, b in res.items() if a not in ("k", "B", "mode")})
+
+
+if __name__ == "__main__":
+    ec = ecoli_reads()
+    save("ecoli_k21_B40_graph", "graph", ec, 21, 40)          # BASELINE.json configs[0]
+    save("ecoli_k21_B16_count", "count", ec, 21, 16)          # spades-kmercount defaults (kmercount.cpp:220)
+    save("ecoli_k55_B16_graph", "graph", ec[:1500], 55, 16)
+    save("ecoli_k77_B7_graph", "graph", ec[:800], 77, 7)
+    save("ecoli_k99_B3_graph", "graph", ec[:800], 99, 3)
+    save("syn_k21_B10_graph", "graph", synthetic_reads(400, 100, 1500, 0.01, seed=1), 21, 10)
+    save("syn_k33_B5_count", "count", synthetic_reads(300, 100, 1500, 0.01, seed=2), 33, 5)
+    save("loops_k21_B10_graph", "graph", loops_reads(), 21, 10)
+    save("dense_k5_B4_graph", "graph", synthetic_reads(200, 60, 200, 0.02, seed=3), 5, 4)
+    save("dense_k3_B1_graph", "graph", synthetic_reads(100, 40, 100, 0.02, seed=4), 3, 1)
+    for nm, (rd, _) in GTEST_CASES.items():
+        save("gtest_" + nm + "_k5", "graph", rd, 5, 2)

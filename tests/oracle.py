@@ -1,0 +1,177 @@
+"""ctypes front end of oracle/liboracle.so -- TEST INFRASTRUCTURE (checker only, never the product path)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORC_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_ORC_DIR, "liboracle.so")
+        src = os.path.join(_ORC_DIR, "spades_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _ORC_DIR, "oracle"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
+        L.orc_xxh3_64.restype = u64; L.orc_xxh3_64.argtypes = [vp, i32]
+        L.orc_xxh3_128.restype = None; L.orc_xxh3_128.argtypes = [vp, i32, vp, vp]
+        L.orc_bucket.restype = u64; L.orc_bucket.argtypes = [vp, i32, u64]
+        L.orc_is_minimal.restype = i32; L.orc_is_minimal.argtypes = [vp, i32]
+        L.orc_rc.restype = None; L.orc_rc.argtypes = [vp, i32, vp]
+        L.orc_count.restype = vp; L.orc_count.argtypes = [vp, vp, vp, i64, i32, i32, i32]
+        L.orc_kmers_from_kpomers.restype = vp; L.orc_kmers_from_kpomers.argtypes = [vp, i32]
+        for f in ("orc_kset_keys", "orc_kset_counts", "orc_kset_bsz"):
+            getattr(L, f).restype = vp; getattr(L, f).argtypes = [vp]
+        L.orc_kset_n.restype = i64; L.orc_kset_n.argtypes = [vp]
+        L.orc_kset_nw.restype = i32; L.orc_kset_nw.argtypes = [vp]
+        L.orc_kset_free.restype = None; L.orc_kset_free.argtypes = [vp]
+        L.orc_mphf_build.restype = vp; L.orc_mphf_build.argtypes = [vp]
+        L.orc_mphf_free.restype = None; L.orc_mphf_free.argtypes = [vp]
+        L.orc_mphf_lookup.restype = u64; L.orc_mphf_lookup.argtypes = [vp, vp]
+        L.orc_mphf_nfinal.restype = u64; L.orc_mphf_nfinal.argtypes = [vp]
+        L.orc_mphf_serialize.restype = i64; L.orc_mphf_serialize.argtypes = [vp, vp]
+        L.orc_masks.restype = None; L.orc_masks.argtypes = [vp, vp, vp, i64]
+        L.orc_coverage.restype = None; L.orc_coverage.argtypes = [vp, vp, vp]
+        L.orc_histogram.restype = i64; L.orc_histogram.argtypes = [vp, i64, vp, i64]
+        L.orc_unitigs.restype = vp; L.orc_unitigs.argtypes = [vp, vp, vp, i32]
+        L.orc_unitigs_n.restype = i64; L.orc_unitigs_n.argtypes = [vp]
+        L.orc_unitig_len.restype = i64; L.orc_unitig_len.argtypes = [vp, i64]
+        L.orc_unitig_seq.restype = vp; L.orc_unitig_seq.argtypes = [vp, i64]
+        L.orc_unitigs_free.restype = None; L.orc_unitigs_free.argtypes = [vp]
+        L.orc_gfa.restype = vp; L.orc_gfa.argtypes = [vp, vp, vp, vp, C.c_char_p, vp]
+        L.orc_free.restype = None; L.orc_free.argtypes = [vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def xxh3_64(words):
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    return int(lib().orc_xxh3_64(_p(w), len(w)))
+
+
+def xxh3_128(words):
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    lo, hi = C.c_uint64(), C.c_uint64()
+    lib().orc_xxh3_128(_p(w), len(w), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class KSet:
+    def __init__(self, h, K, B):
+        self.h, self.K, self.B = h, K, B
+        L = lib()
+        self.n = L.orc_kset_n(h)
+        self.nw = L.orc_kset_nw(h)
+        self.keys = np.ctypeslib.as_array(C.cast(L.orc_kset_keys(h), C.POINTER(C.c_uint64)), shape=(max(self.n, 1) * self.nw,))[: self.n * self.nw].reshape(self.n, self.nw).copy()
+        cp = L.orc_kset_counts(h)
+        self.counts = None if not cp else np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint32)), shape=(max(self.n, 1),))[: self.n].copy()
+        self.bsz = np.ctypeslib.as_array(C.cast(L.orc_kset_bsz(h), C.POINTER(C.c_int64)), shape=(B,)).copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_kset_free(self.h); self.h = None
+
+
+def count(words, offs, lens, K, B, mode):
+    words = np.ascontiguousarray(words, np.uint64); offs = np.ascontiguousarray(offs, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    h = lib().orc_count(_p(words), _p(offs), _p(lens), len(lens), K, B, mode)
+    return KSet(h, K, B)
+
+
+def kmers_from_kpomers(kp: KSet, B):
+    return KSet(lib().orc_kmers_from_kpomers(kp.h, B), kp.K - 1, B)
+
+
+class Mphf:
+    def __init__(self, ks: KSet):
+        self.ks = ks
+        self.h = lib().orc_mphf_build(ks.h)
+
+    def serialize(self) -> bytes:
+        n = lib().orc_mphf_serialize(self.h, None)
+        buf = np.zeros(n, np.uint8)
+        lib().orc_mphf_serialize(self.h, _p(buf))
+        return buf.tobytes()
+
+    def lookup(self, key_words):
+        w = np.ascontiguousarray(key_words, np.uint64)
+        return int(lib().orc_mphf_lookup(self.h, _p(w)))
+
+    def nfinal(self):
+        return int(lib().orc_mphf_nfinal(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_mphf_free(self.h); self.h = None
+
+
+def masks(kp: KSet, mk: Mphf, nk):
+    out = np.zeros(max(nk, 1), np.uint8)
+    lib().orc_masks(kp.h, mk.h, _p(out), nk)
+    return out[:nk]
+
+
+def coverage(kp: KSet, mkp: Mphf):
+    out = np.zeros(max(kp.n, 1), np.uint32)
+    lib().orc_coverage(kp.h, mkp.h, _p(out))
+    return out[: kp.n]
+
+
+def histogram(cov):
+    cov = np.ascontiguousarray(cov, np.uint32)
+    mx = lib().orc_histogram(_p(cov), len(cov), None, 0)
+    hist = np.zeros(max(mx, 1), np.uint64)
+    lib().orc_histogram(_p(cov), len(cov), _p(hist), mx)
+    return hist[:mx]
+
+
+class Unitigs:
+    def __init__(self, km: KSet, mk: Mphf, masks_arr, keep_loops=True):
+        m = np.ascontiguousarray(masks_arr, np.uint8)
+        self.h = lib().orc_unitigs(km.h, mk.h, _p(m), 1 if keep_loops else 0)
+        L = lib()
+        self.seqs = []
+        lut = np.frombuffer(b"ACGT", np.uint8)
+        for i in range(L.orc_unitigs_n(self.h)):
+            n = L.orc_unitig_len(self.h, i)
+            a = np.ctypeslib.as_array(C.cast(L.orc_unitig_seq(self.h, i), C.POINTER(C.c_uint8)), shape=(n,))
+            self.seqs.append(lut[a].tobytes().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_unitigs_free(self.h); self.h = None
+
+
+def gfa(u: Unitigs, mk: Mphf, mkp: Mphf = None, cov=None, version="SPAdes-4.3.0-dev") -> str:
+    n = C.c_int64()
+    covp = None
+    if cov is not None:
+        cov = np.ascontiguousarray(cov, np.uint32); covp = _p(cov)
+    p = lib().orc_gfa(u.h, mk.h, mkp.h if mkp else None, covp, version.encode(), C.byref(n))
+    s = C.string_at(p, n.value).decode()
+    lib().orc_free(p)
+    return s
+
+
+def full_graph(reads, k, B):
+    """Whole path on a list of ACGT strings; returns dict of artefacts named like ref_probe's files."""
+    from spades_b200.packing import pack_reads
+    words, offs, lens = pack_reads(reads)
+    kp = count(words, offs, lens, k + 1, B, 0)
+    km = kmers_from_kpomers(kp, B)
+    mk = Mphf(km)
+    mkp = Mphf(kp)
+    mk_arr = masks(kp, mk, km.n)
+    cov = coverage(kp, mkp)
+    u = Unitigs(km, mk, mk_arr, True)
+    return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, cov=cov, hist=histogram(cov), unitigs=u,
+                gfa=gfa(u, mk, mkp, cov))

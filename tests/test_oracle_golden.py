@@ -1,0 +1,93 @@
+"""CPU tests: the plain-C oracle (oracle/spades_oracle.c) against
+  * golden fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py -> ref_probe),
+  * the known-answer unitig sets of the reference's own gtest (src/test/debruijn/construction_test.cpp:30-64),
+  * RtSeq known answers (src/test/include_test/rtseq_test.cpp) for packing / RC / minimality,
+  * the independent python-xxhash binding (xxHash 0.8.2) for the XXH3 restatement.
+"""
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle as O
+from spades_b200.packing import pack_reads, revcomp, unpack_kmers
+
+
+def oracle_artifacts(reads, k, B):
+    r = O.full_graph(reads, k, B)
+    return dict(kpomers=r["kp"].keys, kp_bsz=r["kp"].bsz, kmers=r["km"].keys, kmer_index=r["mk"].serialize(),
+                kpomer_index=r["mkp"].serialize(), masks=r["masks"], cov=r["cov"], hist=r["hist"],
+                unitigs=r["unitigs"].seqs, gfa=r["gfa"]), r
+
+
+@pytest.mark.parametrize("name", G.names("graph"))
+def test_oracle_graph_matches_reference_golden(name):
+    g = G.load(name)
+    art, r = oracle_artifacts(g["reads"], g["k"], g["B"])
+    assert r["mk"].nfinal() == 0 and r["mkp"].nfinal() == 0
+    assert G.check_graph(g, art) == []
+
+
+@pytest.mark.parametrize("name", G.names("count"))
+def test_oracle_kmercount_matches_reference_golden(name):
+    g = G.load(name)
+    words, offs, lens = pack_reads(g["reads"])
+    ks = O.count(words, offs, lens, g["k"], g["B"], 1)
+    assert G.check_count(g, dict(final_kmers=ks.keys, bsz=ks.bsz)) == []
+
+
+GTEST = {  # construction_test.cpp:30-64
+    "SimpleThread": (["ACAAACCACCA"], ["ACAAACCACCA"]),
+    "SimpleThread2": (["ACAAACCACCC", "AAACCACCCAC"], ["ACAAACCACCCAC"]),
+    "SplitThread": (["ACAAACCACCA", "ACAAACAACCC"], ["ACAAAC", "CAAACCACCA", "CAAACAACCC"]),
+    "SplitThread2": (["ACAAACCACCA", "ACAAACAACCA"], ["AACCACCA", "ACAAAC", "CAAACCA", "CAAACAACCA"]),
+    "Buldge": (["ACAAAACACCA", "ACAAACCACCA"], ["ACAAAACACCA", "ACAAACCACCA"]),
+    "CondenseSimple": (["CGAAACCAC", "CGAAAACAC", "AACCACACC", "AAACACACC"], ["CGAAAACACAC", "CACACC", "CGAAACCACAC"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GTEST))
+def test_oracle_reference_gtest_known_answers(name):
+    reads, etalon = GTEST[name]
+    r = O.full_graph(reads, 5, 3)
+    got = set()
+    for s in r["unitigs"].seqs:
+        got.add(s); got.add(revcomp(s))
+    want = set()
+    for s in etalon:
+        want.add(s); want.add(revcomp(s))
+    assert got == want          # AssertGraph, src/test/debruijn/test_utils.cpp:109-138
+
+
+def test_xxh3_matches_python_xxhash():
+    xxhash = pytest.importorskip("xxhash")
+    rng = np.random.default_rng(0)
+    for nw in (1, 2, 3, 4):
+        for _ in range(200):
+            w = rng.integers(0, 2**63, size=nw, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=nw, dtype=np.uint64)
+            b = w.tobytes()
+            assert O.xxh3_64(w) == xxhash.xxh3_64_intdigest(b)
+            lo, hi = O.xxh3_128(w)
+            assert (hi << 64) | lo == xxhash.xxh3_128_intdigest(b)
+
+
+def test_rtseq_known_answers():
+    # rtseq_test.cpp: packing/str round trip and ReverseComplement (:671 `!RtSeq("ACGTTGCA...")`)
+    import ctypes as C
+    L = O.lib()
+    for s in ["ACGT", "ACGTACGTACGTACGTACGTACGTACGTACGTACG", "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "A" * 127, "ACGTTGCAGGACT"]:
+        K = len(s)
+        w, _, _ = pack_reads([s])
+        assert unpack_kmers(w, K) == [s]
+        out = np.zeros(len(w), np.uint64)
+        L.orc_rc(w.ctypes.data_as(C.c_void_p), K, out.ctypes.data_as(C.c_void_p))
+        assert unpack_kmers(out, K) == [revcomp(s)]
+        assert bool(L.orc_is_minimal(w.ctypes.data_as(C.c_void_p), K)) == (s <= revcomp(s))
+
+
+def test_empty_and_short_inputs():
+    # reads shorter than K are skipped (kmer_splitters.hpp:30-31); empty input gives empty buckets
+    words, offs, lens = pack_reads(["ACGT", "AC"])
+    ks = O.count(words, offs, lens, 6, 4, 0)
+    assert ks.n == 0 and list(ks.bsz) == [0, 0, 0, 0]
+    m = O.Mphf(ks)
+    assert len(m.serialize()) == 8 + 4 * (28 + 8) + 5 * 8

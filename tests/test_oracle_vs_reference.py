@@ -1,0 +1,46 @@
+"""CPU test, build container only: runs the UNMODIFIED reference (oracle/_ref/ref_probe) live on fresh
+seeded inputs and checks the C oracle against every artefact. Skipped where the probe binary is absent."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle as O
+from spades_b200.packing import synthetic_reads
+from test_oracle_golden import oracle_artifacts
+
+PROBE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_probe")
+pytestmark = pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/ref_probe not built (make -C oracle ref)")
+
+
+def run_probe(mode, reads, k, B, T=3):
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        open(rf, "w").write("\n".join(reads) + "\n")
+        out = os.path.join(d, "out")
+        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        g = {f.replace(".", "_"): np.frombuffer(open(os.path.join(out, f), "rb").read(), np.uint8)
+             for f in os.listdir(out) if os.path.isfile(os.path.join(out, f))}
+    g.update(k=k, B=B, reads=reads)
+    return g
+
+
+@pytest.mark.parametrize("k,B,seed", [(21, 16, 11), (31, 5, 12), (55, 30, 13), (63, 9, 14), (77, 4, 15), (127, 6, 16)])
+def test_oracle_vs_live_reference_graph(k, B, seed):
+    reads = synthetic_reads(1500, 150, 3000, 0.01, seed=seed)
+    g = run_probe("graph", reads, k, B)
+    art, _ = oracle_artifacts(reads, k, B)
+    assert G.check_graph(g, art) == []
+
+
+@pytest.mark.parametrize("k,B,seed", [(21, 16, 21), (55, 16, 22), (100, 3, 23)])
+def test_oracle_vs_live_reference_kmercount(k, B, seed):
+    from spades_b200.packing import pack_reads
+    reads = synthetic_reads(800, 150, 2000, 0.01, seed=seed)
+    g = run_probe("count", reads, k, B)
+    words, offs, lens = pack_reads(reads)
+    ks = O.count(words, offs, lens, k, B, 1)
+    assert G.check_count(g, dict(final_kmers=ks.keys, bsz=ks.bsz)) == []
