@@ -1,0 +1,129 @@
+/*
+ * spades_b200.h -- C ABI of libspades_b200.so: the B200-native k-mer counting / de Bruijn construction path.
+ *
+ * Plain pointers and sizes only; every function returns 0 on success or a positive error code (never exits,
+ * never throws); sgpu_last_error() gives the message. One sgpu_ctx per process per GPU, used from one host
+ * thread at a time (the reference calls this path from a single thread too).
+ *
+ * Each entry point replaces one piece of the reference (paths relative to the SPAdes source tree):
+ *
+ *   sgpu_reads_*            io/reads binary read records: Sequence::BinRead (common/sequence/sequence.hpp:808-830),
+ *                           SingleReadSeq (common/io/reads/single_read.hpp:307-323) -- 2-bit packed reads
+ *   sgpu_count              kmers::KMerDiskCounter<RtSeq>::Count over a DeBruijnReadKMerSplitter<..., StoringTypeFilter<
+ *                           InvertableStoring>> (SGPU_CANONICAL; common/kmer_index/kmer_mph/kmer_index_builder.hpp:306-332,
+ *                           kmer_splitters.hpp:112-136) or over spades-kmercount's ParallelSortingSplitter (SGPU_ALL_WINDOWS;
+ *                           projects/spades_tools/kmercount.cpp:48-122,219-220)
+ *   sgpu_kmers_from_kpomers KMerDiskCounter::Count over DeBruijnKMerKMerSplitter (kmer_splitters.hpp:138-207), as called by
+ *                           DeBruijnExtensionIndexBuilder::BuildExtensionIndexFromKPOMers (extension_index/
+ *                           kmer_extension_index_builder.hpp:83-96)
+ *   sgpu_kset_*             kmers::KMerDiskStorage<RtSeq> (kmer_index_builder.hpp:47-256): bucket_size, bucket files, merge()
+ *   sgpu_mphf_build         kmers::KMerIndexBuilder<Index>::BuildIndex(index, storage) (kmer_index_builder.hpp:448-498)
+ *   sgpu_mphf_serialize     kmers::KMerIndex::serialize (kmer_mph/kmer_index.hpp:102-108), byte compatible
+ *   sgpu_mphf_lookup        kmers::KMerIndex::seq_idx (kmer_index.hpp:88-93)
+ *   sgpu_graph_build        FillExtensionsFromIndex (kmer_extension_index_builder.hpp:45-60,102-105) +
+ *                           UnbranchingPathExtractor::ExtractUnbranchingPathsAndLoops (assembly_graph/construction/
+ *                           debruijn_graph_constructor.hpp:399-406) + CoverageHashMapBuilder::BuildIndex
+ *                           (ph_map/coverage_hash_map_builder.hpp:42-56) + FillCoverageAndFlankingFromPHM (raw coverage part,
+ *                           assembly_graph/graph_support/coverage_filling.hpp:90-96)
+ *   sgpu_graph_masks        DeBruijnExtensionIndex::raw_data() (extension_index/kmer_extension_index.hpp:83-84)
+ *   sgpu_graph_coverage     PerfectHashMap<RtSeq,uint32_t>::values() of the coverage map (stages/construction.cpp:371-395)
+ *   sgpu_graph_histogram    the multiplicity histogram of PHMCoverageFiller (stages/construction.cpp:404-418)
+ *   sgpu_graph_unitig*      std::vector<Sequence> returned by ExtractUnbranchingPathsAndLoops
+ *   sgpu_graph_gfa          FastGraphFromSequencesConstructor::ConstructGraph (debruijn_graph_constructor.hpp:506-567) +
+ *                           gfa::GFAWriter::WriteSegmentsAndLinks (io/graph/gfa_writer.cpp:36-116)
+ */
+#ifndef SPADES_B200_H_
+#define SPADES_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgpu_ctx sgpu_ctx;
+typedef struct sgpu_kset sgpu_kset;     /* a counted k-mer set resident in HBM (== KMerDiskStorage contents) */
+typedef struct sgpu_mphf sgpu_mphf;     /* a boomphf-compatible KMerIndex resident in HBM */
+typedef struct sgpu_graph sgpu_graph;   /* masks + coverage + unitigs + link records */
+
+typedef struct sgpu_config {
+    int device;                 /* CUDA device ordinal */
+    uint64_t hbm_budget_bytes;  /* 0 = whatever is free on the device */
+    int verbose;
+} sgpu_config;
+
+enum { SGPU_CANONICAL = 0, SGPU_ALL_WINDOWS = 1 };
+
+enum {
+    SGPU_OK = 0, SGPU_EINVAL = 2, SGPU_ENODEV = 3, SGPU_ENOMEM = 4, SGPU_ECUDA = 5, SGPU_EINTERNAL = 6, SGPU_EUNSUPPORTED = 7,
+    SGPU_EIO = 8
+};
+
+/* device-side milliseconds of the last sgpu_count / sgpu_kmers_from_kpomers / sgpu_mphf_build, measured with CUDA events
+ * on the context's stream, plus the number of kernels launched since the context was created */
+typedef struct sgpu_times {
+    float extract_count_ms, extract_scatter_ms, refine_ms, local_sort_ms, compact_ms, mphf_ms;
+    uint64_t instances;   /* records the partition kernel wrote */
+    uint64_t passes;      /* bucket-group passes */
+    uint64_t launches;    /* kernels launched by this context so far */
+    uint64_t peak_bytes;  /* peak device memory held by this context */
+} sgpu_times;
+
+int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out);
+void sgpu_destroy(sgpu_ctx *ctx);
+const char *sgpu_last_error(const sgpu_ctx *ctx);
+int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out);
+
+/* reads: read r occupies words[offs[r] .. offs[r]+ceil(lens[r]/32)), nucleotide i at bits 2(i%32) of word i/32, A=0 C=1 G=2 T=3
+ * (N-free: apply LongestValid first, io/reads/longest_valid_wrapper.hpp:16-53). offs are relative to `words`. */
+int sgpu_reads_clear(sgpu_ctx *ctx);
+int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
+/* use a read set that already lives in device memory (not copied, must stay valid while the context uses it) */
+int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads);
+
+int sgpu_count(sgpu_ctx *ctx, int K, int num_buckets, int mode, sgpu_kset **out);
+int sgpu_kmers_from_kpomers(sgpu_ctx *ctx, const sgpu_kset *kpomers, int num_buckets, sgpu_kset **out);
+
+int64_t sgpu_kset_size(const sgpu_kset *s);
+int sgpu_kset_k(const sgpu_kset *s);
+int sgpu_kset_num_buckets(const sgpu_kset *s);
+int sgpu_kset_record_bytes(const sgpu_kset *s);                       /* KMerCounter::kmer_size(): 8*ceil(K/32) */
+int sgpu_kset_bucket_sizes(const sgpu_kset *s, int64_t *out);         /* num_buckets entries */
+/* records [first, first+n) of final_kmers order (KMerDiskStorage::merge, kmer_index_builder.hpp:190-203) to host memory */
+int sgpu_kset_download_keys(const sgpu_kset *s, int64_t first, int64_t n, uint64_t *out);
+int sgpu_kset_download_counts(const sgpu_kset *s, int64_t first, int64_t n, uint32_t *out);   /* SGPU_CANONICAL sets only */
+/* writes <prefix>.<b> for every bucket in the reference's bucket file format (raw W-byte records) */
+int sgpu_kset_write_buckets(const sgpu_kset *s, const char *prefix);
+int sgpu_kset_write_final(const sgpu_kset *s, const char *path);      /* final_kmers */
+void sgpu_kset_free(sgpu_kset *s);
+
+int sgpu_mphf_build(sgpu_ctx *ctx, const sgpu_kset *s, sgpu_mphf **out);
+int64_t sgpu_mphf_serialized_size(const sgpu_mphf *m);
+int sgpu_mphf_serialize(const sgpu_mphf *m, uint8_t *out, int64_t cap);
+int sgpu_mphf_lookup(const sgpu_mphf *m, const uint64_t *keys, int64_t n, uint64_t *out_idx);   /* host keys, stored (minimal) form */
+void sgpu_mphf_free(sgpu_mphf *m);
+
+/* kpomers must come from sgpu_count(k+1, B, SGPU_CANONICAL); kmers/kmer_index from sgpu_kmers_from_kpomers / sgpu_mphf_build.
+ * kpomer_index may be NULL (then no coverage: DP/KC are 0 and sgpu_graph_coverage fails). The graph borrows its inputs. */
+int sgpu_graph_build(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *kmers, const sgpu_mphf *kmer_index,
+                     const sgpu_mphf *kpomer_index, int keep_perfect_loops, sgpu_graph **out);
+int sgpu_graph_masks(const sgpu_graph *g, uint8_t *out, int64_t n);           /* n = number of k-mers */
+int sgpu_graph_coverage(const sgpu_graph *g, uint32_t *out, int64_t n);       /* n = number of (k+1)-mers */
+int64_t sgpu_graph_histogram(const sgpu_graph *g, uint64_t *out, int64_t cap);/* returns the histogram length (max coverage) */
+int64_t sgpu_graph_num_unitigs(const sgpu_graph *g);
+int64_t sgpu_graph_unitig_bases(const sgpu_graph *g);
+/* ASCII unitigs concatenated into out (sgpu_graph_unitig_bases() bytes) and their lengths */
+int sgpu_graph_unitigs(const sgpu_graph *g, char *out, uint32_t *lens);
+int64_t sgpu_graph_gfa(const sgpu_graph *g, const char *version, char *out, int64_t cap);   /* returns the text size */
+int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *path);
+void sgpu_graph_free(sgpu_graph *g);
+
+/* self tests of the shared host/device arithmetic (tests only): op 0 = xxh3_64, 1 = xxh3_128 lo, 2 = xxh3_128 hi, 3 = bucket(arg),
+ * 4 = is_minimal, 5.. = rc word j. keys: n records of ceil(K/32) words. on_device != 0 runs the same code in a kernel. */
+int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""ctypes binding of libspades_b200.so (C ABI declared in include/spades_b200.h).
+
+There is NO fallback: if the CUDA library is missing or no GPU is visible the product path raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspades_b200.so")
+
+# every symbol include/spades_b200.h declares (tests check that the library exports exactly these)
+SYMBOLS = [
+    "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_get_times",
+    "sgpu_reads_clear", "sgpu_reads_append_packed", "sgpu_reads_adopt_device",
+    "sgpu_count", "sgpu_kmers_from_kpomers",
+    "sgpu_kset_size", "sgpu_kset_k", "sgpu_kset_num_buckets", "sgpu_kset_record_bytes", "sgpu_kset_bucket_sizes",
+    "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
+    "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
+    "sgpu_graph_build", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
+    "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
+    "sgpu_selftest",
+]
+
+
+class SgpuConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("hbm_budget_bytes", C.c_uint64), ("verbose", C.c_int)]
+
+
+class SgpuTimes(C.Structure):
+    _fields_ = [("extract_count_ms", C.c_float), ("extract_scatter_ms", C.c_float), ("refine_ms", C.c_float),
+                ("local_sort_ms", C.c_float), ("compact_ms", C.c_float), ("mphf_ms", C.c_float),
+                ("instances", C.c_uint64), ("passes", C.c_uint64), ("launches", C.c_uint64), ("peak_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension was not built; there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
+    pp = C.POINTER(vp)
+    L.sgpu_create.restype = i32; L.sgpu_create.argtypes = [C.POINTER(SgpuConfig), pp]
+    L.sgpu_destroy.restype = None; L.sgpu_destroy.argtypes = [vp]
+    L.sgpu_last_error.restype = C.c_char_p; L.sgpu_last_error.argtypes = [vp]
+    L.sgpu_get_times.restype = i32; L.sgpu_get_times.argtypes = [vp, C.POINTER(SgpuTimes)]
+    L.sgpu_reads_clear.restype = i32; L.sgpu_reads_clear.argtypes = [vp]
+    L.sgpu_reads_append_packed.restype = i32; L.sgpu_reads_append_packed.argtypes = [vp, vp, u64, vp, vp, i64]
+    L.sgpu_reads_adopt_device.restype = i32; L.sgpu_reads_adopt_device.argtypes = [vp, vp, u64, vp, vp, i64]
+    L.sgpu_count.restype = i32; L.sgpu_count.argtypes = [vp, i32, i32, i32, pp]
+    L.sgpu_kmers_from_kpomers.restype = i32; L.sgpu_kmers_from_kpomers.argtypes = [vp, vp, i32, pp]
+    L.sgpu_kset_size.restype = i64; L.sgpu_kset_size.argtypes = [vp]
+    L.sgpu_kset_k.restype = i32; L.sgpu_kset_k.argtypes = [vp]
+    L.sgpu_kset_num_buckets.restype = i32; L.sgpu_kset_num_buckets.argtypes = [vp]
+    L.sgpu_kset_record_bytes.restype = i32; L.sgpu_kset_record_bytes.argtypes = [vp]
+    L.sgpu_kset_bucket_sizes.restype = i32; L.sgpu_kset_bucket_sizes.argtypes = [vp, vp]
+    L.sgpu_kset_download_keys.restype = i32; L.sgpu_kset_download_keys.argtypes = [vp, i64, i64, vp]
+    L.sgpu_kset_download_counts.restype = i32; L.sgpu_kset_download_counts.argtypes = [vp, i64, i64, vp]
+    L.sgpu_kset_write_buckets.restype = i32; L.sgpu_kset_write_buckets.argtypes = [vp, C.c_char_p]
+    L.sgpu_kset_write_final.restype = i32; L.sgpu_kset_write_final.argtypes = [vp, C.c_char_p]
+    L.sgpu_kset_free.restype = None; L.sgpu_kset_free.argtypes = [vp]
+    L.sgpu_mphf_build.restype = i32; L.sgpu_mphf_build.argtypes = [vp, vp, pp]
+    L.sgpu_mphf_serialized_size.restype = i64; L.sgpu_mphf_serialized_size.argtypes = [vp]
+    L.sgpu_mphf_serialize.restype = i32; L.sgpu_mphf_serialize.argtypes = [vp, vp, i64]
+    L.sgpu_mphf_lookup.restype = i32; L.sgpu_mphf_lookup.argtypes = [vp, vp, i64, vp]
+    L.sgpu_mphf_free.restype = None; L.sgpu_mphf_free.argtypes = [vp]
+    L.sgpu_graph_build.restype = i32; L.sgpu_graph_build.argtypes = [vp, vp, vp, vp, vp, i32, pp]
+    L.sgpu_graph_masks.restype = i32; L.sgpu_graph_masks.argtypes = [vp, vp, i64]
+    L.sgpu_graph_coverage.restype = i32; L.sgpu_graph_coverage.argtypes = [vp, vp, i64]
+    L.sgpu_graph_histogram.restype = i64; L.sgpu_graph_histogram.argtypes = [vp, vp, i64]
+    L.sgpu_graph_num_unitigs.restype = i64; L.sgpu_graph_num_unitigs.argtypes = [vp]
+    L.sgpu_graph_unitig_bases.restype = i64; L.sgpu_graph_unitig_bases.argtypes = [vp]
+    L.sgpu_graph_unitigs.restype = i32; L.sgpu_graph_unitigs.argtypes = [vp, vp, vp]
+    L.sgpu_graph_gfa.restype = i64; L.sgpu_graph_gfa.argtypes = [vp, C.c_char_p, vp, i64]
+    L.sgpu_graph_write_gfa.restype = i32; L.sgpu_graph_write_gfa.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.sgpu_graph_free.restype = None; L.sgpu_graph_free.argtypes = [vp]
+    L.sgpu_selftest.restype = i32; L.sgpu_selftest.argtypes = [vp, i32, i32, i32, u64, vp, i64, vp]
+    _lib = L
+    return L

@@ -1,0 +1,381 @@
+// api.cu -- the extern "C" boundary (include/spades_b200.h). No exceptions cross it; no CPU fallbacks live behind it.
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/spades_b200.h"
+#include "graph.h"
+#include "sgpu_internal.h"
+
+using namespace sg;
+
+struct sgpu_ctx { Ctx c; };
+struct sgpu_kset { KSet *s; };
+struct sgpu_mphf { Mphf *m; std::vector<uint8_t> ser; bool have_ser = false; };
+struct sgpu_graph { Graph *g; };
+
+static int fail(Ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code ? code : SGPU_EINTERNAL;
+}
+#define API_TRY(ctxptr, ...)                                    \
+    try { __VA_ARGS__; return SGPU_OK; }                           \
+    catch (const sg::Error &e) { return fail((ctxptr), e.code, e.what()); } \
+    catch (const std::bad_alloc &) { return fail((ctxptr), SGPU_ENOMEM, "host allocation failed"); } \
+    catch (const std::exception &e) { return fail((ctxptr), SGPU_EINTERNAL, e.what()); }
+
+extern "C" {
+
+int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out) {
+    if (!out) return SGPU_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return SGPU_ENODEV; }
+    int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) return SGPU_EINVAL;
+    if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return SGPU_ENODEV; }
+    sgpu_ctx *h = new sgpu_ctx();
+    h->c.device = dev;
+    h->c.hbm_budget = cfg ? (size_t)cfg->hbm_budget_bytes : 0;
+    h->c.verbose = cfg ? cfg->verbose : 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError(); delete h; return SGPU_ECUDA;
+    }
+    h->c.num_sms = prop.multiProcessorCount;
+    *out = h;
+    return SGPU_OK;
+}
+
+void sgpu_destroy(sgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
+    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+
+const char *sgpu_last_error(const sgpu_ctx *ctx) { return ctx ? ctx->c.err.c_str() : "no context"; }
+
+int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out) {
+    if (!ctx || !out) return SGPU_EINVAL;
+    const PhaseTimes &t = ctx->c.times;
+    out->extract_count_ms = t.extract_count; out->extract_scatter_ms = t.extract_scatter; out->refine_ms = t.refine;
+    out->local_sort_ms = t.local_sort; out->compact_ms = t.compact; out->mphf_ms = t.mphf;
+    out->instances = t.instances; out->passes = t.passes; out->launches = ctx->c.launches; out->peak_bytes = ctx->c.peak;
+    return SGPU_OK;
+}
+
+int sgpu_reads_clear(sgpu_ctx *ctx) {
+    if (!ctx) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear();
+        c->r_words.release(); c->r_offs.release(); c->r_lens.release();
+        c->d_words = nullptr; c->d_offs = nullptr; c->d_lens = nullptr; c->n_reads = 0; c->n_words = 0; c->staged_dirty = false;
+    })
+}
+
+int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads) {
+    if (!ctx || nreads < 0 || (nreads && (!words || !offs || !lens))) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        const uint64_t base = c->h_words.size();
+        for (int64_t r = 0; r < nreads; ++r) {
+            const uint64_t need = ((uint64_t)lens[r] + 31) / 32;
+            SG_CHECK(offs[r] + need <= nwords, SGPU_EINVAL, "read extends past the word buffer");
+            c->h_offs.push_back(base + offs[r]);
+            c->h_lens.push_back(lens[r]);
+        }
+        c->h_words.insert(c->h_words.end(), words, words + nwords);
+        c->staged_dirty = true;
+    })
+}
+
+int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads) {
+    if (!ctx || nreads < 0) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear(); c->staged_dirty = false;
+        c->r_words.release(); c->r_offs.release(); c->r_lens.release();
+        c->d_words = d_words; c->d_offs = d_offs; c->d_lens = d_lens; c->n_reads = nreads; c->n_words = nwords;
+    })
+}
+
+int sgpu_count(sgpu_ctx *ctx, int K, int num_buckets, int mode, sgpu_kset **out) {
+    if (!ctx || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CHECK(mode == SGPU_CANONICAL || mode == SGPU_ALL_WINDOWS, SGPU_EINVAL, "bad mode");
+        SG_CUDA(cudaSetDevice(c->device));
+        KSet *s = count_from_reads(c, K, num_buckets, mode);
+        *out = new sgpu_kset{s};
+    })
+}
+
+int sgpu_kmers_from_kpomers(sgpu_ctx *ctx, const sgpu_kset *kpomers, int num_buckets, sgpu_kset **out) {
+    if (!ctx || !kpomers || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        KSet *s = kmers_from_kpomers(c, kpomers->s, num_buckets);
+        *out = new sgpu_kset{s};
+    })
+}
+
+int64_t sgpu_kset_size(const sgpu_kset *s) { return s ? s->s->n : -1; }
+int sgpu_kset_k(const sgpu_kset *s) { return s ? s->s->K : -1; }
+int sgpu_kset_num_buckets(const sgpu_kset *s) { return s ? s->s->B : -1; }
+int sgpu_kset_record_bytes(const sgpu_kset *s) { return s ? 8 * s->s->nw : -1; }
+int sgpu_kset_bucket_sizes(const sgpu_kset *s, int64_t *out) {
+    if (!s || !out) return SGPU_EINVAL;
+    for (int b = 0; b < s->s->B; ++b) out[b] = s->s->bsz[b];
+    return SGPU_OK;
+}
+
+}  // extern "C"
+
+template <class T, class Get>
+static void download_range(const KSet *ks, int64_t first, int64_t n, T *out, size_t per, Get get) {
+    SG_CHECK(first >= 0 && n >= 0 && first + n <= ks->n, SGPU_EINVAL, "range outside the k-mer set");
+    Ctx *c = ks->ctx;
+    SG_CUDA(cudaSetDevice(c->device));
+    int64_t done = 0;
+    for (const Chunk &ch : ks->chunks) {
+        const int64_t lo = std::max(first, ch.first), hi = std::min(first + n, ch.first + ch.n);
+        if (lo >= hi) continue;
+        SG_CUDA(cudaMemcpyAsync(out + (size_t)(lo - first) * per, get(ch) + (size_t)(lo - ch.first) * per, (size_t)(hi - lo) * per * sizeof(T),
+                                cudaMemcpyDeviceToHost, c->stream));
+        done += hi - lo;
+    }
+    SG_CUDA(cudaStreamSynchronize(c->stream));
+    SG_CHECK(done == n, SGPU_EINTERNAL, "chunk table does not cover the range");
+}
+
+static void write_range(const KSet *ks, int64_t first, int64_t n, FILE *f) {
+    const size_t W = (size_t)ks->nw;
+    const int64_t step = 1 << 22;
+    std::vector<uint64_t> buf;
+    for (int64_t o = 0; o < n; o += step) {
+        const int64_t m = std::min(step, n - o);
+        buf.resize((size_t)m * W);
+        download_range<uint64_t>(ks, first + o, m, buf.data(), W, [](const Chunk &ch) { return ch.keys.p; });
+        SG_CHECK(fwrite(buf.data(), 8 * W, (size_t)m, f) == (size_t)m, SGPU_EIO, "short write");
+    }
+}
+
+extern "C" {
+
+int sgpu_kset_download_keys(const sgpu_kset *s, int64_t first, int64_t n, uint64_t *out) {
+    if (!s || (n && !out)) return SGPU_EINVAL;
+    Ctx *c = s->s->ctx;
+    API_TRY(c, { download_range<uint64_t>(s->s, first, n, out, (size_t)s->s->nw, [](const Chunk &ch) { return ch.keys.p; }); })
+}
+int sgpu_kset_download_counts(const sgpu_kset *s, int64_t first, int64_t n, uint32_t *out) {
+    if (!s || (n && !out)) return SGPU_EINVAL;
+    Ctx *c = s->s->ctx;
+    API_TRY(c, {
+        SG_CHECK(s->s->has_counts, SGPU_EINVAL, "this k-mer set carries no multiplicities");
+        download_range<uint32_t>(s->s, first, n, out, 1, [](const Chunk &ch) { return ch.counts.p; });
+    })
+}
+
+int sgpu_kset_write_buckets(const sgpu_kset *s, const char *prefix) {
+    if (!s || !prefix) return SGPU_EINVAL;
+    Ctx *c = s->s->ctx;
+    API_TRY(c, {
+        for (int b = 0; b < s->s->B; ++b) {
+            std::string p = std::string(prefix) + "." + std::to_string(b);
+            FILE *f = fopen(p.c_str(), "wb");
+            SG_CHECK(f, SGPU_EIO, "cannot open bucket file for writing");
+            try { write_range(s->s, s->s->bstart[b], s->s->bsz[b], f); } catch (...) { fclose(f); throw; }
+            fclose(f);
+        }
+    })
+}
+int sgpu_kset_write_final(const sgpu_kset *s, const char *path) {
+    if (!s || !path) return SGPU_EINVAL;
+    Ctx *c = s->s->ctx;
+    API_TRY(c, {
+        FILE *f = fopen(path, "wb");
+        SG_CHECK(f, SGPU_EIO, "cannot open final_kmers for writing");
+        try { write_range(s->s, 0, s->s->n, f); } catch (...) { fclose(f); throw; }
+        fclose(f);
+    })
+}
+void sgpu_kset_free(sgpu_kset *s) {
+    if (!s) return;
+    if (s->s) { cudaSetDevice(s->s->ctx->device); delete s->s; }
+    delete s;
+}
+
+int sgpu_mphf_build(sgpu_ctx *ctx, const sgpu_kset *s, sgpu_mphf **out) {
+    if (!ctx || !s || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        Mphf *m = mphf_build(c, s->s);
+        *out = new sgpu_mphf{m, {}, false};
+    })
+}
+static void ensure_ser(sgpu_mphf *m) {
+    if (!m->have_ser) { m->ser = mphf_serialize(m->m); m->have_ser = true; }
+}
+int64_t sgpu_mphf_serialized_size(const sgpu_mphf *m) {
+    if (!m) return -1;
+    try { cudaSetDevice(m->m->ctx->device); ensure_ser(const_cast<sgpu_mphf *>(m)); return (int64_t)m->ser.size(); }
+    catch (const std::exception &e) { m->m->ctx->err = e.what(); return -1; }
+}
+int sgpu_mphf_serialize(const sgpu_mphf *m, uint8_t *out, int64_t cap) {
+    if (!m || !out) return SGPU_EINVAL;
+    Ctx *c = m->m->ctx;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        ensure_ser(const_cast<sgpu_mphf *>(m));
+        SG_CHECK((int64_t)m->ser.size() <= cap, SGPU_EINVAL, "output buffer too small");
+        memcpy(out, m->ser.data(), m->ser.size());
+    })
+}
+int sgpu_mphf_lookup(const sgpu_mphf *m, const uint64_t *keys, int64_t n, uint64_t *out_idx) {
+    if (!m || (n && (!keys || !out_idx))) return SGPU_EINVAL;
+    Ctx *c = m->m->ctx;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); mphf_lookup_host_keys(c, m->m, keys, n, out_idx); })
+}
+void sgpu_mphf_free(sgpu_mphf *m) {
+    if (!m) return;
+    if (m->m) { cudaSetDevice(m->m->ctx->device); delete m->m; }
+    delete m;
+}
+
+int sgpu_graph_build(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *kmers, const sgpu_mphf *kmer_index, const sgpu_mphf *kpomer_index,
+                     int keep_perfect_loops, sgpu_graph **out) {
+    if (!ctx || !kpomers || !kmers || !kmer_index || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0);
+        *out = new sgpu_graph{g};
+    })
+}
+int sgpu_graph_masks(const sgpu_graph *g, uint8_t *out, int64_t n) {
+    if (!g || (n && !out)) return SGPU_EINVAL;
+    Ctx *c = g->g->ctx;
+    API_TRY(c, {
+        SG_CHECK(n == g->g->km->n, SGPU_EINVAL, "mask array size != number of k-mers");
+        SG_CUDA(cudaSetDevice(c->device));
+        if (n) SG_CUDA(cudaMemcpy(out, g->g->masks_final.p, (size_t)n, cudaMemcpyDeviceToHost));
+    })
+}
+int sgpu_graph_coverage(const sgpu_graph *g, uint32_t *out, int64_t n) {
+    if (!g || (n && !out)) return SGPU_EINVAL;
+    Ctx *c = g->g->ctx;
+    API_TRY(c, {
+        SG_CHECK(g->g->cov.p, SGPU_EINVAL, "graph was built without a (k+1)-mer index: no coverage");
+        SG_CHECK(n == g->g->kp->n, SGPU_EINVAL, "coverage array size != number of (k+1)-mers");
+        SG_CUDA(cudaSetDevice(c->device));
+        if (n) SG_CUDA(cudaMemcpy(out, g->g->cov.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    })
+}
+int64_t sgpu_graph_histogram(const sgpu_graph *g, uint64_t *out, int64_t cap) {
+    if (!g) return -1;
+    Ctx *c = g->g->ctx;
+    try {
+        cudaSetDevice(c->device);
+        std::vector<uint64_t> h = graph_histogram(c, g->g);
+        if (out) for (int64_t i = 0; i < (int64_t)h.size() && i < cap; ++i) out[i] = h[i];
+        return (int64_t)h.size();
+    } catch (const std::exception &e) { c->err = e.what(); return -1; }
+}
+int64_t sgpu_graph_num_unitigs(const sgpu_graph *g) { return g ? (int64_t)g->g->edge_len.size() : -1; }
+int64_t sgpu_graph_unitig_bases(const sgpu_graph *g) { return g ? (int64_t)g->g->seq.size() : -1; }
+int sgpu_graph_unitigs(const sgpu_graph *g, char *out, uint32_t *lens) {
+    if (!g) return SGPU_EINVAL;
+    if (out && !g->g->seq.empty()) memcpy(out, g->g->seq.data(), g->g->seq.size());
+    if (lens) for (size_t i = 0; i < g->g->edge_len.size(); ++i) lens[i] = g->g->edge_len[i];
+    return SGPU_OK;
+}
+int64_t sgpu_graph_gfa(const sgpu_graph *g, const char *version, char *out, int64_t cap) {
+    if (!g) return -1;
+    try {
+        std::string t = graph_gfa(g->g, version ? version : "SPAdes-4.3.0-dev");
+        if (out && (int64_t)t.size() <= cap) memcpy(out, t.data(), t.size());
+        return (int64_t)t.size();
+    } catch (const std::exception &e) { g->g->ctx->err = e.what(); return -1; }
+}
+int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *path) {
+    if (!g || !path) return SGPU_EINVAL;
+    Ctx *c = g->g->ctx;
+    API_TRY(c, {
+        std::string t = graph_gfa(g->g, version ? version : "SPAdes-4.3.0-dev");
+        FILE *f = fopen(path, "wb");
+        SG_CHECK(f, SGPU_EIO, "cannot open GFA file for writing");
+        const bool ok = fwrite(t.data(), 1, t.size(), f) == t.size();
+        fclose(f);
+        SG_CHECK(ok, SGPU_EIO, "short write");
+    })
+}
+void sgpu_graph_free(sgpu_graph *g) {
+    if (!g) return;
+    if (g->g) { cudaSetDevice(g->g->ctx->device); delete g->g; }
+    delete g;
+}
+
+}  // extern "C"
+
+// ---- self test of kmer_dev.cuh on host and device -----------------------------------------------------------------------
+template <int NW>
+__host__ __device__ uint64_t selftest_one(int op, int K, uint64_t arg, const uint64_t *key) {
+    Kmer<NW> k;
+    for (int q = 0; q < NW; ++q) k.w[q] = key[q];
+    switch (op) {
+        case 0: return xxh3_64<NW>(k);
+        case 1: return xxh3_128<NW>(k).lo;
+        case 2: return xxh3_128<NW>(k).hi;
+        case 3: return kmer_bucket<NW>(k, (uint32_t)arg);
+        case 4: return kmer_is_minimal<NW>(k, kmer_rc<NW>(k, K)) ? 1 : 0;
+        case 9: return key_bits<NW>(k, K, (int)(arg >> 8), (int)(arg & 255));
+        default: {
+            int j = op - 5;
+            Kmer<NW> r = kmer_rc<NW>(k, K);
+            return j < NW ? r.w[j] : 0;
+        }
+    }
+}
+template <int NW>
+__global__ void selftest_k(int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = selftest_one<NW>(op, K, arg, keys + i * NW);
+}
+template <int NW>
+static void selftest_nw(Ctx *c, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
+    if (!on_device) {
+        for (int64_t i = 0; i < n; ++i) out[i] = selftest_one<NW>(op, K, arg, keys + i * NW);
+        return;
+    }
+    SG_CHECK(c, SGPU_EINVAL, "device self test needs a context");
+    DArr<uint64_t> dk(c, (size_t)n * NW), dout(c, (size_t)n);
+    SG_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * NW * 8, cudaMemcpyHostToDevice, c->stream));
+    selftest_k<NW><<<div_up(n, 256), 256, 0, c->stream>>>(op, K, arg, dk.p, n, dout.p);
+    c->launches++;
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SG_CUDA(cudaStreamSynchronize(c->stream));
+}
+extern "C" int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
+    if (K < 1 || K > 128 || n < 0 || (n && (!keys || !out))) return SGPU_EINVAL;
+    Ctx *c = ctx ? &ctx->c : nullptr;
+    API_TRY(c, {
+        if (on_device) SG_CUDA(cudaSetDevice(c->device));
+        switch (nwords_of(K)) {
+            case 1: selftest_nw<1>(c, on_device, op, K, arg, keys, n, out); break;
+            case 2: selftest_nw<2>(c, on_device, op, K, arg, keys, n, out); break;
+            case 3: selftest_nw<3>(c, on_device, op, K, arg, keys, n, out); break;
+            default: selftest_nw<4>(c, on_device, op, K, arg, keys, n, out); break;
+        }
+    })
+}

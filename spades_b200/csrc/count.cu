@@ -1,0 +1,842 @@
+// count.cu -- k-mer extraction, partition, sort/unique/count. The B200 replacement for
+//   KMerSortingSplitter::Split / DumpBuffers   (src/common/kmer_index/kmer_mph/kmer_splitter.hpp:56-179)
+//   DeBruijnReadKMerSplitter / DeBruijnKMerKMerSplitter (…/kmer_splitters.hpp:28-207)
+//   ParallelSortingSplitter (projects/spades_tools/kmercount.cpp:48-122)
+//   KMerDiskCounter::Count / MergeKMers (…/kmer_index_builder.hpp:306-431)
+// Output per bucket == the reference's kmers.<b> file: strictly increasing W-byte records, order of
+// pdqsort_pod.h:725-734; multiplicities == CoverageHashMapBuilder's second pass (coverage_hash_map_builder.hpp:18-40).
+//
+// Pipeline (all in HBM, see DESIGN.md "count"):
+//   A  level-A partition : records -> (bucket, top rA key bits) partitions. Two kernels over the source with
+//      identical static work assignment: per-CTA histograms, then scatter with CTA-private cursors held in
+//      shared memory (no global atomics; 16-byte stores merge in L2).
+//   B  MSD refinement    : any segment longer than the local-sort capacity is split by its next r key bits by
+//      ONE CTA (histogram + scatter through shared-memory cursors), ping-ponging between two buffers; repeated
+//      until every segment fits or its key bits are exhausted (then all its records are equal).
+//   C  local sort        : one CTA per segment: LSD radix sort in shared memory over the remaining key bits
+//      (optimistic 32-bit window + verification, full range on failure), run-length unique/count, written
+//      back in place; then a compaction copy into the dense bucket-major result.
+#include <algorithm>
+
+#include "sgpu_internal.h"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------------------
+// record sources
+// ------------------------------------------------------------------------------------------------------------
+struct ReadsSrc {
+    const uint64_t *words;
+    const uint64_t *offs;
+    const uint32_t *lens;
+    int64_t n;          // items = reads
+    int K;
+    int both;           // 1: every window emits fwd and rc (spades-kmercount), 0: canonical form once
+    __device__ __forceinline__ uint32_t nrec(int64_t item) const {
+        int L = (int)lens[item];
+        uint32_t w = L >= K ? (uint32_t)(L - K + 1) : 0u;
+        return both ? 2u * w : w;
+    }
+    template <int NW>
+    __device__ __forceinline__ Kmer<NW> get(int64_t item, uint32_t j) const {
+        const uint64_t *s = words + offs[item];
+        uint32_t pos = both ? (j >> 1) : j;
+        Kmer<NW> f = kmer_window<NW>(s, (int64_t)pos, K);
+        Kmer<NW> r = kmer_rc<NW>(f, K);
+        if (both) return (j & 1) ? r : f;
+        return kmer_is_minimal<NW>(f, r) ? f : r;
+    }
+};
+
+// distinct (K+1)-mers -> their two K-mers in canonical form (DeBruijnKMerKMerSplitter with add_rc + IsMinimal filter)
+template <int NWS>
+struct KpomerSrc {
+    const uint64_t *keys;   // NWS words per record
+    int64_t n;
+    int K;                  // target K
+    __device__ __forceinline__ uint32_t nrec(int64_t) const { return 2u; }
+    template <int NW>
+    __device__ __forceinline__ Kmer<NW> get(int64_t item, uint32_t j) const {
+        Kmer<NWS> x;
+#pragma unroll
+        for (int q = 0; q < NWS; ++q) x.w[q] = keys[item * NWS + q];
+        Kmer<NW> f = j ? kmer_suffix<NW, NWS>(x, K) : kmer_prefix<NW, NWS>(x, K);
+        Kmer<NW> r = kmer_rc<NW>(f, K);
+        return kmer_is_minimal<NW>(f, r) ? f : r;
+    }
+};
+
+template <int NW>
+__device__ __forceinline__ void store_rec(uint64_t *dst, const Kmer<NW> &k) {
+    if (NW == 2) {
+        *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(k.w[0], k.w[1]);
+    } else if (NW == 4) {
+        reinterpret_cast<ulonglong2 *>(dst)[0] = make_ulonglong2(k.w[0], k.w[1]);
+        reinterpret_cast<ulonglong2 *>(dst)[1] = make_ulonglong2(k.w[2], k.w[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) dst[q] = k.w[q];
+    }
+}
+template <int NW>
+__device__ __forceinline__ Kmer<NW> load_rec(const uint64_t *src) {
+    Kmer<NW> k;
+    if (NW == 2) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src);
+        k.w[0] = v.x; k.w[1] = v.y;
+    } else if (NW == 4) {
+        ulonglong2 a = reinterpret_cast<const ulonglong2 *>(src)[0], b = reinterpret_cast<const ulonglong2 *>(src)[1];
+        k.w[0] = a.x; k.w[1] = a.y; k.w[2] = b.x; k.w[3] = b.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) k.w[q] = src[q];
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// level A
+// ------------------------------------------------------------------------------------------------------------
+struct LevelA {
+    int K;
+    uint32_t B;
+    uint32_t b_lo, b_hi;    // buckets of this pass
+    int rA;                 // key bits folded into the partition id
+    uint32_t PA;            // (b_hi-b_lo) << rA
+};
+
+static const int kATile = 256;        // items (reads) per tile
+static const int kAThreads = 512;
+
+// tile prologue: per-item record counts -> exclusive prefix in shared memory; returns the tile total
+template <class Src>
+__device__ __forceinline__ uint32_t tile_prefix(const Src &src, int64_t item0, int nitems, uint32_t *pref /*kATile+1*/) {
+    // kAThreads >= kATile: thread t owns item t
+    uint32_t c = 0;
+    if ((int)threadIdx.x < nitems) c = src.nrec(item0 + threadIdx.x);
+    // block scan over the first kATile threads (8 warps)
+    __shared__ uint32_t wsum[kATile / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (warp < kATile / 32 && lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < kATile / 32; ++w) { uint32_t t = wsum[w]; wsum[w] = run; run += t; }
+        wsum[kATile / 32] = run;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < kATile) pref[threadIdx.x] = wsum[warp] + inc - c;
+    uint32_t total = wsum[kATile / 32];
+    if (threadIdx.x == 0) pref[kATile] = total;
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ int find_item(const uint32_t *pref, int nitems, uint32_t i) {
+    // largest t with pref[t] <= i   (pref is exclusive, nitems <= kATile)
+    int lo = 0, hi = nitems - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (pref[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int NW>
+__device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint32_t *part) {
+    uint32_t b = kmer_bucket<NW>(k, p.B);
+    if (b < p.b_lo || b >= p.b_hi) return false;
+    *part = ((b - p.b_lo) << p.rA) | (p.rA ? key_bits<NW>(k, p.K, 0, p.rA) : 0u);
+    return true;
+}
+
+// items are split statically: CTA g owns tiles [g*tiles_per, ...) so that count and scatter agree
+template <int NW, class Src>
+__global__ void __launch_bounds__(kAThreads) levelA_count_k(Src src, LevelA p, uint32_t *__restrict__ blk_counts) {
+    extern __shared__ uint32_t sm_dyn[];
+    uint32_t *hist = sm_dyn;                  // PA
+    __shared__ uint32_t pref[kATile + 1];
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            int it = find_item(pref, nitems, i);
+            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
+            uint32_t part;
+            if (part_of<NW>(p, k, &part)) atomicAdd(&hist[part], 1u);
+        }
+        __syncthreads();
+    }
+    uint32_t *out = blk_counts + (size_t)blockIdx.x * p.PA;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) out[i] += hist[i];
+}
+
+// one thread per partition: totals and per-CTA bases. base[g][part] is the running cursor of CTA g.
+__global__ void levelA_totals_k(const uint32_t *__restrict__ blk_counts, uint32_t PA, int G, uint64_t *__restrict__ part_total) {
+    uint32_t part = blockIdx.x * blockDim.x + threadIdx.x;
+    if (part >= PA) return;
+    uint64_t s = 0;
+    for (int g = 0; g < G; ++g) s += blk_counts[(size_t)g * PA + part];
+    part_total[part] = s;
+}
+__global__ void levelA_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t PA, int G, const uint64_t *__restrict__ part_start,
+                               uint64_t *__restrict__ base) {
+    uint32_t part = blockIdx.x * blockDim.x + threadIdx.x;
+    if (part >= PA) return;
+    uint64_t run = part_start[part];
+    for (int g = 0; g < G; ++g) {
+        base[(size_t)g * PA + part] = run;
+        run += blk_counts[(size_t)g * PA + part];
+    }
+}
+
+template <int NW, class Src>
+__global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out) {
+    extern __shared__ uint32_t sm_dyn[];
+    uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    __shared__ uint32_t pref[kATile + 1];
+    uint64_t *mybase = base + (size_t)blockIdx.x * p.PA;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
+    __syncthreads();
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            int it = find_item(pref, nitems, i);
+            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
+            uint32_t part;
+            if (part_of<NW>(p, k, &part)) {
+                uint32_t slot = atomicAdd(&cnt[part], 1u);
+                store_rec<NW>(out + (cur_base[part] + slot) * NW, k);
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// segments
+// ------------------------------------------------------------------------------------------------------------
+struct Seg {
+    uint64_t start;     // record index in its buffer
+    uint64_t len;
+    uint32_t bits;      // key bits already fixed by partitioning
+    uint32_t bb;        // (bucket << 1) | buffer
+};
+
+__global__ void seg_init_k(const uint64_t *__restrict__ part_start, const uint64_t *__restrict__ part_total, uint32_t PA, int rA,
+                           uint32_t b_lo, Seg *__restrict__ segs) {
+    uint32_t part = blockIdx.x * blockDim.x + threadIdx.x;
+    if (part >= PA) return;
+    Seg s;
+    s.start = part_start[part]; s.len = part_total[part]; s.bits = (uint32_t)rA; s.bb = ((b_lo + (part >> rA)) << 1) | 0u;
+    segs[part] = s;
+}
+
+struct RefinePlan { uint32_t cap, target, rmax; int total_bits; };
+__device__ __forceinline__ int plan_r(const RefinePlan &rp, uint64_t len, uint32_t bits) {
+    if (len <= rp.cap) return 0;
+    int rem = rp.total_bits - (int)bits;
+    if (rem <= 0) return 0;
+    uint64_t want = (len + rp.target - 1) / rp.target;
+    int r = 1;
+    while (r < (int)rp.rmax && (1ull << r) < want) ++r;
+    return r < rem ? r : rem;
+}
+// children[i] = 2^r or 1 ; work flag
+__global__ void refine_plan_k(const Seg *__restrict__ segs, uint64_t n, RefinePlan rp, uint32_t *__restrict__ nchild, uint32_t *__restrict__ isw) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = plan_r(rp, segs[i].len, segs[i].bits);
+    nchild[i] = r ? (1u << r) : 1u;
+    isw[i] = r ? 1u : 0u;
+}
+__global__ void refine_copy_k(const Seg *__restrict__ segs, uint64_t n, const uint32_t *__restrict__ isw, const uint64_t *__restrict__ child_base,
+                              const uint64_t *__restrict__ work_pos, Seg *__restrict__ nsegs, uint64_t *__restrict__ worklist) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (isw[i]) worklist[work_pos[i]] = i;
+    else nsegs[child_base[i]] = segs[i];
+}
+
+static const int kRThreads = 1024;
+static const int kRMaxBins = 2048;
+
+// one CTA splits one oversize segment by its next r key bits: buf[bb&1] -> buf[(bb&1)^1]
+template <int NW>
+__global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ segs, const uint64_t *__restrict__ worklist, uint64_t nwork,
+                                                     const uint64_t *__restrict__ child_base, RefinePlan rp, int K,
+                                                     uint64_t *__restrict__ buf0, uint64_t *__restrict__ buf1, Seg *__restrict__ nsegs,
+                                                     unsigned long long *__restrict__ work_counter) {
+    __shared__ uint32_t hist[kRMaxBins];
+    __shared__ uint32_t warp_tot[kRThreads / 32];
+    __shared__ unsigned long long s_w;
+    for (;;) {
+        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
+        __syncthreads();
+        const uint64_t wi = s_w;
+        __syncthreads();
+        if (wi >= nwork) return;
+        const uint64_t si = worklist[wi];
+        const Seg s = segs[si];
+        const int r = plan_r(rp, s.len, s.bits);
+        const uint32_t nb = 1u << r;
+        const uint64_t *src = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
+        uint64_t *dst = ((s.bb & 1) ? buf0 : buf1) + s.start * NW;
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) {
+            Kmer<NW> k = load_rec<NW>(src + i * NW);
+            atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of hist[0..nb) (nb <= 2048 = 2 per thread)
+        uint32_t a = 0, b = 0;
+        const uint32_t i0 = 2 * threadIdx.x;
+        if (i0 < nb) a = hist[i0];
+        if (i0 + 1 < nb) b = hist[i0 + 1];
+        uint32_t v = a + b, inc = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_tot[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t ex = warp_tot[warp] + inc - v;
+        const uint64_t cb = child_base[si];
+        if (i0 < nb) {
+            Seg c; c.start = s.start + ex; c.len = a; c.bits = s.bits + (uint32_t)r; c.bb = s.bb ^ 1u;
+            nsegs[cb + i0] = c;
+        }
+        if (i0 + 1 < nb) {
+            Seg c; c.start = s.start + ex + a; c.len = b; c.bits = s.bits + (uint32_t)r; c.bb = s.bb ^ 1u;
+            nsegs[cb + i0 + 1] = c;
+        }
+        __syncthreads();
+        if (i0 < nb) hist[i0] = ex;
+        if (i0 + 1 < nb) hist[i0 + 1] = ex + a;
+        __syncthreads();
+        for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) {
+            Kmer<NW> k = load_rec<NW>(src + i * NW);
+            uint32_t slot = atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
+            store_rec<NW>(dst + (uint64_t)slot * NW, k);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// local sort + unique + count
+// ------------------------------------------------------------------------------------------------------------
+template <int NW> struct SortCfg { static const int CAP = NW == 1 ? 4096 : (NW == 2 ? 2048 : 1024); };
+static const int kSThreads = 256;
+static const int kSWarps = kSThreads / 32;
+
+// stable LSD pass over key bits [pos, pos+width) : A -> Bf
+template <int NW>
+__device__ __forceinline__ void lsd_pass(const uint64_t *A, uint64_t *Bf, uint32_t n, int K, int pos, int width, uint32_t *cnt /*[kSWarps][256]*/,
+                                         uint32_t *tot /*[256]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = ((n + kSWarps * 32 - 1) / (kSWarps * 32)) * 32;   // items per warp, multiple of 32
+    const uint32_t w0 = warp * chunk;
+    for (int i = threadIdx.x; i < kSWarps * 256; i += kSThreads) cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t r = 0; r < chunk; r += 32) {
+        const uint32_t i = w0 + r + lane;
+        uint32_t d = 256;
+        if (i < n) d = key_bits<NW>(load_rec<NW>(A + (size_t)i * NW), K, pos, width);
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        if (d < 256 && (int)(__ffs(m) - 1) == lane) cnt[warp * 256 + d] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: warp prefix + digit totals
+    {
+        const uint32_t d = threadIdx.x;     // kSThreads == 256 digits
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kSWarps; ++w) { uint32_t t = cnt[w * 256 + d]; cnt[w * 256 + d] = run; run += t; }
+        // exclusive scan of run over 256 digits
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) tot[warp] = inc;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += tot[w];
+        __syncthreads();
+        const uint32_t ex = wb + inc - run;
+#pragma unroll
+        for (int w = 0; w < kSWarps; ++w) cnt[w * 256 + d] += ex;
+    }
+    __syncthreads();
+    for (uint32_t r = 0; r < chunk; r += 32) {
+        const uint32_t i = w0 + r + lane;
+        uint32_t d = 256;
+        Kmer<NW> k;
+        if (i < n) { k = load_rec<NW>(A + (size_t)i * NW); d = key_bits<NW>(k, K, pos, width); }
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        uint32_t rank = 0;
+        if (d < 256) rank = cnt[warp * 256 + d] + __popc(m & ((1u << lane) - 1));
+        __syncwarp();
+        if (d < 256) {
+            store_rec<NW>(Bf + (size_t)rank * NW, k);
+            if ((int)(__ffs(m) - 1) == lane) cnt[warp * 256 + d] += __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// sort A[0..n) by key bits [lo, hi) (MSB-first positions). Result may end up in A or Bf; returns pointer.
+template <int NW>
+__device__ __forceinline__ uint64_t *lsd_sort_range(uint64_t *A, uint64_t *Bf, uint32_t n, int K, int lo, int hi, uint32_t *cnt, uint32_t *tot) {
+    int p = hi;
+    while (p > lo) {
+        int w = p - lo >= 8 ? 8 : p - lo;
+        lsd_pass<NW>(A, Bf, n, K, p - w, w, cnt, tot);
+        uint64_t *t = A; A = Bf; Bf = t;
+        p -= w;
+    }
+    return A;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kSThreads) local_sort_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
+                                                         uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
+                                                         unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
+    constexpr int CAP = SortCfg<NW>::CAP;
+    extern __shared__ uint64_t sm64[];
+    uint64_t *A = sm64;                         // CAP*NW
+    uint64_t *Bf = sm64 + (size_t)CAP * NW;     // CAP*NW
+    __shared__ uint32_t cnt[kSWarps * 256];
+    __shared__ uint32_t tot[kSWarps + 1];
+    __shared__ uint32_t heads[CAP + 1];
+    __shared__ unsigned long long s_w;
+    __shared__ int s_flag;
+    const int total_bits = 2 * K;
+    for (;;) {
+        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
+        __syncthreads();
+        const uint64_t si = s_w;
+        __syncthreads();
+        if (si >= nsegs) return;
+        const Seg s = segs[si];
+        uint64_t *gsrc = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
+        uint32_t *gcnt = reinterpret_cast<uint32_t *>(((s.bb & 1) ? buf0 : buf1) + s.start * NW);   // counts live in the partner buffer
+        if (s.len == 0) { if (threadIdx.x == 0) ndist[si] = 0; continue; }
+        if (s.len > (uint64_t)CAP) {
+            // only possible when every key bit is fixed: all records are equal
+            if (threadIdx.x == 0) { gcnt[0] = (uint32_t)s.len; ndist[si] = 1; if (s.bits < (uint32_t)total_bits) atomicAdd(&stats[0], 1ull); }
+            continue;
+        }
+        const uint32_t n = (uint32_t)s.len;
+        for (uint32_t i = threadIdx.x; i < n * NW; i += kSThreads) A[i] = gsrc[i];
+        __syncthreads();
+        uint64_t *S = A;
+        const int lo = (int)s.bits;
+        if (n > 1 && lo < total_bits) {
+            const int hi1 = lo + 32 < total_bits ? lo + 32 : total_bits;
+            S = lsd_sort_range<NW>(A, Bf, n, K, lo, hi1, cnt, tot);
+            if (hi1 < total_bits) {
+                // verify full order; the 32-bit window almost always decides it
+                if (threadIdx.x == 0) s_flag = 0;
+                __syncthreads();
+                int bad = 0;
+                for (uint32_t i = threadIdx.x + 1; i < n; i += kSThreads)
+                    if (kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) > 0) bad = 1;
+                if (bad) s_flag = 1;
+                __syncthreads();
+                if (s_flag) {
+                    if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
+                    uint64_t *O = (S == A) ? Bf : A;
+                    S = lsd_sort_range<NW>(S, O, n, K, lo, total_bits, cnt, tot);
+                }
+            }
+        }
+        // run-length unique: heads[j] = position of the j-th distinct key
+        // each thread owns a contiguous slice so distinct indices come out in order
+        const uint32_t per = (n + kSThreads - 1) / kSThreads;
+        const uint32_t i0 = threadIdx.x * per, i1 = min(n, i0 + per);
+        uint32_t nh = 0;
+        for (uint32_t i = i0; i < i1; ++i)
+            if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) ++nh;
+        // block exclusive scan of nh
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            uint32_t inc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) tot[warp] = inc;
+            __syncthreads();
+            uint32_t wb = 0, all = 0;
+            for (int w = 0; w < kSWarps; ++w) { if (w < warp) wb += tot[w]; all += tot[w]; }
+            uint32_t j = wb + inc - nh;
+            for (uint32_t i = i0; i < i1; ++i)
+                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) heads[j++] = i;
+            if (threadIdx.x == 0) { heads[all] = n; ndist[si] = all; }
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; q < all; q += kSThreads) {
+                const uint32_t h = heads[q];
+                store_rec<NW>(gsrc + (size_t)q * NW, load_rec<NW>(S + (size_t)h * NW));
+                gcnt[q] = heads[q + 1] - h;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// compaction: one warp per segment copies its distinct records / counts to the dense output
+template <int NW>
+__global__ void compact_k(const Seg *__restrict__ segs, uint64_t nsegs, const uint32_t *__restrict__ ndist, const uint64_t *__restrict__ dbase,
+                          const uint64_t *__restrict__ buf0, const uint64_t *__restrict__ buf1, int K, int want_counts, int double_selfrc,
+                          uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_counts, unsigned long long *__restrict__ bucket_sizes) {
+    const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= nsegs) return;
+    const Seg s = segs[wid];
+    const uint32_t nd = ndist[wid];
+    if (nd == 0) return;
+    const uint64_t *src = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
+    const uint32_t *csrc = reinterpret_cast<const uint32_t *>(((s.bb & 1) ? buf0 : buf1) + s.start * NW);
+    const uint64_t ob = dbase[wid];
+    for (uint32_t q = lane; q < nd; q += 32) {
+        Kmer<NW> k = load_rec<NW>(src + (size_t)q * NW);
+        store_rec<NW>(out_keys + (ob + q) * NW, k);
+        if (want_counts) {
+            uint32_t c = csrc[q];
+            if (double_selfrc && kmer_eq<NW>(k, kmer_rc<NW>(k, K))) c *= 2u;   // a self-RC (k+1)-mer is seen in the read and in its RC
+            out_counts[ob + q] = c;
+        }
+    }
+    if (lane == 0) atomicAdd(&bucket_sizes[s.bb >> 1], (unsigned long long)nd);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------------------
+struct Timer {
+    cudaEvent_t a, b; cudaStream_t s;
+    Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+static int ilog2_floor(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
+
+template <int NW, class Src>
+static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
+                             KSet *out) {
+    constexpr int CAP = SortCfg<NW>::CAP;
+    const uint32_t TARGET = CAP * 3 / 8;
+    const int total_bits = 2 * K;
+    const int G = ctx->num_sms * 2;
+    const uint32_t PA_MAX = 4096;
+    const size_t W = 8 * NW;
+    cudaStream_t st = ctx->stream;
+    Timer tm(st);
+
+    out->bsz.assign(B, 0);
+    DArr<unsigned long long> d_bsz(ctx, B);
+    SG_CUDA(cudaMemsetAsync(d_bsz.p, 0, B * sizeof(unsigned long long), st));
+
+    // pass planning: records of a pass must fit twice (ping-pong) next to what is already resident
+    size_t free_b = 0, total_b = 0;
+    SG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = ctx->hbm_budget ? ctx->hbm_budget : (size_t)(free_b * 0.90);
+    int npass = 1;
+    {
+        // results (distinct keys + counts) accumulate; assume <= 60% of the instances stay (refined per pass below)
+        double per_pass = 2.0 * (double)est_records * W;
+        double avail = (double)budget * 0.55;
+        if (per_pass > avail) npass = (int)(per_pass / avail) + 1;
+        if (npass > B) npass = B;
+    }
+    std::vector<std::pair<int, int>> todo;     // bucket ranges, processed in order
+    for (int p = 0; p < npass; ++p) {
+        int lo = (int)((int64_t)B * p / npass), hi = (int)((int64_t)B * (p + 1) / npass);
+        if (hi > lo) todo.push_back({lo, hi});
+    }
+    int64_t first = 0;
+    size_t ti = 0;
+    while (ti < todo.size()) {
+        const int b_lo = todo[ti].first, b_hi = todo[ti].second;
+        const uint32_t nb = (uint32_t)(b_hi - b_lo);
+        LevelA pa;
+        pa.K = K; pa.B = (uint32_t)B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi;
+        // rA: enough level-A partitions that level-A segments are small multiples of the local capacity,
+        // bounded by shared memory (PA_MAX) and by the key length
+        {
+            uint64_t est_pass = est_records * nb / (uint64_t)B + 1;
+            int want = ilog2_floor(est_pass / TARGET + 1) + 1;              // total fan-out bits wanted
+            int bbits = ilog2_floor(nb) + (((1u << ilog2_floor(nb)) < nb) ? 1 : 0);
+            int rA = want - bbits;
+            if (rA < 0) rA = 0;
+            while (rA > 0 && ((uint64_t)nb << rA) > PA_MAX) --rA;
+            if (rA > total_bits) rA = total_bits;
+            if (rA > 24) rA = 24;
+            pa.rA = rA;
+            pa.PA = nb << rA;
+        }
+        if (pa.PA > 8192) {   // too many buckets for one pass's shared-memory histogram: split the range
+            int mid = b_lo + (b_hi - b_lo) / 2;
+            todo[ti] = {b_lo, mid};
+            todo.insert(todo.begin() + ti + 1, {mid, b_hi});
+            continue;
+        }
+        const uint32_t PA = pa.PA;
+        // ---- A1: count
+        DArr<uint32_t> blk_counts(ctx, (size_t)G * PA);
+        SG_CUDA(cudaMemsetAsync(blk_counts.p, 0, blk_counts.bytes(), st));
+        tm.start();
+        for (const Src &src : srcs) {
+            if (src.n == 0) continue;
+            levelA_count_k<NW, Src><<<G, kAThreads, PA * sizeof(uint32_t), st>>>(src, pa, blk_counts.p);
+            ctx->launches++;
+        }
+        SG_CUDA(cudaGetLastError());
+        DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1);
+        levelA_totals_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p, PA, G, part_total.p);
+        ctx->launches++;
+        SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
+        exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
+        uint64_t I = 0;
+        SG_CUDA(cudaMemcpyAsync(&I, part_start.p + PA, 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        ctx->times.extract_count += tm.stop();
+        // does the pass fit?  X + Y + (worst case) all-distinct output
+        {
+            SG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t lim = ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(free_b * 0.92);
+            double need = (double)I * W * 2.0 + (double)I * (W + 4) * 0.6 + (64 << 20);
+            if (need > (double)lim && nb > 1) {
+                int mid = b_lo + (b_hi - b_lo) / 2;
+                todo[ti] = {b_lo, mid};
+                todo.insert(todo.begin() + ti + 1, {mid, b_hi});
+                continue;
+            }
+        }
+        ctx->times.passes++;
+        ctx->times.instances += I;
+        // ---- A2: scatter
+        DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
+        {
+            DArr<uint64_t> base(ctx, (size_t)G * PA);
+            levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p, PA, G, part_start.p, base.p);
+            ctx->launches++;
+            tm.start();
+            size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (const Src &src : srcs) {
+                if (src.n == 0) continue;
+                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p);
+                ctx->launches++;
+            }
+            SG_CUDA(cudaGetLastError());
+            ctx->times.extract_scatter += tm.stop();
+        }
+        blk_counts.release();
+        // ---- segments + refinement rounds
+        uint64_t nsegs = PA;
+        DArr<Seg> segs(ctx, nsegs);
+        seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start.p, part_total.p, PA, pa.rA, (uint32_t)b_lo, segs.p);
+        ctx->launches++;
+        RefinePlan rp; rp.cap = CAP; rp.target = TARGET; rp.rmax = 11; rp.total_bits = total_bits;
+        DArr<unsigned long long> wcounter(ctx, 4);
+        tm.start();
+        for (int round = 0; round < 300; ++round) {
+            DArr<uint32_t> nchild(ctx, nsegs + 1), isw(ctx, nsegs + 1);
+            DArr<uint64_t> cbase(ctx, nsegs + 1), wpos(ctx, nsegs + 1);
+            SG_CUDA(cudaMemsetAsync(nchild.p + nsegs, 0, 4, st));
+            SG_CUDA(cudaMemsetAsync(isw.p + nsegs, 0, 4, st));
+            refine_plan_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, rp, nchild.p, isw.p);
+            ctx->launches++;
+            exclusive_scan_u32_to_u64(ctx, nchild.p, cbase.p, nsegs + 1);
+            exclusive_scan_u32_to_u64(ctx, isw.p, wpos.p, nsegs + 1);
+            uint64_t tot[2];
+            SG_CUDA(cudaMemcpyAsync(&tot[0], cbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(&tot[1], wpos.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            if (tot[1] == 0) break;
+            DArr<Seg> nsegs_arr(ctx, tot[0]);
+            DArr<uint64_t> worklist(ctx, tot[1]);
+            refine_copy_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, isw.p, cbase.p, wpos.p, nsegs_arr.p, worklist.p);
+            ctx->launches++;
+            SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
+            int grid = (int)std::min<uint64_t>(tot[1], (uint64_t)ctx->num_sms * 2);
+            refine_k<NW><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p);
+            ctx->launches++;
+            SG_CUDA(cudaGetLastError());
+            SG_CUDA(cudaStreamSynchronize(st));
+            segs = std::move(nsegs_arr);
+            nsegs = tot[0];
+        }
+        ctx->times.refine += tm.stop();
+        // ---- local sort
+        DArr<uint32_t> ndist(ctx, nsegs + 1);
+        DArr<unsigned long long> stats(ctx, 4);
+        SG_CUDA(cudaMemsetAsync(ndist.p, 0, ndist.bytes(), st));
+        SG_CUDA(cudaMemsetAsync(stats.p, 0, 32, st));
+        SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
+        tm.start();
+        {
+            size_t smem = (size_t)2 * CAP * NW * sizeof(uint64_t);
+            SG_CUDA(cudaFuncSetAttribute(local_sort_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, local_sort_k<NW>, kSThreads, smem));
+            if (occ < 1) occ = 1;
+            int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
+            if (grid < 1) grid = 1;
+            local_sort_k<NW><<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+            ctx->launches++;
+            SG_CUDA(cudaGetLastError());
+        }
+        DArr<uint64_t> dbase(ctx, nsegs + 1);
+        exclusive_scan_u32_to_u64(ctx, ndist.p, dbase.p, nsegs + 1);
+        uint64_t D = 0;
+        unsigned long long h_stats[4];
+        SG_CUDA(cudaMemcpyAsync(&D, dbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(h_stats, stats.p, 32, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        ctx->times.local_sort += tm.stop();
+        SG_CHECK(h_stats[0] == 0, 6, "internal: oversize segment with unfixed key bits reached the local sort");
+        // ---- compaction into the dense chunk
+        Chunk ch;
+        ch.n = (int64_t)D; ch.b_lo = b_lo; ch.b_hi = b_hi; ch.first = first;
+        ch.keys.alloc(ctx, (size_t)D * NW + 2);
+        if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1);
+        tm.start();
+        if (nsegs) {
+            compact_k<NW><<<div_up((int64_t)nsegs * 32, 256), 256, 0, st>>>(segs.p, nsegs, ndist.p, dbase.p, X.p, Y.p, K, want_counts ? 1 : 0,
+                                                                         double_selfrc ? 1 : 0, ch.keys.p, ch.counts.p, d_bsz.p);
+            ctx->launches++;
+            SG_CUDA(cudaGetLastError());
+        }
+        ctx->times.compact += tm.stop();
+        first += (int64_t)D;
+        out->chunks.push_back(std::move(ch));
+        ++ti;
+    }
+    std::vector<unsigned long long> hb(B);
+    SG_CUDA(cudaMemcpyAsync(hb.data(), d_bsz.p, B * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    out->bstart.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) { out->bsz[b] = (int64_t)hb[b]; out->bstart[b + 1] = out->bstart[b] + out->bsz[b]; }
+    out->n = first;
+    SG_CHECK(out->bstart[B] == out->n, 6, "internal: bucket sizes do not add up");
+}
+
+__global__ void count_windows_k(const uint32_t *__restrict__ lens, int64_t n, int K, unsigned long long *__restrict__ out) {
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int L = (int)lens[i];
+        if (L >= K) s += (unsigned long long)(L - K + 1);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+template <int NW>
+static KSet *count_reads_nw(Ctx *ctx, int K, int B, int mode) {
+    ensure_reads_on_device(ctx);
+    KSet *ks = new KSet();
+    ks->ctx = ctx; ks->K = K; ks->nw = NW; ks->B = B; ks->has_counts = (mode == kCanonical);
+    try {
+        DArr<unsigned long long> d_w(ctx, 1);
+        SG_CUDA(cudaMemsetAsync(d_w.p, 0, 8, ctx->stream));
+        if (ctx->n_reads) {
+            count_windows_k<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_lens, ctx->n_reads, K, d_w.p);
+            ctx->launches++;
+        }
+        unsigned long long wn = 0;
+        SG_CUDA(cudaMemcpyAsync(&wn, d_w.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ReadsSrc src;
+        src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = (mode == kAllWindows);
+        std::vector<ReadsSrc> srcs{src};
+        run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), (uint64_t)wn * (mode == kAllWindows ? 2 : 1), ks);
+    } catch (...) { delete ks; throw; }
+    return ks;
+}
+
+KSet *count_from_reads(Ctx *ctx, int K, int B, int mode) {
+    SG_CHECK(K >= 1 && K <= 128, 2, "K must be in [1,128]");
+    SG_CHECK(B >= 1 && B <= (1 << 20), 2, "num_buckets must be in [1, 2^20]");
+    ctx->times = PhaseTimes();
+    switch (nwords_of(K)) {
+        case 1: return count_reads_nw<1>(ctx, K, B, mode);
+        case 2: return count_reads_nw<2>(ctx, K, B, mode);
+        case 3: return count_reads_nw<3>(ctx, K, B, mode);
+        default: return count_reads_nw<4>(ctx, K, B, mode);
+    }
+}
+
+template <int NW, int NWS>
+static KSet *kmers_from_kpomers_nw(Ctx *ctx, const KSet *kp, int B) {
+    const int K = kp->K - 1;
+    KSet *ks = new KSet();
+    ks->ctx = ctx; ks->K = K; ks->nw = NW; ks->B = B; ks->has_counts = false;
+    try {
+        std::vector<KpomerSrc<NWS>> srcs;
+        for (const Chunk &c : kp->chunks) {
+            KpomerSrc<NWS> s; s.keys = c.keys.p; s.n = c.n; s.K = K;
+            srcs.push_back(s);
+        }
+        run_count_chunks<NW, KpomerSrc<NWS>>(ctx, srcs, K, B, false, false, (uint64_t)kp->n * 2, ks);
+    } catch (...) { delete ks; throw; }
+    return ks;
+}
+
+KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B) {
+    SG_CHECK(kp->K >= 2, 2, "source k-mers too short");
+    const int K = kp->K - 1;
+    const int nw = nwords_of(K), nws = kp->nw;
+    ctx->times = PhaseTimes();
+    if (nw == 1 && nws == 1) return kmers_from_kpomers_nw<1, 1>(ctx, kp, B);
+    if (nw == 1 && nws == 2) return kmers_from_kpomers_nw<1, 2>(ctx, kp, B);
+    if (nw == 2 && nws == 2) return kmers_from_kpomers_nw<2, 2>(ctx, kp, B);
+    if (nw == 2 && nws == 3) return kmers_from_kpomers_nw<2, 3>(ctx, kp, B);
+    if (nw == 3 && nws == 3) return kmers_from_kpomers_nw<3, 3>(ctx, kp, B);
+    if (nw == 3 && nws == 4) return kmers_from_kpomers_nw<3, 4>(ctx, kp, B);
+    if (nw == 4 && nws == 4) return kmers_from_kpomers_nw<4, 4>(ctx, kp, B);
+    throw Error(2, "unsupported k-mer word combination");
+}
+
+}  // namespace sg

@@ -1,0 +1,94 @@
+"""Host-side mirror of the reference's graph-construction interface over the C ABI.
+
+  DeBruijnExtensionIndexBuilder.BuildExtensionIndexFromStream / FromKPOMers
+        src/common/kmer_index/extension_index/kmer_extension_index_builder.hpp:63-107
+  UnbranchingPathExtractor.ExtractUnbranchingPathsAndLoops, FastGraphFromSequencesConstructor.ConstructGraph
+        src/common/assembly_graph/construction/debruijn_graph_constructor.hpp:399-406,506-567
+  CoverageHashMapBuilder / PHMCoverageFiller histogram   ph_map/coverage_hash_map_builder.hpp:42-56, stages/construction.cpp:404-418
+  gfa::GFAWriter                                            io/graph/gfa_writer.cpp:36-116
+"""
+import ctypes as C
+
+import numpy as np
+
+from .kmer_index import (Context, DeBruijnKMerKMerSplitter, DeBruijnReadKMerSplitter, KMerDiskCounter, KMerIndexBuilder, SpadesGpuError, _p)
+
+
+class DeBruijnGraph:
+    """masks + coverage + unitigs + links of the condensed graph."""
+
+    def __init__(self, ctx, h, kpomers, kmers, kmer_index, kpomer_index):
+        self.ctx, self.h = ctx, h
+        self.kpomers, self.kmers, self.kmer_index, self.kpomer_index = kpomers, kmers, kmer_index, kpomer_index
+
+    def masks(self):
+        n = self.kmers.total_kmers()
+        out = np.zeros(max(n, 1), np.uint8)
+        self.ctx.check(self.ctx.L.sgpu_graph_masks(self.h, _p(out), n))
+        return out[:n]
+
+    def coverage(self):
+        n = self.kpomers.total_kmers()
+        out = np.zeros(max(n, 1), np.uint32)
+        self.ctx.check(self.ctx.L.sgpu_graph_coverage(self.h, _p(out), n))
+        return out[:n]
+
+    def histogram(self):
+        n = self.ctx.L.sgpu_graph_histogram(self.h, None, 0)
+        if n < 0:
+            raise SpadesGpuError(self.ctx.L.sgpu_last_error(self.ctx.h).decode())
+        out = np.zeros(max(n, 1), np.uint64)
+        self.ctx.L.sgpu_graph_histogram(self.h, _p(out), n)
+        return out[:n]
+
+    def unitigs(self):
+        ne = self.ctx.L.sgpu_graph_num_unitigs(self.h)
+        nb = self.ctx.L.sgpu_graph_unitig_bases(self.h)
+        buf = np.zeros(max(nb, 1), np.uint8); lens = np.zeros(max(ne, 1), np.uint32)
+        self.ctx.check(self.ctx.L.sgpu_graph_unitigs(self.h, _p(buf), _p(lens)))
+        s = buf[:nb].tobytes().decode()
+        out, o = [], 0
+        for l in lens[:ne]:
+            out.append(s[o:o + int(l)]); o += int(l)
+        return out
+
+    def gfa(self, version="SPAdes-4.3.0-dev"):
+        n = self.ctx.L.sgpu_graph_gfa(self.h, version.encode(), None, 0)
+        if n < 0:
+            raise SpadesGpuError(self.ctx.L.sgpu_last_error(self.ctx.h).decode())
+        buf = np.zeros(max(n, 1), np.uint8)
+        self.ctx.L.sgpu_graph_gfa(self.h, version.encode(), _p(buf), n)
+        return buf[:n].tobytes().decode()
+
+    def write_gfa(self, path, version="SPAdes-4.3.0-dev"):
+        self.ctx.check(self.ctx.L.sgpu_graph_write_gfa(self.h, version.encode(), str(path).encode()))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.sgpu_graph_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeBruijnGraphConstructor:
+    """spades-gbuilder's sequence: (k+1)-mers -> k-mers -> MPHFs -> masks -> unitigs (+loops) -> graph (+coverage)."""
+
+    def __init__(self, ctx: Context, k: int, num_buckets: int):
+        if k % 2 == 0:
+            raise ValueError("k-mer size must be odd")   # projects/spades_tools/gbuilder.cpp:125
+        self.ctx, self.k, self.B = ctx, k, num_buckets
+
+    def ConstructGraph(self, keep_perfect_loops=True, with_coverage=True) -> DeBruijnGraph:
+        ctx, k, B = self.ctx, self.k, self.B
+        kpomers = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(k + 1)).Count(B)
+        kmers = KMerDiskCounter(ctx, DeBruijnKMerKMerSplitter(k, kpomers)).Count(B)
+        kmer_index = KMerIndexBuilder(ctx).BuildIndex(kmers)
+        kpomer_index = KMerIndexBuilder(ctx).BuildIndex(kpomers) if with_coverage else None
+        h = C.c_void_p()
+        ctx.check(ctx.L.sgpu_graph_build(ctx.h, kpomers.h, kmers.h, kmer_index.h, kpomer_index.h if kpomer_index else None,
+                                         1 if keep_perfect_loops else 0, C.byref(h)))
+        return DeBruijnGraph(ctx, h, kpomers, kmers, kmer_index, kpomer_index)

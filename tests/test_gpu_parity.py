@@ -1,0 +1,154 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI (spades_b200/_lib.py);
+the checker is the reference's golden output (tests/golden) or the C oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle as O
+from spades_b200.packing import pack_reads, revcomp, synthetic_reads
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_art(reads, k, B):
+    r = O.full_graph(reads, k, B)
+    return dict(kpomers=r["kp"].keys, kp_bsz=r["kp"].bsz, kmers=r["km"].keys, kmer_index=r["mk"].serialize(),
+                kpomer_index=r["mkp"].serialize(), masks=r["masks"], cov=r["cov"], hist=r["hist"].astype(np.int64),
+                unitigs=r["unitigs"].seqs, gfa=r["gfa"], kp_counts=r["kp"].counts)
+
+
+def _compare(a, b, B):
+    bad = []
+    for key in ("kpomers", "kp_bsz", "kmers", "masks", "cov", "hist", "kp_counts"):
+        if not np.array_equal(np.asarray(a[key]).ravel(), np.asarray(b[key]).ravel()):
+            bad.append(key)
+    for key in ("kmer_index", "kpomer_index"):
+        if not G.index_equal(a[key], b[key], B):
+            bad.append(key)
+    if list(a["unitigs"]) != list(b["unitigs"]):
+        bad.append("unitigs")
+    if a["gfa"] != b["gfa"]:
+        bad.append("gfa")
+    return bad
+
+
+def test_device_arithmetic():
+    from gpu_util import ctx
+    from test_hostdev_helpers import check_all
+    check_all(ctx().h, 1)
+
+
+@pytest.mark.parametrize("name", G.names("graph"))
+def test_graph_matches_reference_golden(name):
+    from gpu_util import gpu_graph_artifacts
+    g = G.load(name)
+    art, _ = gpu_graph_artifacts(g["reads"], g["k"], g["B"])
+    assert G.check_graph(g, art) == []
+
+
+@pytest.mark.parametrize("name", G.names("count"))
+def test_kmercount_matches_reference_golden(name):
+    from gpu_util import gpu_count_artifacts
+    g = G.load(name)
+    art, _ = gpu_count_artifacts(g["reads"], g["k"], g["B"])
+    assert G.check_count(g, art) == []
+
+
+@pytest.mark.parametrize("k,B,n,L,glen,seed", [
+    (21, 16, 3000, 100, 4000, 1), (31, 7, 2000, 150, 3000, 2), (33, 40, 2000, 150, 3000, 3), (55, 80, 3000, 150, 5000, 4),
+    (63, 5, 1500, 150, 2000, 5), (65, 9, 1500, 150, 2000, 6), (77, 3, 1500, 150, 2000, 7), (99, 11, 1200, 150, 2000, 8),
+    (127, 2, 1000, 150, 1500, 9), (5, 4, 400, 60, 300, 10), (3, 1, 200, 40, 100, 11),
+])
+def test_graph_matches_oracle_random(k, B, n, L, glen, seed):
+    from gpu_util import gpu_graph_artifacts
+    reads = synthetic_reads(n, L, glen, 0.01, seed=seed)
+    art, _ = gpu_graph_artifacts(reads, k, B)
+    assert _compare(art, _oracle_art(reads, k, B), B) == []
+
+
+def test_ragged_empty_and_short_reads():
+    from gpu_util import gpu_graph_artifacts
+    rng = np.random.default_rng(3)
+    base = synthetic_reads(600, 150, 1500, 0.01, seed=12)
+    reads = []
+    for i, r in enumerate(base):
+        cut = int(rng.integers(1, 150))
+        reads.append(r[:cut])                      # lengths 1..149, many shorter than k+1 (skipped, kmer_splitters.hpp:30-31)
+    reads += ["A", "ACGT", "ACGTACGTACGTACGTACGTACGT"]
+    art, _ = gpu_graph_artifacts(reads, 21, 6)
+    assert _compare(art, _oracle_art(reads, 21, 6), 6) == []
+
+
+def test_no_kmers_at_all():
+    from gpu_util import gpu_graph_artifacts
+    reads = ["ACGT", "AC", "GGGTTT"]
+    art, _ = gpu_graph_artifacts(reads, 21, 4)
+    assert art["kpomers"].size == 0 and art["kmers"].size == 0 and art["unitigs"] == []
+    assert _compare(art, _oracle_art(reads, 21, 4), 4) == []
+
+
+def test_heavy_hitters_and_low_complexity():
+    """the same read thousands of times (segments of identical keys larger than the local-sort capacity), poly-A,
+    tandem repeats (long shared key prefixes -> the 32-bit optimistic sort window must fall back)."""
+    from gpu_util import gpu_graph_artifacts
+    one = synthetic_reads(1, 150, 400, 0.0, seed=21)[0]
+    reads = [one] * 5000 + ["A" * 150] * 3000 + ["AC" * 75] * 100 + ["ACGTTGCA" * 18 + "ACGTTG"] * 50
+    reads += synthetic_reads(500, 150, 800, 0.01, seed=22)
+    for k, B in ((21, 3), (55, 2)):
+        art, _ = gpu_graph_artifacts(reads, k, B)
+        assert _compare(art, _oracle_art(reads, k, B), B) == []
+
+
+def test_perfect_loops_and_hairpin_loop():
+    from gpu_util import gpu_graph_artifacts
+    rng = np.random.default_rng(5)
+    g = "".join("ACGT"[i] for i in rng.integers(0, 4, 700))
+    gg = g + g
+    reads = [gg[i:i + 120] for i in range(0, 700, 7)]
+    x = "".join("ACGT"[i] for i in rng.integers(0, 4, 200))
+    h = x + revcomp(x)
+    hh = h + h
+    reads += [hh[i:i + 150] for i in range(0, 400, 5)]
+    for k, B in ((21, 4), (33, 2)):
+        art, _ = gpu_graph_artifacts(reads, k, B)
+        assert _compare(art, _oracle_art(reads, k, B), B) == []
+
+
+@pytest.mark.parametrize("K,B,seed", [(21, 16, 31), (32, 3, 32), (55, 16, 33), (64, 5, 34), (96, 4, 35), (128, 2, 36)])
+def test_kmercount_matches_oracle_random(K, B, seed):
+    from gpu_util import gpu_count_artifacts
+    reads = synthetic_reads(1500, 150, 2500, 0.01, seed=seed)
+    art, _ = gpu_count_artifacts(reads, K, B)
+    words, offs, lens = pack_reads(reads)
+    ks = O.count(words, offs, lens, K, B, 1)
+    assert np.array_equal(art["final_kmers"].ravel(), ks.keys.ravel()) and np.array_equal(art["bsz"], ks.bsz)
+
+
+def test_medium_size_properties_and_oracle():
+    """60 k reads x 150 bp, k=55 (5.7 M windows): exercises level-A fan-out + MSD refinement at non-toy sizes."""
+    from gpu_util import ctx
+    from spades_b200.kmer_index import DeBruijnReadKMerSplitter, KMerDiskCounter, KMerIndexBuilder
+    from spades_b200.packing import pack_fixed
+    codes = synthetic_reads(60000, 150, 60000, 0.01, seed=77, as_codes=True)
+    words, offs, lens = pack_fixed(codes)
+    c = ctx()
+    c.set_reads(words, offs, lens)
+    K, B = 56, 80
+    st = KMerDiskCounter(c, DeBruijnReadKMerSplitter(K)).Count(B)
+    keys, counts, bsz = st.kmers(), st.counts(), st.bucket_sizes()
+    # size-independent properties: total multiplicity == number of windows (no self-RC doubling can lose any), strictly
+    # increasing inside buckets, bucket function honoured
+    assert int(counts.astype(np.uint64).sum()) >= 60000 * (150 - K + 1)
+    off = 0
+    for b in range(B):
+        kb = keys[off:off + bsz[b]]
+        if len(kb) > 1:
+            lt = (kb[:-1, 0] < kb[1:, 0]) | ((kb[:-1, 0] == kb[1:, 0]) & (kb[:-1, 1] < kb[1:, 1]))
+            assert lt.all()
+        off += bsz[b]
+    ks = O.count(words, offs, lens, K, B, 0)
+    assert np.array_equal(keys.ravel(), ks.keys.ravel()) and np.array_equal(counts, ks.counts) and np.array_equal(bsz, ks.bsz)
+    idx = KMerIndexBuilder(c).BuildIndex(st)
+    ids = idx.seq_idx(keys)
+    assert len(np.unique(ids)) == len(keys) and ids.max() == len(keys) - 1       # phm_test.cpp:22-79 properties
+    assert G.index_equal(O.Mphf(ks).serialize(), idx.serialize(), B)
