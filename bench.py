@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- Mk-mers/s of the hot path (extract + count + index) on synthetic 150 bp reads, k=55.
+
+One "step" = one pass of the hot path over one batch of synthetic reads:
+    reads (2-bit packed)  ->  canonical (k+1)-mers  ->  XXH3 bucket partition  ->  per-bucket sort/unique/count
+                           ->  boomphf-compatible MPHF over the distinct (k+1)-mers
+i.e. what KMerDiskCounter::Count + KMerIndexBuilder::BuildIndex do in the reference
+(kmer_index_builder.hpp:306-332,448-498). k-mers = N_reads x (L - K + 1) forward windows, K = k+1 = 56.
+
+  value : whole-job throughput with the packed reads already resident in HBM when the timed region starts
+  e2e   : same metric through the C ABI with HOST buffers: pinned-host -> device copy of the reads, the step, and the
+          device -> host read of the result (bucket sizes + serialized KMerIndex) inside the timed region
+  --impl reference : the UNMODIFIED reference (oracle/_ref/ref_probe bench mode) on the host cores, bounded sample
+
+Timing: CUDA events on the stream the library runs on (it is handed torch's current stream), barrier + synchronize on
+both sides, max over ranks. Inputs (>= 0.4 GB) and intermediates (tens of GB) are far larger than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_GRAPH = 55
+K = K_GRAPH + 1
+READ_LEN = 150
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("SGPU_BENCH_READS", 20_000_000)), help="reads per GPU")
+    ap.add_argument("--buckets", type=int, default=0, help="0 = 10 x host threads, as the reference's graph path (construction.cpp:242)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic reads: uniform genome, uniform start, random strand, 1% substitutions; generated on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def gen_reads_device(torch, n_reads, genome_len, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    genome = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=device, generator=g)
+    nwr = (READ_LEN + 31) // 32
+    words = torch.zeros(n_reads * nwr + 8, dtype=torch.int64, device=device)
+    shifts = (torch.arange(32, device=device, dtype=torch.int64) * 2)
+    ar = torch.arange(READ_LEN, device=device)
+    chunk = 1_000_000
+    for s in range(0, n_reads, chunk):
+        c = min(chunk, n_reads - s)
+        starts = torch.randint(0, genome_len - READ_LEN + 1, (c,), device=device, generator=g)
+        reads = genome[starts[:, None] + ar[None, :]]
+        strand = torch.rand(c, device=device, generator=g) < 0.5
+        reads = torch.where(strand[:, None], (3 - reads).flip(1), reads)
+        errs = torch.rand((c, READ_LEN), device=device, generator=g) < 0.01
+        sub = torch.randint(1, 4, (c, READ_LEN), dtype=torch.uint8, device=device, generator=g)
+        reads = torch.where(errs, (reads + sub) & 3, reads)
+        padded = torch.zeros((c, nwr * 32), dtype=torch.int64, device=device)
+        padded[:, :READ_LEN] = reads.to(torch.int64)
+        w = (padded.view(c, nwr, 32) << shifts).sum(dim=2)
+        words[s * nwr:(s + c) * nwr] = w.reshape(-1)
+        del reads, padded, w, errs, sub, strand, starts
+    offs = torch.arange(n_reads, device=device, dtype=torch.int64) * nwr
+    lens = torch.full((n_reads,), READ_LEN, dtype=torch.int32, device=device)
+    return words, offs, lens, nwr
+
+
+def unpack_to_text(words_np, nwr, n, path):
+    import numpy as np
+    w = words_np[: n * nwr].reshape(n, nwr).astype(np.uint64)
+    sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))
+    codes = ((w[:, :, None] >> sh[None, None, :]) & np.uint64(3)).astype(np.uint8).reshape(n, nwr * 32)[:, :READ_LEN]
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    txt = lut[codes]
+    out = np.empty((n, READ_LEN + 1), dtype=np.uint8)
+    out[:, :READ_LEN] = txt
+    out[:, READ_LEN] = 10
+    out.tofile(path)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.maxclk = [], set(), None
+        self.stop_ev = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.maxclk = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """UNMODIFIED reference (ref_probe 'bench') on the host cores. Rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    probe = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+    T = host_threads()
+    B = args.buckets or 10 * T
+    n = args.cpu_sample_reads
+    if not os.path.exists(probe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_probe was not built (needs /root/reference at build time)"}))
+        return
+    reads = _cpu_sample(n)
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        reads.tofile(rf)
+        reps = args.warmup + args.steps
+        out = subprocess.run([probe, "bench", rf, str(K_GRAPH), str(B), str(T), os.path.join(d, "out"), str(reps)],
+                             capture_output=True, text=True).stdout
+    recs = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("BENCH ")]
+    timed = recs[args.warmup:]
+    tot = sum(r["total_s"] for r in timed)
+    windows = timed[0]["windows"]
+    val = windows * len(timed) / tot / 1e6
+    line = {"metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": val, "unit": "Mk-mers/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(timed), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "synthetic %d x 150 bp reads (bounded sample of the bench workload), k=55 (K=56 canonical (k+1)-mers), %d buckets" % (n, B),
+                       "k": K_GRAPH, "reads": n, "buckets": B},
+            "cpu_baseline": {"value": val, "unit": "Mk-mers/s", "cores": T, "kind": "reference",
+                             "sample": "%d reads x 150 bp, in-memory read streams, count+index region of ref_probe (unmodified SPAdes KMerDiskCounter + KMerIndexBuilder)" % n},
+            "e2e": {"value": val, "unit": "Mk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _cpu_sample(n):
+    """first n reads of the bench generator (seed 42, rank 0), as a text matrix; generated on the CPU with the same
+    torch generator semantics is not needed -- the sample only has to have the workload's shape (same genome size ratio)."""
+    import numpy as np
+    from spades_b200.packing import synthetic_reads
+    codes = synthetic_reads(n, READ_LEN, max(READ_LEN + 1, n), 0.01, seed=42, as_codes=True)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = np.empty((n, READ_LEN + 1), dtype=np.uint8)
+    out[:, :READ_LEN] = lut[codes]
+    out[:, READ_LEN] = 10
+    return out
+
+
+def cpu_baseline(args):
+    probe = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+    T = host_threads()
+    B = args.buckets or 10 * T
+    n = args.cpu_sample_reads
+    if os.path.exists(probe):
+        reads = _cpu_sample(n)
+        with tempfile.TemporaryDirectory() as d:
+            rf = os.path.join(d, "reads.txt")
+            reads.tofile(rf)
+            out = subprocess.run([probe, "bench", rf, str(K_GRAPH), str(B), str(T), os.path.join(d, "out"), "2"], capture_output=True, text=True).stdout
+        recs = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("BENCH ")]
+        r = recs[-1]
+        return {"value": r["windows"] / r["total_s"] / 1e6, "unit": "Mk-mers/s", "cores": T, "kind": "reference",
+                "sample": "%d reads x 150 bp (2nd of 2 runs), unmodified SPAdes KMerDiskCounter::Count + KMerIndexBuilder::BuildIndex via oracle/_ref/ref_probe, %d buckets, in-memory streams" % (n, B)}
+    # the plain-C oracle port (single thread)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle as O
+    from spades_b200.packing import pack_fixed, synthetic_reads
+    n = min(n, 100_000)
+    codes = synthetic_reads(n, READ_LEN, max(READ_LEN + 1, n), 0.01, seed=42, as_codes=True)
+    words, offs, lens = pack_fixed(codes)
+    t0 = time.time()
+    ks = O.count(words, offs, lens, K, B, 0)
+    O.Mphf(ks)
+    dt = time.time() - t0
+    return {"value": n * (READ_LEN - K + 1) / dt / 1e6, "unit": "Mk-mers/s", "cores": 1, "kind": "port", "sample": "%d reads x 150 bp, oracle/spades_oracle.c count+mphf" % n}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from spades_b200.kmer_index import Context, DeBruijnReadKMerSplitter, KMerDiskCounter, KMerIndexBuilder
+
+    T = host_threads()
+    B = args.buckets or 10 * T
+    n_reads = args.reads
+    genome_len = max(READ_LEN + 1, n_reads)          # 150x coverage like config 3 (100 M reads over 100 Mbp)
+    words, offs, lens, nwr = gen_reads_device(torch, n_reads, genome_len, 42 + rank, dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    ctx = Context(local_rank, stream=stream.cuda_stream)
+    nwords = n_reads * nwr
+
+    def step_resident():
+        ctx.adopt_device_reads(words.data_ptr(), nwords, offs.data_ptr(), lens.data_ptr(), n_reads)
+        st = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
+        idx = KMerIndexBuilder(ctx).BuildIndex(st)
+        return st, idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: reads resident in HBM
+    for _ in range(args.warmup):
+        st, idx = step_resident(); idx.free(); st.free()
+    phases = {k: 0.0 for k in ("extract_count_ms", "extract_scatter_ms", "refine_ms", "local_sort_ms", "compact_ms", "mphf_ms")}
+    l0 = ctx.times()["launches"]
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    distinct = instances = passes = 0
+    for _ in range(args.steps):
+        st, idx = step_resident()
+        t = ctx.times()
+        for kname in phases:
+            phases[kname] += t[kname]
+        distinct, instances, passes = st.total_kmers(), t["instances"], t["passes"]
+        idx.free(); st.free()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_ev.set(); sampler.join()
+    launches = ctx.times()["launches"] - l0
+    peak = ctx.times()["peak_bytes"]
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    windows_per_step = n_reads * (READ_LEN - K + 1) * world
+    value = windows_per_step * args.steps / (ms / 1e3) / 1e6
+
+    # ---- e2e: host buffers in, host result out
+    h_words = words[:nwords].cpu().pin_memory(); h_offs = offs.cpu().pin_memory(); h_lens = lens.cpu().pin_memory()
+    d2h = 0
+
+    def step_e2e():
+        nonlocal d2h
+        ctx.upload_reads(h_words.data_ptr(), nwords, h_offs.data_ptr(), h_lens.data_ptr(), n_reads)
+        st = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
+        idx = KMerIndexBuilder(ctx).BuildIndex(st)
+        ser = idx.serialize()
+        bsz = st.bucket_sizes()
+        d2h = len(ser) + bsz.nbytes
+        idx.free(); st.free()
+
+    step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e3.record(stream)
+    barrier()
+    ems = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = windows_per_step * args.steps / (float(ems.item()) / 1e3) / 1e6
+    h2d = h_words.numel() * 8 + h_offs.numel() * 8 + h_lens.numel() * 4
+
+    if rank == 0:
+        W = 16
+        steps = args.steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        per_step = {k2: v / steps for k2, v in phases.items()}
+        # algorithmic bytes per step of each kernel family: I = instances, D = distinct
+        I, D = instances, distinct
+        alg = {
+            "extract_scatter_ms": n_reads * nwr * 8 + I * W,                 # packed reads in, records out
+            "extract_count_ms": n_reads * nwr * 8,                           # packed reads in
+            "refine_ms": 2 * I * W,                                          # one read + one write of every record
+            "local_sort_ms": I * W + D * (W + 4),                            # records in, distinct records + counts out
+            "compact_ms": 2 * D * (W + 4),
+        }
+        dom = max(alg, key=lambda k2: per_step[k2])
+        achieved = alg[dom] / (per_step[dom] / 1e3) / 1e9 if per_step[dom] > 0 else 0.0
+        kernel_names = {"extract_scatter_ms": "levelA_scatter_k (radix partition)", "extract_count_ms": "levelA_count_k", "refine_ms": "refine_k (MSD split)",
+                        "local_sort_ms": "local_sort_k", "compact_ms": "compact_k"}
+        line = {
+            "metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": value, "unit": "Mk-mers/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": "synthetic %d x 150 bp reads per GPU (uniform genome %d bp, 1%% substitutions, random strand), k=55: canonical (k+1)=56-mers, "
+                                   "%d XXH3 buckets, sort/unique/count + boomphf MPHF (extract+count+index)" % (n_reads, genome_len, B),
+                       "k": K_GRAPH, "reads_per_gpu": n_reads, "buckets": B, "distinct_kpomers": int(distinct), "instances": int(instances), "passes": int(passes),
+                       "l2": "inputs (%.1f GB) and intermediates larger than L2; no flush needed" % (nwords * 8 / 1e9), "peak_hbm_gb": peak / 1e9},
+            "clocks": sampler.result(), "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "Mk-mers/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "pinned host reads -> sgpu_reads_upload -> sgpu_count -> sgpu_mphf_build -> sgpu_mphf_serialize + bucket sizes to host; sorted (k+1)-mers stay in HBM for the graph phases"},
+            "phases_ms_per_step": per_step,
+            "roofline": {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_step": int(alg[dom]),
+                         "all": {kernel_names[k2]: (alg[k2] / (per_step[k2] / 1e3) / 1e9 if per_step[k2] > 0 else None) for k2 in alg}},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,7 @@ typedef struct sgpu_config {
     int device;                 /* CUDA device ordinal */
     uint64_t hbm_budget_bytes;  /* 0 = whatever is free on the device */
     int verbose;
+    uint64_t stream;            /* a cudaStream_t to run on (e.g. the caller's timing stream); 0 = create a private stream */
 } sgpu_config;
 
 enum { SGPU_CANONICAL = 0, SGPU_ALL_WINDOWS = 1 };
@@ -79,6 +80,8 @@ int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out);
  * (N-free: apply LongestValid first, io/reads/longest_valid_wrapper.hpp:16-53). offs are relative to `words`. */
 int sgpu_reads_clear(sgpu_ctx *ctx);
 int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
+/* replace the read set with these HOST buffers, copied straight to the device (pinned buffers copy at full PCIe rate) */
+int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
 /* use a read set that already lives in device memory (not copied, must stay valid while the context uses it) */
 int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads);
 

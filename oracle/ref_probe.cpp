@@ -135,6 +135,30 @@ int main(int argc, char **argv) {
     }
 
     using Splitter = kmers::DeBruijnReadKMerSplitter<Read, kmers::StoringTypeFilter<kmers::InvertableStoring>>;
+    if (mode == "bench") {
+        // timed region == the GPU bench step: extract + count the (k+1)-mers (KMerDiskCounter::Count) and index them
+        // (KMerIndexBuilder::BuildIndex over the storage, as CoverageHashMapBuilder does, coverage_hash_map_builder.hpp:46).
+        // Input parsing / packing above is outside the region, like "reads resident" on the GPU side.
+        int reps = argc > 7 ? atoi(argv[7]) : 1;
+        for (int rep = 0; rep < reps; ++rep) {
+            auto wd = fs::tmp::make_temp_dir(outdir / "tmp", "bench");
+            streams.reset();
+            double t0 = omp_get_wtime();
+            kmers::KMerDiskCounter<RtSeq> counter(wd, Splitter(wd, k + 1, streams, 0));
+            auto kpomers = counter.Count(B, T);
+            double t1 = omp_get_wtime();
+            using CoverageMap = kmers::PerfectHashMap<RtSeq, uint32_t, kmers::slim_kmer_index_traits<RtSeq>, kmers::DefaultStoring>;
+            CoverageMap cm(k + 1);
+            kmers::PerfectHashMapBuilder().BuildIndex(cm, kpomers, T);
+            double t2 = omp_get_wtime();
+            size_t windows = 0;
+            for (const auto &s : seqs) if (s.size() >= k + 1) windows += s.size() - k;
+            printf("BENCH {\"rep\": %d, \"count_s\": %.6f, \"index_s\": %.6f, \"total_s\": %.6f, \"windows\": %zu, \"distinct\": %zu, \"threads\": %u, \"buckets\": %u}\n",
+                   rep, t1 - t0, t2 - t1, t2 - t0, windows, kpomers.total_kmers(), T, B);
+            fflush(stdout);
+        }
+        return 0;
+    }
     kmers::KMerDiskCounter<RtSeq> counter(workdir, Splitter(workdir, k + 1, streams, 0));
     auto kpomers = counter.Count(B, T);
     {

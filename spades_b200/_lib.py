@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libspades_b200.so")
 # every symbol include/spades_b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_get_times",
-    "sgpu_reads_clear", "sgpu_reads_append_packed", "sgpu_reads_adopt_device",
+    "sgpu_reads_clear", "sgpu_reads_append_packed", "sgpu_reads_upload", "sgpu_reads_adopt_device",
     "sgpu_count", "sgpu_kmers_from_kpomers",
     "sgpu_kset_size", "sgpu_kset_k", "sgpu_kset_num_buckets", "sgpu_kset_record_bytes", "sgpu_kset_bucket_sizes",
     "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
@@ -23,7 +23,7 @@ SYMBOLS = [
 
 
 class SgpuConfig(C.Structure):
-    _fields_ = [("device", C.c_int), ("hbm_budget_bytes", C.c_uint64), ("verbose", C.c_int)]
+    _fields_ = [("device", C.c_int), ("hbm_budget_bytes", C.c_uint64), ("verbose", C.c_int), ("stream", C.c_uint64)]
 
 
 class SgpuTimes(C.Structure):
@@ -51,6 +51,7 @@ def load():
     L.sgpu_get_times.restype = i32; L.sgpu_get_times.argtypes = [vp, C.POINTER(SgpuTimes)]
     L.sgpu_reads_clear.restype = i32; L.sgpu_reads_clear.argtypes = [vp]
     L.sgpu_reads_append_packed.restype = i32; L.sgpu_reads_append_packed.argtypes = [vp, vp, u64, vp, vp, i64]
+    L.sgpu_reads_upload.restype = i32; L.sgpu_reads_upload.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_reads_adopt_device.restype = i32; L.sgpu_reads_adopt_device.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_count.restype = i32; L.sgpu_count.argtypes = [vp, i32, i32, i32, pp]
     L.sgpu_kmers_from_kpomers.restype = i32; L.sgpu_kmers_from_kpomers.argtypes = [vp, vp, i32, pp]

@@ -9,7 +9,7 @@
 
 using namespace sg;
 
-struct sgpu_ctx { Ctx c; };
+struct sgpu_ctx { Ctx c; bool own_stream = true; };
 struct sgpu_kset { KSet *s; };
 struct sgpu_mphf { Mphf *m; std::vector<uint8_t> ser; bool have_ser = false; };
 struct sgpu_graph { Graph *g; };
@@ -39,9 +39,9 @@ int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out) {
     h->c.hbm_budget = cfg ? (size_t)cfg->hbm_budget_bytes : 0;
     h->c.verbose = cfg ? cfg->verbose : 0;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaGetLastError(); delete h; return SGPU_ECUDA;
-    }
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); delete h; return SGPU_ECUDA; }
+    if (cfg && cfg->stream) { h->c.stream = (cudaStream_t)(uintptr_t)cfg->stream; h->own_stream = false; }
+    else if (cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete h; return SGPU_ECUDA; }
     h->c.num_sms = prop.multiProcessorCount;
     *out = h;
     return SGPU_OK;
@@ -51,7 +51,7 @@ void sgpu_destroy(sgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
-    if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+    if (ctx->c.stream && ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }
 
@@ -90,6 +90,24 @@ int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwor
         }
         c->h_words.insert(c->h_words.end(), words, words + nwords);
         c->staged_dirty = true;
+    })
+}
+
+int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads) {
+    if (!ctx || nreads < 0 || (nreads && (!words || !offs || !lens))) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear(); c->staged_dirty = false;
+        if (c->r_words.n < nwords + 4) c->r_words.alloc(c, nwords + 4);
+        if (c->r_offs.n < (size_t)nreads + 1) c->r_offs.alloc(c, (size_t)nreads + 1);
+        if (c->r_lens.n < (size_t)nreads + 1) c->r_lens.alloc(c, (size_t)nreads + 1);
+        if (nwords) SG_CUDA(cudaMemcpyAsync(c->r_words.p, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
+        if (nreads) {
+            SG_CUDA(cudaMemcpyAsync(c->r_offs.p, offs, (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));
+            SG_CUDA(cudaMemcpyAsync(c->r_lens.p, lens, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        c->d_words = c->r_words.p; c->d_offs = c->r_offs.p; c->d_lens = c->r_lens.p; c->n_reads = nreads; c->n_words = nwords;
     })
 }
 

@@ -27,9 +27,9 @@ def _p(a):
 class Context:
     """One GPU context (one per process per GPU)."""
 
-    def __init__(self, device=0, hbm_budget_bytes=0, verbose=0):
+    def __init__(self, device=0, hbm_budget_bytes=0, verbose=0, stream=0):
         self.L = _lib.load()
-        cfg = _lib.SgpuConfig(device, hbm_budget_bytes, verbose)
+        cfg = _lib.SgpuConfig(device, hbm_budget_bytes, verbose, stream)
         h = C.c_void_p()
         rc = self.L.sgpu_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -54,6 +54,10 @@ class Context:
         words = np.ascontiguousarray(words, np.uint64); offs = np.ascontiguousarray(offs, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
         self.check(self.L.sgpu_reads_clear(self.h))
         self.check(self.L.sgpu_reads_append_packed(self.h, _p(words), len(words), _p(offs), _p(lens), len(lens)))
+
+    def upload_reads(self, words_ptr, nwords, offs_ptr, lens_ptr, nreads):
+        """Raw host pointers (e.g. pinned torch tensors) copied straight to the device."""
+        self.check(self.L.sgpu_reads_upload(self.h, C.c_void_p(words_ptr), nwords, C.c_void_p(offs_ptr), C.c_void_p(lens_ptr), nreads))
 
     def adopt_device_reads(self, d_words_ptr, nwords, d_offs_ptr, d_lens_ptr, nreads):
         self.check(self.L.sgpu_reads_adopt_device(self.h, C.c_void_p(d_words_ptr), nwords, C.c_void_p(d_offs_ptr), C.c_void_p(d_lens_ptr), nreads))

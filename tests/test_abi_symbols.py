@@ -32,7 +32,7 @@ def test_no_gpu_is_a_loud_error_not_a_fallback():
         pytest.skip("GPU present")
     L = _lib.load()
     h = C.c_void_p()
-    cfg = _lib.SgpuConfig(0, 0, 0)
+    cfg = _lib.SgpuConfig(0, 0, 0, 0)
     assert L.sgpu_create(C.byref(cfg), C.byref(h)) == 3      # SGPU_ENODEV
     from spades_b200.kmer_index import Context, SpadesGpuError
     with pytest.raises(SpadesGpuError):
