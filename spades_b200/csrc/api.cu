@@ -51,6 +51,7 @@ void sgpu_destroy(sgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
+    ctx->c.pool_trim();
     if (ctx->c.stream && ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }

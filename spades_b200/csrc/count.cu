@@ -16,6 +16,8 @@
 //   C  local sort        : one CTA per segment: LSD radix sort in shared memory over the remaining key bits
 //      (optimistic 32-bit window + verification, full range on failure), run-length unique/count, written
 //      back in place; then a compaction copy into the dense bucket-major result.
+#include <time.h>
+
 #include <algorithm>
 
 #include "sgpu_internal.h"
@@ -106,7 +108,7 @@ struct LevelA {
 };
 
 static const int kATile = 256;        // items (reads) per tile
-static const int kAThreads = 512;
+static const int kAThreads = 1024;
 
 // tile prologue: per-item record counts -> exclusive prefix in shared memory; returns the tile total
 template <class Src>
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
 // ------------------------------------------------------------------------------------------------------------
 // local sort + unique + count
 // ------------------------------------------------------------------------------------------------------------
-template <int NW> struct SortCfg { static const int CAP = NW == 1 ? 4096 : (NW == 2 ? 2048 : 1024); };
+template <int NW> struct SortCfg { static const int CAP = NW <= 2 ? 2048 : 1024; };
 static const int kSThreads = 256;
 static const int kSWarps = kSThreads / 32;
 
@@ -522,6 +524,440 @@ __global__ void __launch_bounds__(kSThreads) local_sort_k(const Seg *__restrict_
     }
 }
 
+// ---- local sort, second generation -------------------------------------------------------------------------------
+// After level A + MSD refinement a segment holds ~CAP/3 records that agree on their first `bits` key bits. Most of
+// them are copies of a few keys (a genomic (k+1)-mer is seen ~coverage times) plus error singletons. Instead of a
+// full radix sort: ONE counting pass on the next kBinBits key bits into shared-memory bins, then one thread per bin
+// collapses equal keys (bins hold 0, 1 or "c copies of one key" almost always), insertion-sorts the bin's few
+// distinct keys and the bins are concatenated. Bins whose dedup work explodes (many distinct keys sharing a long
+// prefix: low-complexity sequence) make the CTA fall back to the exact LSD radix path above.
+static const int kBinBits = 11;
+static const int kBins = 1 << kBinBits;
+
+template <int NW>
+__global__ void __launch_bounds__(kSThreads) local_sort2_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
+                                                          uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
+                                                          unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
+    constexpr int CAP = SortCfg<NW>::CAP;
+    extern __shared__ uint64_t sm64[];
+    uint64_t *A = sm64;                                   // CAP*NW
+    uint64_t *Bf = A + (size_t)CAP * NW;                  // CAP*NW
+    uint32_t *cntB = reinterpret_cast<uint32_t *>(Bf + (size_t)CAP * NW);   // CAP     multiplicity per slot of Bf
+    uint32_t *cntA = cntB + CAP;                          // CAP+1   (also `heads` of the LSD fallback)
+    uint32_t *hist = cntA + CAP + 1;                      // kBins   (also cursor)
+    uint32_t *bstart = hist + kBins;                      // kBins+1
+    uint32_t *lsdcnt = bstart + kBins + 1;                // kSWarps*256
+    __shared__ uint32_t tot[kSWarps + 1];
+    __shared__ unsigned long long s_w;
+    __shared__ int s_flag;
+    const int total_bits = 2 * K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) { s_w = atomicAdd(work_counter, 1ull); s_flag = 0; }
+        __syncthreads();
+        const uint64_t si = s_w;
+        if (si >= nsegs) return;
+        const Seg s = segs[si];
+        uint64_t *gsrc = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
+        uint32_t *gcnt = reinterpret_cast<uint32_t *>(((s.bb & 1) ? buf0 : buf1) + s.start * NW);
+        if (s.len == 0) { if (threadIdx.x == 0) ndist[si] = 0; __syncthreads(); continue; }
+        if (s.len > (uint64_t)CAP) {
+            if (threadIdx.x == 0) { gcnt[0] = (uint32_t)s.len; ndist[si] = 1; if (s.bits < (uint32_t)total_bits) atomicAdd(&stats[0], 1ull); }
+            __syncthreads();
+            continue;
+        }
+        const uint32_t n = (uint32_t)s.len;
+        const int lo = (int)s.bits;
+        const int r2 = (total_bits - lo) < kBinBits ? (total_bits - lo) : kBinBits;
+        const uint32_t nb = 1u << r2;
+        // ---- phase 1: load + histogram
+        for (uint32_t i = threadIdx.x; i < nb; i += kSThreads) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += kSThreads) {
+            Kmer<NW> k = load_rec<NW>(gsrc + (size_t)i * NW);
+            store_rec<NW>(A + (size_t)i * NW, k);
+            atomicAdd(&hist[r2 ? key_bits<NW>(k, K, lo, r2) : 0u], 1u);
+        }
+        __syncthreads();
+        // ---- phase 2: exclusive scan of the bins (each thread owns kBins/kSThreads consecutive bins)
+        constexpr int BPT = kBins / kSThreads;
+        const uint32_t b0 = threadIdx.x * BPT;
+        uint32_t loc[BPT];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { loc[q] = (b0 + q < nb) ? hist[b0 + q] : 0; sum += loc[q]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) tot[warp] = inc;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += tot[w];
+        uint32_t run = wb + inc - sum;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            if (b0 + q < nb) { bstart[b0 + q] = run; hist[b0 + q] = run; }
+            run += loc[q];
+        }
+        if (threadIdx.x == kSThreads - 1) bstart[nb] = n;
+        __syncthreads();
+        // ---- phase 3: scatter into bins
+        for (uint32_t i = threadIdx.x; i < n; i += kSThreads) {
+            Kmer<NW> k = load_rec<NW>(A + (size_t)i * NW);
+            const uint32_t pos = atomicAdd(&hist[r2 ? key_bits<NW>(k, K, lo, r2) : 0u], 1u);
+            store_rec<NW>(Bf + (size_t)pos * NW, k);
+        }
+        __syncthreads();
+        // ---- phase 4: per-bin dedup + tiny sort. distinct keys of bin b end up in Bf[bstart[b] .. +d) with cntB
+        uint32_t dloc[BPT];
+        uint32_t dsum = 0;
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            dloc[q] = 0;
+            if (b0 + q >= nb) continue;
+            const uint32_t bs = bstart[b0 + q], be = bstart[b0 + q + 1];
+            if (be == bs) continue;
+            if (be - bs == 1) { cntB[bs] = 1; dloc[q] = 1; dsum += 1; continue; }
+            uint32_t rem_end = be, p = bs, work = 0;
+            while (p < rem_end) {
+                const Kmer<NW> key = load_rec<NW>(Bf + (size_t)p * NW);
+                uint32_t c = 1, w = p + 1;
+                for (uint32_t j = p + 1; j < rem_end; ++j) {
+                    const Kmer<NW> x = load_rec<NW>(Bf + (size_t)j * NW);
+                    if (kmer_eq<NW>(x, key)) ++c;
+                    else { if (w != j) store_rec<NW>(Bf + (size_t)w * NW, x); ++w; }
+                }
+                work += rem_end - p;
+                cntB[p] = c;
+                rem_end = w;
+                ++p;
+                if (work > 4096u || p - bs > 24u) { bad = true; break; }
+            }
+            if (bad) break;
+            const uint32_t d = p - bs;
+            for (uint32_t a = bs + 1; a < bs + d; ++a) {             // insertion sort of the d distinct keys
+                const Kmer<NW> key = load_rec<NW>(Bf + (size_t)a * NW);
+                const uint32_t kc = cntB[a];
+                uint32_t z = a;
+                while (z > bs && kmer_word_cmp<NW>(load_rec<NW>(Bf + (size_t)(z - 1) * NW), key) > 0) {
+                    store_rec<NW>(Bf + (size_t)z * NW, load_rec<NW>(Bf + (size_t)(z - 1) * NW));
+                    cntB[z] = cntB[z - 1];
+                    --z;
+                }
+                store_rec<NW>(Bf + (size_t)z * NW, key);
+                cntB[z] = kc;
+            }
+            dloc[q] = d; dsum += d;
+        }
+        if (bad) s_flag = 1;
+        __syncthreads();
+        if (s_flag) {
+            // exact fallback: LSD radix over every remaining key bit, then run-length unique (A still holds the records)
+            if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
+            uint64_t *S = lsd_sort_range<NW>(A, Bf, n, K, lo, total_bits, lsdcnt, tot);
+            uint32_t *heads = cntA;
+            const uint32_t per = (n + kSThreads - 1) / kSThreads;
+            const uint32_t i0 = threadIdx.x * per, i1 = min(n, i0 + per);
+            uint32_t nh = 0;
+            for (uint32_t i = i0; i < i1; ++i)
+                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) ++nh;
+            uint32_t hinc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, hinc, o);
+                if (lane >= o) hinc += t;
+            }
+            if (lane == 31) tot[warp] = hinc;
+            __syncthreads();
+            uint32_t hb = 0, all = 0;
+            for (int w = 0; w < kSWarps; ++w) { if (w < warp) hb += tot[w]; all += tot[w]; }
+            uint32_t j = hb + hinc - nh;
+            for (uint32_t i = i0; i < i1; ++i)
+                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) heads[j++] = i;
+            if (threadIdx.x == 0) { heads[all] = n; ndist[si] = all; }
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; q < all; q += kSThreads) {
+                const uint32_t h = heads[q];
+                store_rec<NW>(gsrc + (size_t)q * NW, load_rec<NW>(S + (size_t)h * NW));
+                gcnt[q] = heads[q + 1] - h;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- phase 5: concatenate the bins' distinct keys (A is free now) and write back coalesced
+        uint32_t dinc = dsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, dinc, o);
+            if (lane >= o) dinc += t;
+        }
+        if (lane == 31) tot[warp] = dinc;
+        __syncthreads();
+        uint32_t db = 0, all = 0;
+        for (int w = 0; w < kSWarps; ++w) { if (w < warp) db += tot[w]; all += tot[w]; }
+        uint32_t o = db + dinc - dsum;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            if (!dloc[q]) continue;
+            const uint32_t bs = bstart[b0 + q];
+            for (uint32_t z = 0; z < dloc[q]; ++z) {
+                store_rec<NW>(A + (size_t)(o + z) * NW, load_rec<NW>(Bf + (size_t)(bs + z) * NW));
+                cntA[o + z] = cntB[bs + z];
+            }
+            o += dloc[q];
+        }
+        if (threadIdx.x == 0) ndist[si] = all;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < all * NW; i += kSThreads) gsrc[i] = A[i];
+        for (uint32_t i = threadIdx.x; i < all; i += kSThreads) gcnt[i] = cntA[i];
+        __syncthreads();
+    }
+}
+
+// ---- local sort, third generation: representative + residual ------------------------------------------------------
+// ncu on the second generation showed 8.5 active lanes per instruction and barrier stalls on top: one thread chewing
+// through the ~coverage copies of a genomic k-mer held up its whole CTA. Here every bin elects a representative (the
+// record with the smallest index, one shared-memory atomicMin per record); records equal to their bin's representative
+// only bump a counter. Only the few records that differ from it (bins holding two or more distinct keys) are scattered
+// into a small residual buffer and deduplicated by one thread per bin, so the per-bin work is a handful of compares.
+// Anything unusual (residual overflow, a bin with many distinct keys) falls back to the exact LSD radix path, which
+// uses the segment's region in the partner buffer as scratch.
+static const int kResCap = 512;
+
+template <int NW>
+__global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
+                                                          uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
+                                                          unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
+    constexpr int CAP = SortCfg<NW>::CAP;
+    constexpr int BPT = kBins / kSThreads;
+    constexpr int IPT = CAP / kSThreads;                  // records per thread
+    extern __shared__ uint64_t sm64[];
+    uint64_t *A = sm64;                                   // CAP*NW   the segment
+    uint64_t *R = A + (size_t)CAP * NW;                   // kResCap*NW residual records, grouped by bin
+    uint32_t *rep = reinterpret_cast<uint32_t *>(R + (size_t)kResCap * NW);   // kBins  index of the bin's representative
+    uint32_t *repcnt = rep + kBins;                       // kBins  copies of the representative besides itself
+    uint32_t *rhist = repcnt + kBins;                     // kBins  residual count -> cursor
+    uint16_t *rstart = reinterpret_cast<uint16_t *>(rhist + kBins);           // kBins+2
+    uint16_t *rcnt = rstart + kBins + 2;                  // kResCap multiplicity per residual slot
+    uint32_t *lsdcnt = rep;                               // fallback only (kSWarps*256 <= 3*kBins)
+    __shared__ uint32_t tot[kSWarps + 1];
+    __shared__ unsigned long long s_w;
+    __shared__ int s_flag;
+    const int total_bits = 2 * K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) { s_w = atomicAdd(work_counter, 1ull); s_flag = 0; }
+        __syncthreads();
+        const uint64_t si = s_w;
+        if (si >= nsegs) return;
+        const Seg s = segs[si];
+        uint64_t *gsrc = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
+        uint64_t *gpartner = ((s.bb & 1) ? buf0 : buf1) + s.start * NW;
+        uint32_t *gcnt = reinterpret_cast<uint32_t *>(gpartner);
+        if (s.len == 0) { if (threadIdx.x == 0) ndist[si] = 0; __syncthreads(); continue; }
+        if (s.len > (uint64_t)CAP) {
+            if (threadIdx.x == 0) { gcnt[0] = (uint32_t)s.len; ndist[si] = 1; if (s.bits < (uint32_t)total_bits) atomicAdd(&stats[0], 1ull); }
+            __syncthreads();
+            continue;
+        }
+        const uint32_t n = (uint32_t)s.len;
+        const int lo = (int)s.bits;
+        const int r2 = (total_bits - lo) < kBinBits ? (total_bits - lo) : kBinBits;
+        const uint32_t nb = 1u << r2;
+        for (uint32_t i = threadIdx.x; i < nb; i += kSThreads) { rep[i] = 0xffffffffu; repcnt[i] = 0; rhist[i] = 0; }
+        __syncthreads();
+        // ---- P1: load, elect representatives
+        uint32_t dig[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t i = threadIdx.x + j * kSThreads;
+            dig[j] = 0;
+            if (i < n) {
+                Kmer<NW> k = load_rec<NW>(gsrc + (size_t)i * NW);
+                store_rec<NW>(A + (size_t)i * NW, k);
+                dig[j] = r2 ? key_bits<NW>(k, K, lo, r2) : 0u;
+                atomicMin(&rep[dig[j]], i);
+            }
+        }
+        __syncthreads();
+        // ---- P2: copies of the representative only count; everything else is residual
+        uint32_t resmask = 0;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t i = threadIdx.x + j * kSThreads;
+            if (i < n) {
+                const uint32_t r = rep[dig[j]];
+                if (r != i) {
+                    if (kmer_eq<NW>(load_rec<NW>(A + (size_t)i * NW), load_rec<NW>(A + (size_t)r * NW))) atomicAdd(&repcnt[dig[j]], 1u);
+                    else { atomicAdd(&rhist[dig[j]], 1u); resmask |= 1u << j; }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P3: exclusive scan of the residual counts
+        const uint32_t b0 = threadIdx.x * BPT;
+        uint32_t loc[BPT];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { loc[q] = (b0 + q < nb) ? rhist[b0 + q] : 0; sum += loc[q]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) tot[warp] = inc;
+        __syncthreads();
+        uint32_t wb = 0, rtotal = 0;
+        for (int w = 0; w < kSWarps; ++w) { if (w < warp) wb += tot[w]; rtotal += tot[w]; }
+        {
+            uint32_t run = wb + inc - sum;
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                if (b0 + q < nb) { rstart[b0 + q] = (uint16_t)run; rhist[b0 + q] = run; }
+                run += loc[q];
+            }
+            if (threadIdx.x == kSThreads - 1) rstart[nb] = (uint16_t)rtotal;
+        }
+        bool bad = rtotal > (uint32_t)kResCap;
+        __syncthreads();
+        // ---- P4: scatter the residual records into their bins
+        if (!bad) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                if (resmask & (1u << j)) {
+                    const uint32_t i = threadIdx.x + j * kSThreads;
+                    const uint32_t pos = atomicAdd(&rhist[dig[j]], 1u);
+                    store_rec<NW>(R + (size_t)pos * NW, load_rec<NW>(A + (size_t)i * NW));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P5: dedup + sort each bin's residual (tiny), count distinct keys per bin
+        uint32_t dloc[BPT];
+        uint32_t dsum = 0;
+        if (!bad) {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                dloc[q] = 0;
+                if (b0 + q >= nb || rep[b0 + q] == 0xffffffffu) continue;
+                const uint32_t bs = rstart[b0 + q], be = rstart[b0 + q + 1];
+                uint32_t d = 0;
+                if (be - bs == 1) { rcnt[bs] = 1; d = 1; }
+                else if (be > bs) {
+                    uint32_t rem_end = be, p = bs, work = 0;
+                    while (p < rem_end) {
+                        const Kmer<NW> key = load_rec<NW>(R + (size_t)p * NW);
+                        uint32_t c = 1, w = p + 1;
+                        for (uint32_t j = p + 1; j < rem_end; ++j) {
+                            const Kmer<NW> x = load_rec<NW>(R + (size_t)j * NW);
+                            if (kmer_eq<NW>(x, key)) ++c;
+                            else { if (w != j) store_rec<NW>(R + (size_t)w * NW, x); ++w; }
+                        }
+                        work += rem_end - p;
+                        rcnt[p] = (uint16_t)c;
+                        rem_end = w;
+                        ++p;
+                        if (work > 1024u || p - bs > 16u) { bad = true; break; }
+                    }
+                    if (bad) break;
+                    d = p - bs;
+                    for (uint32_t a = bs + 1; a < bs + d; ++a) {
+                        const Kmer<NW> key = load_rec<NW>(R + (size_t)a * NW);
+                        const uint16_t kc = rcnt[a];
+                        uint32_t z = a;
+                        while (z > bs && kmer_word_cmp<NW>(load_rec<NW>(R + (size_t)(z - 1) * NW), key) > 0) {
+                            store_rec<NW>(R + (size_t)z * NW, load_rec<NW>(R + (size_t)(z - 1) * NW));
+                            rcnt[z] = rcnt[z - 1];
+                            --z;
+                        }
+                        store_rec<NW>(R + (size_t)z * NW, key);
+                        rcnt[z] = kc;
+                    }
+                }
+                dloc[q] = d + 1;
+                dsum += d + 1;
+            }
+        }
+        if (bad) s_flag = 1;
+        __syncthreads();
+        if (s_flag) {
+            // exact fallback: LSD radix over every remaining key bit (scratch = the partner buffer's region), run-length unique
+            if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
+            __syncthreads();
+            uint64_t *S = lsd_sort_range<NW>(A, gpartner, n, K, lo, total_bits, lsdcnt, tot);
+            if (S != A) {
+                for (uint32_t i = threadIdx.x; i < n * NW; i += kSThreads) A[i] = S[i];
+                __syncthreads();
+            }
+            uint32_t *heads = rep;      // the sort is done: the 3*kBins u32 of rep/repcnt/rhist (>= CAP+1) are free
+            __syncthreads();
+            const uint32_t per = (n + kSThreads - 1) / kSThreads;
+            const uint32_t i0 = threadIdx.x * per, i1 = min(n, i0 + per);
+            uint32_t nh = 0;
+            for (uint32_t i = i0; i < i1; ++i)
+                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(A + (size_t)(i - 1) * NW), load_rec<NW>(A + (size_t)i * NW)) != 0) ++nh;
+            uint32_t hinc = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, hinc, o);
+                if (lane >= o) hinc += t;
+            }
+            if (lane == 31) tot[warp] = hinc;
+            __syncthreads();
+            uint32_t hb = 0, all = 0;
+            for (int w = 0; w < kSWarps; ++w) { if (w < warp) hb += tot[w]; all += tot[w]; }
+            uint32_t j = hb + hinc - nh;
+            for (uint32_t i = i0; i < i1; ++i)
+                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(A + (size_t)(i - 1) * NW), load_rec<NW>(A + (size_t)i * NW)) != 0) heads[j++] = i;
+            if (threadIdx.x == 0) { heads[all] = n; ndist[si] = all; }
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; q < all; q += kSThreads) {
+                const uint32_t h = heads[q];
+                store_rec<NW>(gsrc + (size_t)q * NW, load_rec<NW>(A + (size_t)h * NW));
+                gcnt[q] = heads[q + 1] - h;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- P6: output offsets, then every thread writes its bins in key order (representative merged into the residual list)
+        uint32_t dinc = dsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, dinc, o);
+            if (lane >= o) dinc += t;
+        }
+        if (lane == 31) tot[warp] = dinc;
+        __syncthreads();
+        uint32_t db = 0, all = 0;
+        for (int w = 0; w < kSWarps; ++w) { if (w < warp) db += tot[w]; all += tot[w]; }
+        uint32_t o = db + dinc - dsum;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            if (!dloc[q]) continue;
+            const uint32_t b = b0 + q;
+            const Kmer<NW> rk = load_rec<NW>(A + (size_t)rep[b] * NW);
+            const uint32_t rc = repcnt[b] + 1;
+            const uint32_t bs = rstart[b], d = dloc[q] - 1;
+            bool placed = false;
+            for (uint32_t z = 0; z < d; ++z) {
+                const Kmer<NW> x = load_rec<NW>(R + (size_t)(bs + z) * NW);
+                if (!placed && kmer_word_cmp<NW>(rk, x) < 0) {
+                    store_rec<NW>(gsrc + (size_t)o * NW, rk); gcnt[o] = rc; ++o; placed = true;
+                }
+                store_rec<NW>(gsrc + (size_t)o * NW, x); gcnt[o] = rcnt[bs + z]; ++o;
+            }
+            if (!placed) { store_rec<NW>(gsrc + (size_t)o * NW, rk); gcnt[o] = rc; ++o; }
+        }
+        if (threadIdx.x == 0) ndist[si] = all;
+        __syncthreads();
+    }
+}
+
 // compaction: one warp per segment copies its distinct records / counts to the dense output
 template <int NW>
 __global__ void compact_k(const Seg *__restrict__ segs, uint64_t nsegs, const uint32_t *__restrict__ ndist, const uint64_t *__restrict__ dbase,
@@ -559,6 +995,19 @@ struct Timer {
     float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
+struct Trace {
+    bool on; cudaStream_t st; double t0;
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    Trace(cudaStream_t s) : on(getenv("SGPU_TRACE") != nullptr), st(s), t0(now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        double t = now();
+        fprintf(stderr, "[sgpu-trace] %-28s %9.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+
 static int ilog2_floor(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
 
 template <int NW, class Src>
@@ -567,19 +1016,21 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
     constexpr int CAP = SortCfg<NW>::CAP;
     const uint32_t TARGET = CAP * 3 / 8;
     const int total_bits = 2 * K;
-    const int G = ctx->num_sms * 2;
-    const uint32_t PA_MAX = 4096;
+    // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
+    // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
+    const int G = getenv("SGPU_A_CTAS_PER_SM") ? ctx->num_sms * atoi(getenv("SGPU_A_CTAS_PER_SM")) : ctx->num_sms;
+    const uint32_t PA_MAX = getenv("SGPU_PA_MAX") ? (uint32_t)atoi(getenv("SGPU_PA_MAX")) : 2048;
     const size_t W = 8 * NW;
     cudaStream_t st = ctx->stream;
     Timer tm(st);
+    Trace tr(st);
 
     out->bsz.assign(B, 0);
     DArr<unsigned long long> d_bsz(ctx, B);
     SG_CUDA(cudaMemsetAsync(d_bsz.p, 0, B * sizeof(unsigned long long), st));
 
     // pass planning: records of a pass must fit twice (ping-pong) next to what is already resident
-    size_t free_b = 0, total_b = 0;
-    SG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = ctx->free_bytes();
     size_t budget = ctx->hbm_budget ? ctx->hbm_budget : (size_t)(free_b * 0.90);
     int npass = 1;
     {
@@ -641,9 +1092,10 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         SG_CUDA(cudaMemcpyAsync(&I, part_start.p + PA, 8, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
         ctx->times.extract_count += tm.stop();
+        tr.mark("A1 count+totals");
         // does the pass fit?  X + Y + (worst case) all-distinct output
         {
-            SG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            free_b = ctx->free_bytes();
             size_t lim = ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(free_b * 0.92);
             double need = (double)I * W * 2.0 + (double)I * (W + 4) * 0.6 + (64 << 20);
             if (need > (double)lim && nb > 1) {
@@ -657,6 +1109,7 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         ctx->times.instances += I;
         // ---- A2: scatter
         DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
+        tr.mark("alloc X,Y");
         {
             DArr<uint64_t> base(ctx, (size_t)G * PA);
             levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p, PA, G, part_start.p, base.p);
@@ -671,6 +1124,7 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             }
             SG_CUDA(cudaGetLastError());
             ctx->times.extract_scatter += tm.stop();
+            tr.mark("A2 scatter");
         }
         blk_counts.release();
         // ---- segments + refinement rounds
@@ -694,9 +1148,11 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             SG_CUDA(cudaMemcpyAsync(&tot[0], cbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaMemcpyAsync(&tot[1], wpos.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
             SG_CUDA(cudaStreamSynchronize(st));
+            tr.mark("refine plan+scans");
             if (tot[1] == 0) break;
             DArr<Seg> nsegs_arr(ctx, tot[0]);
             DArr<uint64_t> worklist(ctx, tot[1]);
+            tr.mark("refine allocs");
             refine_copy_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, isw.p, cbase.p, wpos.p, nsegs_arr.p, worklist.p);
             ctx->launches++;
             SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
@@ -705,10 +1161,12 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
             SG_CUDA(cudaStreamSynchronize(st));
+            tr.mark("refine kernel");
             segs = std::move(nsegs_arr);
             nsegs = tot[0];
         }
         ctx->times.refine += tm.stop();
+        tr.mark("refine end");
         // ---- local sort
         DArr<uint32_t> ndist(ctx, nsegs + 1);
         DArr<unsigned long long> stats(ctx, 4);
@@ -717,14 +1175,15 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
         tm.start();
         {
-            size_t smem = (size_t)2 * CAP * NW * sizeof(uint64_t);
-            SG_CUDA(cudaFuncSetAttribute(local_sort_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * kBins * sizeof(uint32_t) +
+                          ((size_t)kBins + 2 + kResCap) * sizeof(uint16_t) + 16;
+            SG_CUDA(cudaFuncSetAttribute(local_sort3_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;
-            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, local_sort_k<NW>, kSThreads, smem));
+            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, local_sort3_k<NW>, kSThreads, smem));
             if (occ < 1) occ = 1;
             int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
             if (grid < 1) grid = 1;
-            local_sort_k<NW><<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+            local_sort3_k<NW><<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
         }
@@ -736,6 +1195,7 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         SG_CUDA(cudaMemcpyAsync(h_stats, stats.p, 32, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
         ctx->times.local_sort += tm.stop();
+        tr.mark("local sort");
         SG_CHECK(h_stats[0] == 0, 6, "internal: oversize segment with unfixed key bits reached the local sort");
         // ---- compaction into the dense chunk
         Chunk ch;
@@ -750,9 +1210,11 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             SG_CUDA(cudaGetLastError());
         }
         ctx->times.compact += tm.stop();
+        tr.mark("compact");
         first += (int64_t)D;
         out->chunks.push_back(std::move(ch));
         ++ti;
+        tr.mark("pass end (before frees)");
     }
     std::vector<unsigned long long> hb(B);
     SG_CUDA(cudaMemcpyAsync(hb.data(), d_bsz.p, B * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -44,14 +44,15 @@ template <class T>
 struct DArr {
     T *p = nullptr;
     size_t n = 0;
+    size_t blk = 0;     // bytes of the underlying block
     Ctx *ctx = nullptr;
     DArr() {}
     DArr(Ctx *c, size_t n_) { alloc(c, n_); }
     DArr(const DArr &) = delete;
     DArr &operator=(const DArr &) = delete;
-    DArr(DArr &&o) noexcept { p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; }
+    DArr(DArr &&o) noexcept { p = o.p; n = o.n; blk = o.blk; ctx = o.ctx; o.p = nullptr; o.n = 0; o.blk = 0; }
     DArr &operator=(DArr &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; blk = o.blk; ctx = o.ctx; o.p = nullptr; o.n = 0; o.blk = 0; }
         return *this;
     }
     ~DArr() { release(); }
@@ -89,30 +90,77 @@ struct Ctx {
     std::vector<uint64_t> h_words, h_offs;   // host staging until first use
     std::vector<uint32_t> h_lens;
     bool staged_dirty = false;
+    // caching device allocator: freed blocks are kept for reuse (a bench step repeats the same sizes), and are
+    // handed back to the driver only under memory pressure or when the context dies
+    std::vector<std::pair<void *, size_t>> pool_free;
+    size_t pool_cached = 0;
+    void *pool_alloc(size_t bytes, size_t *blk);
+    void pool_release(void *p, size_t blk);
+    void pool_trim();
+    size_t free_bytes();     // driver-free + cached
 };
+
+inline void Ctx::pool_trim() {
+    for (auto &b : pool_free) cudaFree(b.first);
+    pool_free.clear();
+    pool_cached = 0;
+}
+inline size_t Ctx::free_bytes() {
+    size_t f = 0, t = 0;
+    cudaMemGetInfo(&f, &t);
+    return f + pool_cached;
+}
+inline void *Ctx::pool_alloc(size_t bytes, size_t *blk) {
+    size_t want = (bytes + 511) & ~(size_t)511;
+    int best = -1;
+    for (int i = 0; i < (int)pool_free.size(); ++i) {
+        size_t sz = pool_free[i].second;
+        if (sz >= want && sz <= want + want / 4 + (1 << 20) && (best < 0 || sz < pool_free[best].second)) best = i;
+    }
+    if (best >= 0) {
+        void *p = pool_free[best].first;
+        *blk = pool_free[best].second;
+        pool_cached -= *blk;
+        pool_free.erase(pool_free.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char m[256];
+        snprintf(m, sizeof m, "cudaMalloc(%zu bytes) failed: %s (resident %zu)", want, cudaGetErrorString(e), allocated);
+        throw Error(4, m);
+    }
+    *blk = want;
+    return p;
+}
+inline void Ctx::pool_release(void *p, size_t blk) {
+    pool_free.push_back({p, blk});
+    pool_cached += blk;
+}
 
 template <class T>
 void DArr<T>::alloc(Ctx *c, size_t n_) {
     release();
     ctx = c; n = n_;
     size_t b = (n_ ? n_ : 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void **)&p, b);
-    if (e != cudaSuccess) {
-        p = nullptr; n = 0;
-        char m[256];
-        snprintf(m, sizeof m, "cudaMalloc(%zu bytes) failed: %s (resident %zu)", b, cudaGetErrorString(e), c ? c->allocated : 0);
-        cudaGetLastError();
-        throw Error(4, m);
-    }
-    if (c) { c->allocated += b; if (c->allocated > c->peak) c->peak = c->allocated; }
+    p = (T *)c->pool_alloc(b, &blk);
+    c->allocated += blk;
+    if (c->allocated > c->peak) c->peak = c->allocated;
 }
 template <class T>
 void DArr<T>::release() {
     if (p) {
-        cudaFree(p);
-        if (ctx) ctx->allocated -= (n ? n : 1) * sizeof(T);
+        ctx->allocated -= blk;
+        ctx->pool_release(p, blk);
     }
-    p = nullptr; n = 0;
+    p = nullptr; n = 0; blk = 0;
 }
 
 // A counted k-mer set resident in HBM: what KMerDiskCounter::Count leaves on disk
