@@ -277,15 +277,20 @@ def main():
     # ---- e2e: host buffers in, host result out
     h_words = words[:nwords].cpu().pin_memory(); h_offs = offs.cpu().pin_memory(); h_lens = lens.cpu().pin_memory()
     d2h = 0
+    h_index = None     # pinned host buffer the serialized KMerIndex lands in
+    h_bsz = np.zeros(B, np.int64)
 
     def step_e2e():
-        nonlocal d2h
+        nonlocal d2h, h_index
         ctx.upload_reads(h_words.data_ptr(), nwords, h_offs.data_ptr(), h_lens.data_ptr(), n_reads)
         st = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
         idx = KMerIndexBuilder(ctx).BuildIndex(st)
-        ser = idx.serialize()
-        bsz = st.bucket_sizes()
-        d2h = len(ser) + bsz.nbytes
+        need = idx.serialized_size()
+        if h_index is None or h_index.numel() < need:
+            h_index = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8).pin_memory()
+        nser = idx.serialize_into(h_index.data_ptr(), h_index.numel())
+        h_bsz[:] = st.bucket_sizes()
+        d2h = nser + h_bsz.nbytes
         idx.free(); st.free()
 
     step_e2e()

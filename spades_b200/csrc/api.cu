@@ -11,7 +11,7 @@ using namespace sg;
 
 struct sgpu_ctx { Ctx c; bool own_stream = true; };
 struct sgpu_kset { KSet *s; };
-struct sgpu_mphf { Mphf *m; std::vector<uint8_t> ser; bool have_ser = false; };
+struct sgpu_mphf { Mphf *m; };
 struct sgpu_graph { Graph *g; };
 
 static int fail(Ctx *c, int code, const std::string &msg) {
@@ -238,25 +238,16 @@ int sgpu_mphf_build(sgpu_ctx *ctx, const sgpu_kset *s, sgpu_mphf **out) {
     API_TRY(c, {
         SG_CUDA(cudaSetDevice(c->device));
         Mphf *m = mphf_build(c, s->s);
-        *out = new sgpu_mphf{m, {}, false};
+        *out = new sgpu_mphf{m};
     })
 }
-static void ensure_ser(sgpu_mphf *m) {
-    if (!m->have_ser) { m->ser = mphf_serialize(m->m); m->have_ser = true; }
-}
-int64_t sgpu_mphf_serialized_size(const sgpu_mphf *m) {
-    if (!m) return -1;
-    try { cudaSetDevice(m->m->ctx->device); ensure_ser(const_cast<sgpu_mphf *>(m)); return (int64_t)m->ser.size(); }
-    catch (const std::exception &e) { m->m->ctx->err = e.what(); return -1; }
-}
+int64_t sgpu_mphf_serialized_size(const sgpu_mphf *m) { return m ? (int64_t)mphf_serialized_size(m->m) : -1; }
 int sgpu_mphf_serialize(const sgpu_mphf *m, uint8_t *out, int64_t cap) {
-    if (!m || !out) return SGPU_EINVAL;
+    if (!m || !out || cap < 0) return SGPU_EINVAL;
     Ctx *c = m->m->ctx;
     API_TRY(c, {
         SG_CUDA(cudaSetDevice(c->device));
-        ensure_ser(const_cast<sgpu_mphf *>(m));
-        SG_CHECK((int64_t)m->ser.size() <= cap, SGPU_EINVAL, "output buffer too small");
-        memcpy(out, m->ser.data(), m->ser.size());
+        mphf_serialize_to(m->m, out, (size_t)cap);
     })
 }
 int sgpu_mphf_lookup(const sgpu_mphf *m, const uint64_t *keys, int64_t n, uint64_t *out_idx) {

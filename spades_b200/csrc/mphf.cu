@@ -244,16 +244,33 @@ Mphf *mphf_build(Ctx *ctx, const KSet *ks) {
     return m;
 }
 
-// KMerIndex::serialize (kmer_index.hpp:102-108) -> mphf::save (BooPHF.h:514-535) -> bitVector::save (:316-323)
-std::vector<uint8_t> mphf_serialize(const Mphf *m) {
-    Ctx *ctx = m->ctx;
-    const int B = m->B;
-    std::vector<uint64_t> hbits(m->total_words + 8), hranks(m->total_words / 8 + 1);
-    if (m->total_words) {
-        SG_CUDA(cudaMemcpyAsync(hbits.data(), m->bits.p, m->total_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        SG_CUDA(cudaMemcpyAsync(hranks.data(), m->ranks.p, (m->total_words / 8) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        SG_CUDA(cudaStreamSynchronize(ctx->stream));
+// KMerIndex::serialize (kmer_index.hpp:102-108) -> mphf::save (BooPHF.h:514-535) -> bitVector::save (:316-323).
+// The byte image is assembled ON THE DEVICE (piece copies + scalar patches) and leaves in one device->host copy straight
+// into the caller's buffer (pinned buffers get the full PCIe rate). Fields are only 4-byte aligned (28-byte bucket header).
+struct SerPiece { uint64_t src_word; uint64_t dst_byte; uint64_t nwords; uint32_t from_ranks; uint32_t pad; };
+struct SerPatch { uint64_t dst_byte; uint64_t value; uint32_t nbytes; uint32_t pad; };
+
+__global__ void ser_pieces_k(const SerPiece *__restrict__ pieces, const uint64_t *__restrict__ bits, const uint64_t *__restrict__ ranks,
+                             uint32_t *__restrict__ img32) {
+    const SerPiece p = pieces[blockIdx.x];
+    const uint64_t *src = (p.from_ranks ? ranks : bits) + p.src_word;
+    uint32_t *dst = img32 + (p.dst_byte >> 2);
+    for (uint64_t i = threadIdx.x; i < p.nwords; i += blockDim.x) {
+        const uint64_t v = src[i];
+        dst[2 * i] = (uint32_t)v;
+        dst[2 * i + 1] = (uint32_t)(v >> 32);
     }
+}
+__global__ void ser_patches_k(const SerPatch *__restrict__ patches, uint64_t n, uint32_t *__restrict__ img32) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SerPatch p = patches[i];
+    img32[p.dst_byte >> 2] = (uint32_t)p.value;
+    if (p.nbytes == 8) img32[(p.dst_byte >> 2) + 1] = (uint32_t)(p.value >> 32);
+}
+
+size_t mphf_serialized_size(const Mphf *m) {
+    const int B = m->B;
     size_t total = 8;
     for (int b = 0; b < B; ++b) {
         total += 28 + 8;
@@ -263,32 +280,53 @@ std::vector<uint8_t> mphf_serialize(const Mphf *m) {
                 total += 16 + 8 * m->nchar[p] + 8 + 8 * ((m->nchar[p] + 7) / 8);
             }
     }
-    total += 8 * ((size_t)B + 1);
-    std::vector<uint8_t> out(total);
+    return total + 8 * ((size_t)B + 1);
+}
+
+void mphf_serialize_to(const Mphf *m, uint8_t *out, size_t cap) {
+    Ctx *ctx = m->ctx;
+    const int B = m->B;
+    const size_t total = mphf_serialized_size(m);
+    SG_CHECK(total <= cap, 2, "output buffer too small for the serialized index");
+    std::vector<SerPiece> pieces;
+    std::vector<SerPatch> patches;
     size_t pos = 0;
-    auto put = [&](const void *src, size_t nbytes) { memcpy(out.data() + pos, src, nbytes); pos += nbytes; };
-    uint64_t nseg = (uint64_t)B;
-    put(&nseg, 8);
+    auto patch = [&](uint64_t v, uint32_t nbytes) { patches.push_back(SerPatch{pos, v, nbytes, 0}); pos += nbytes; };
+    patch((uint64_t)B, 8);
     for (int b = 0; b < B; ++b) {
-        double gamma = 4.0; int nl = kLevels; uint64_t nelem = (uint64_t)m->bsz[b];
-        uint64_t lr = nelem ? m->lastrank[b] : 0;     // the reference leaves this field uninitialised for empty buckets
-        put(&gamma, 8); put(&nl, 4); put(&lr, 8); put(&nelem, 8);
+        const double gamma = 4.0; uint64_t gbits; memcpy(&gbits, &gamma, 8);
+        const uint64_t nelem = (uint64_t)m->bsz[b];
+        patch(gbits, 8); patch((uint64_t)kLevels, 4);
+        patch(nelem ? m->lastrank[b] : 0, 8);     // the reference leaves this field uninitialised for empty buckets
+        patch(nelem, 8);
         if (nelem) {
             for (int l = 0; l < kLevels; ++l) {
                 const size_t p = (size_t)l * B + b;
-                uint64_t nr = (m->nchar[p] + 7) / 8;
-                put(&m->dom[p], 8); put(&m->nchar[p], 8);
-                put(hbits.data() + m->woff[p], 8 * m->nchar[p]);
-                put(&nr, 8);
-                put(hranks.data() + (m->woff[p] >> 3), 8 * nr);
+                const uint64_t nr = (m->nchar[p] + 7) / 8;
+                patch(m->dom[p], 8); patch(m->nchar[p], 8);
+                pieces.push_back(SerPiece{m->woff[p], pos, m->nchar[p], 0, 0}); pos += 8 * m->nchar[p];
+                patch(nr, 8);
+                pieces.push_back(SerPiece{m->woff[p] >> 3, pos, nr, 1, 0}); pos += 8 * nr;
             }
         }
-        uint64_t nfinal = 0;
-        put(&nfinal, 8);
+        patch(0, 8);                                // final-hash map size (must be empty, checked at build time)
     }
-    put(m->starts.data(), 8 * ((size_t)B + 1));
+    for (int i = 0; i <= B; ++i) patch(m->starts[i], 8);
     SG_CHECK(pos == total, 6, "internal: serialized size mismatch");
-    return out;
+    DArr<uint32_t> img(ctx, total / 4 + 2);
+    DArr<SerPiece> dp(ctx, pieces.size() + 1);
+    DArr<SerPatch> dq(ctx, patches.size() + 1);
+    if (!pieces.empty()) SG_CUDA(cudaMemcpyAsync(dp.p, pieces.data(), pieces.size() * sizeof(SerPiece), cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(cudaMemcpyAsync(dq.p, patches.data(), patches.size() * sizeof(SerPatch), cudaMemcpyHostToDevice, ctx->stream));
+    if (!pieces.empty()) {
+        ser_pieces_k<<<(unsigned)pieces.size(), 256, 0, ctx->stream>>>(dp.p, m->bits.p, m->ranks.p, img.p);
+        ctx->launches++;
+    }
+    ser_patches_k<<<div_up((int64_t)patches.size(), 256), 256, 0, ctx->stream>>>(dq.p, patches.size(), img.p);
+    ctx->launches++;
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(out, img.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 void mphf_lookup_host_keys(Ctx *ctx, const Mphf *m, const uint64_t *h_keys, int64_t n, uint64_t *h_out) {

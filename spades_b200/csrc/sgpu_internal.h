@@ -212,7 +212,8 @@ KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B);
 
 // mphf.cu
 Mphf *mphf_build(Ctx *ctx, const KSet *ks);
-std::vector<uint8_t> mphf_serialize(const Mphf *m);
+size_t mphf_serialized_size(const Mphf *m);
+void mphf_serialize_to(const Mphf *m, uint8_t *out, size_t cap);
 void mphf_lookup_host_keys(Ctx *ctx, const Mphf *m, const uint64_t *h_keys, int64_t n, uint64_t *h_out);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -180,6 +180,15 @@ class KMerIndex:
         self.ctx.check(self.ctx.L.sgpu_mphf_serialize(self.h, _p(buf), n))
         return buf.tobytes()
 
+    def serialized_size(self) -> int:
+        return int(self.ctx.L.sgpu_mphf_serialized_size(self.h))
+
+    def serialize_into(self, host_ptr, cap):
+        """KMerIndex::serialize bytes written to caller memory (e.g. a pinned buffer); returns the size."""
+        n = self.serialized_size()
+        self.ctx.check(self.ctx.L.sgpu_mphf_serialize(self.h, C.c_void_p(host_ptr), cap))
+        return n
+
     def seq_idx(self, keys):
         keys = np.ascontiguousarray(keys, np.uint64).reshape(-1, self.storage.nw)
         out = np.zeros(max(len(keys), 1), np.uint64)
