@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=int(os.environ.get("SGPU_BENCH_READS", 20_000_000)), help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("SGPU_BENCH_READS", 100_000_000)), help="reads per GPU")
     ap.add_argument("--buckets", type=int, default=0, help="0 = 10 x host threads, as the reference's graph path (construction.cpp:242)")
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,9 +233,16 @@ def main():
     ctx = Context(local_rank, stream=stream.cuda_stream)
     nwords = n_reads * nwr
 
+    def count(ctx_):
+        # N>1: buckets are owned by ranks; the exchange is fused into the partition kernel (NVLink peer stores)
+        if world > 1:
+            from spades_b200.distributed import DistributedKMerCounter
+            return DistributedKMerCounter(ctx_, K).Count(B)
+        return KMerDiskCounter(ctx_, DeBruijnReadKMerSplitter(K)).Count(B)
+
     def step_resident():
         ctx.adopt_device_reads(words.data_ptr(), nwords, offs.data_ptr(), lens.data_ptr(), n_reads)
-        st = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
+        st = count(ctx)
         idx = KMerIndexBuilder(ctx).BuildIndex(st)
         return st, idx
 
@@ -283,7 +290,7 @@ def main():
     def step_e2e():
         nonlocal d2h, h_index
         ctx.upload_reads(h_words.data_ptr(), nwords, h_offs.data_ptr(), h_lens.data_ptr(), n_reads)
-        st = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
+        st = count(ctx)
         idx = KMerIndexBuilder(ctx).BuildIndex(st)
         need = idx.serialized_size()
         if h_index is None or h_index.numel() < need:
@@ -337,6 +344,7 @@ def main():
             "config": {"workload": "synthetic %d x 150 bp reads per GPU (uniform genome %d bp, 1%% substitutions, random strand), k=55: canonical (k+1)=56-mers, "
                                    "%d XXH3 buckets, sort/unique/count + boomphf MPHF (extract+count+index)" % (n_reads, genome_len, B),
                        "k": K_GRAPH, "reads_per_gpu": n_reads, "buckets": B, "distinct_kpomers": int(distinct), "instances": int(instances), "passes": int(passes),
+                       "parallelism": ("1 GPU" if world == 1 else "%d GPUs: reads sharded, buckets owned by ranks, partition kernel stores records into the owner over NVLink peer memory" % world),
                        "l2": "inputs (%.1f GB) and intermediates larger than L2; no flush needed" % (nwords * 8 / 1e9), "peak_hbm_gb": peak / 1e9},
             "clocks": sampler.result(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mk-mers/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

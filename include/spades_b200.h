@@ -122,6 +122,29 @@ int64_t sgpu_graph_gfa(const sgpu_graph *g, const char *version, char *out, int6
 int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *path);
 void sgpu_graph_free(sgpu_graph *g);
 
+/* ---- multi-GPU count (one process per GPU). Replaces hpcspades' shared-filesystem + MPI pattern
+ * (projects/hpcspades/mpi/stages/construction_mpi.cpp:222-300, mpi/kmer_index/kmer_extension_index_builder_mpi.hpp:87,190):
+ * buckets are owned by ranks; sgpu_dist_scatter is ONE kernel that partitions this rank's reads and stores every record
+ * directly into its owner GPU's buffer over NVLink peer memory (cudaIpc mappings). The host language only moves the small
+ * tables between ranks (torch.distributed / MPI all_gather) and provides the barriers:
+ *   begin -> local_counts -> [all_gather counts] -> plan -> ipc_handle -> [all_gather handles] -> open_peers ->
+ *   for each pass: [barrier] scatter [barrier] sort   -> end (k-mer set holding this rank's buckets) */
+typedef struct sgpu_dist sgpu_dist;
+int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, int rank, sgpu_dist **out);
+int64_t sgpu_dist_num_partitions(const sgpu_dist *d);
+int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out);                 /* num_partitions host entries */
+int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_partitions, rank-major, host */, uint64_t budget_bytes,
+                   int *npass, uint64_t *exchange_records);
+int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64);                 /* 64-byte cudaIpcMemHandle of this rank's exchange buffer */
+int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x 64 bytes */);
+int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* fused partition + NVLink exchange kernel */
+int sgpu_dist_sort(sgpu_dist *d, int pass);                             /* refinement + local sort + compaction of what arrived */
+int sgpu_dist_end(sgpu_dist *d, sgpu_kset **out);
+void sgpu_dist_free(sgpu_dist *d);
+/* the planning step alone (pure host arithmetic, no GPU): returns npass and fills pass_bounds[0..npass] */
+int sgpu_dist_plan_host(int world, int num_buckets, int key_bits_in_partition, const uint64_t *all_counts, uint64_t budget_bytes,
+                        int record_bytes, int *pass_bounds, uint64_t *max_recv);
+
 /* self tests of the shared host/device arithmetic (tests only): op 0 = xxh3_64, 1 = xxh3_128 lo, 2 = xxh3_128 hi, 3 = bucket(arg),
  * 4 = is_minimal, 5.. = rc word j. keys: n records of ceil(K/32) words. on_device != 0 runs the same code in a kernel. */
 int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out);

@@ -18,6 +18,8 @@ SYMBOLS = [
     "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
     "sgpu_graph_build", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
+    "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_ipc_handle",
+    "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
     "sgpu_selftest",
 ]
 
@@ -80,6 +82,17 @@ def load():
     L.sgpu_graph_gfa.restype = i64; L.sgpu_graph_gfa.argtypes = [vp, C.c_char_p, vp, i64]
     L.sgpu_graph_write_gfa.restype = i32; L.sgpu_graph_write_gfa.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.sgpu_graph_free.restype = None; L.sgpu_graph_free.argtypes = [vp]
+    L.sgpu_dist_begin.restype = i32; L.sgpu_dist_begin.argtypes = [vp, i32, i32, i32, i32, i32, pp]
+    L.sgpu_dist_num_partitions.restype = i64; L.sgpu_dist_num_partitions.argtypes = [vp]
+    L.sgpu_dist_local_counts.restype = i32; L.sgpu_dist_local_counts.argtypes = [vp, vp]
+    L.sgpu_dist_plan.restype = i32; L.sgpu_dist_plan.argtypes = [vp, vp, u64, C.POINTER(i32), C.POINTER(u64)]
+    L.sgpu_dist_ipc_handle.restype = i32; L.sgpu_dist_ipc_handle.argtypes = [vp, vp]
+    L.sgpu_dist_open_peers.restype = i32; L.sgpu_dist_open_peers.argtypes = [vp, vp]
+    L.sgpu_dist_scatter.restype = i32; L.sgpu_dist_scatter.argtypes = [vp, i32]
+    L.sgpu_dist_sort.restype = i32; L.sgpu_dist_sort.argtypes = [vp, i32]
+    L.sgpu_dist_end.restype = i32; L.sgpu_dist_end.argtypes = [vp, pp]
+    L.sgpu_dist_free.restype = None; L.sgpu_dist_free.argtypes = [vp]
+    L.sgpu_dist_plan_host.restype = i32; L.sgpu_dist_plan_host.argtypes = [i32, i32, i32, vp, u64, i32, vp, C.POINTER(u64)]
     L.sgpu_selftest.restype = i32; L.sgpu_selftest.argtypes = [vp, i32, i32, i32, u64, vp, i64, vp]
     _lib = L
     return L

@@ -337,6 +337,62 @@ void sgpu_graph_free(sgpu_graph *g) {
 
 }  // extern "C"
 
+struct sgpu_dist { DistState *d; Ctx *c; };
+extern "C" {
+int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, int rank, sgpu_dist **out) {
+    if (!ctx || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        DistState *d = dist_begin(c, K, num_buckets, mode, world, rank);
+        *out = new sgpu_dist{d, c};
+    })
+}
+int64_t sgpu_dist_num_partitions(const sgpu_dist *d) { return d ? (int64_t)dist_num_partitions(d->d) : -1; }
+int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out) {
+    if (!d || !out) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_local_counts(d->d, out); })
+}
+int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts, uint64_t budget_bytes, int *npass, uint64_t *exchange_records) {
+    if (!d || !all_counts || !npass || !exchange_records) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_plan(d->d, all_counts, budget_bytes, npass, exchange_records); })
+}
+int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64) {
+    if (!d || !out64) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_ipc_handle(d->d, out64); })
+}
+int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles) {
+    if (!d || !handles) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_open_peers(d->d, handles); })
+}
+int sgpu_dist_scatter(sgpu_dist *d, int pass) {
+    if (!d) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_scatter(d->d, pass); })
+}
+int sgpu_dist_sort(sgpu_dist *d, int pass) {
+    if (!d) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_sort(d->d, pass); })
+}
+int sgpu_dist_end(sgpu_dist *d, sgpu_kset **out) {
+    if (!d || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); KSet *s = dist_end(d->d); *out = new sgpu_kset{s}; })
+}
+void sgpu_dist_free(sgpu_dist *d) {
+    if (!d) return;
+    cudaSetDevice(d->c->device);
+    dist_free(d->d);
+    delete d;
+}
+int sgpu_dist_plan_host(int world, int num_buckets, int key_bits_in_partition, const uint64_t *all_counts, uint64_t budget_bytes, int record_bytes,
+                        int *pass_bounds, uint64_t *max_recv) {
+    if (world < 1 || num_buckets < 1 || !all_counts || !pass_bounds || !max_recv) return -1;
+    try { return dist_plan_host(world, num_buckets, key_bits_in_partition, all_counts, budget_bytes, record_bytes, pass_bounds, max_recv); }
+    catch (...) { return -1; }
+}
+}  // extern "C"
+
 // ---- self test of kmer_dev.cuh on host and device -----------------------------------------------------------------------
 template <int NW>
 __host__ __device__ uint64_t selftest_one(int op, int K, uint64_t arg, const uint64_t *key) {

@@ -193,14 +193,14 @@ __global__ void levelA_totals_k(const uint32_t *__restrict__ blk_counts, uint32_
     for (int g = 0; g < G; ++g) s += blk_counts[(size_t)g * PA + part];
     part_total[part] = s;
 }
-__global__ void levelA_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t PA, int G, const uint64_t *__restrict__ part_start,
-                               uint64_t *__restrict__ base) {
+__global__ void levelA_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t stride, uint32_t PA, int G,
+                               const uint64_t *__restrict__ part_start, uint64_t *__restrict__ base) {
     uint32_t part = blockIdx.x * blockDim.x + threadIdx.x;
     if (part >= PA) return;
     uint64_t run = part_start[part];
     for (int g = 0; g < G; ++g) {
         base[(size_t)g * PA + part] = run;
-        run += blk_counts[(size_t)g * PA + part];
+        run += blk_counts[(size_t)g * stride + part];
     }
 }
 
@@ -1010,127 +1010,18 @@ struct Trace {
 
 static int ilog2_floor(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
 
-template <int NW, class Src>
-static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
-                             KSet *out) {
+template <int NW>
+static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, const uint64_t *part_start_p, const uint64_t *part_total_p, uint32_t PA,
+                      int rA_, uint32_t b_lo, int b_hi, int64_t first, bool want_counts, bool double_selfrc, unsigned long long *d_bsz_p, Chunk &ch_out,
+                      Timer &tm, Trace &tr) {
     constexpr int CAP = SortCfg<NW>::CAP;
     const uint32_t TARGET = CAP * 3 / 8;
     const int total_bits = 2 * K;
-    // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
-    // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
-    const int G = getenv("SGPU_A_CTAS_PER_SM") ? ctx->num_sms * atoi(getenv("SGPU_A_CTAS_PER_SM")) : ctx->num_sms;
-    const uint32_t PA_MAX = getenv("SGPU_PA_MAX") ? (uint32_t)atoi(getenv("SGPU_PA_MAX")) : 2048;
-    const size_t W = 8 * NW;
     cudaStream_t st = ctx->stream;
-    Timer tm(st);
-    Trace tr(st);
-
-    out->bsz.assign(B, 0);
-    DArr<unsigned long long> d_bsz(ctx, B);
-    SG_CUDA(cudaMemsetAsync(d_bsz.p, 0, B * sizeof(unsigned long long), st));
-
-    // pass planning: records of a pass must fit twice (ping-pong) next to what is already resident
-    size_t free_b = ctx->free_bytes();
-    size_t budget = ctx->hbm_budget ? ctx->hbm_budget : (size_t)(free_b * 0.90);
-    int npass = 1;
-    {
-        // results (distinct keys + counts) accumulate; assume <= 60% of the instances stay (refined per pass below)
-        double per_pass = 2.0 * (double)est_records * W;
-        double avail = (double)budget * 0.55;
-        if (per_pass > avail) npass = (int)(per_pass / avail) + 1;
-        if (npass > B) npass = B;
-    }
-    std::vector<std::pair<int, int>> todo;     // bucket ranges, processed in order
-    for (int p = 0; p < npass; ++p) {
-        int lo = (int)((int64_t)B * p / npass), hi = (int)((int64_t)B * (p + 1) / npass);
-        if (hi > lo) todo.push_back({lo, hi});
-    }
-    int64_t first = 0;
-    size_t ti = 0;
-    while (ti < todo.size()) {
-        const int b_lo = todo[ti].first, b_hi = todo[ti].second;
-        const uint32_t nb = (uint32_t)(b_hi - b_lo);
-        LevelA pa;
-        pa.K = K; pa.B = (uint32_t)B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi;
-        // rA: enough level-A partitions that level-A segments are small multiples of the local capacity,
-        // bounded by shared memory (PA_MAX) and by the key length
-        {
-            uint64_t est_pass = est_records * nb / (uint64_t)B + 1;
-            int want = ilog2_floor(est_pass / TARGET + 1) + 1;              // total fan-out bits wanted
-            int bbits = ilog2_floor(nb) + (((1u << ilog2_floor(nb)) < nb) ? 1 : 0);
-            int rA = want - bbits;
-            if (rA < 0) rA = 0;
-            while (rA > 0 && ((uint64_t)nb << rA) > PA_MAX) --rA;
-            if (rA > total_bits) rA = total_bits;
-            if (rA > 24) rA = 24;
-            pa.rA = rA;
-            pa.PA = nb << rA;
-        }
-        if (pa.PA > 8192) {   // too many buckets for one pass's shared-memory histogram: split the range
-            int mid = b_lo + (b_hi - b_lo) / 2;
-            todo[ti] = {b_lo, mid};
-            todo.insert(todo.begin() + ti + 1, {mid, b_hi});
-            continue;
-        }
-        const uint32_t PA = pa.PA;
-        // ---- A1: count
-        DArr<uint32_t> blk_counts(ctx, (size_t)G * PA);
-        SG_CUDA(cudaMemsetAsync(blk_counts.p, 0, blk_counts.bytes(), st));
-        tm.start();
-        for (const Src &src : srcs) {
-            if (src.n == 0) continue;
-            levelA_count_k<NW, Src><<<G, kAThreads, PA * sizeof(uint32_t), st>>>(src, pa, blk_counts.p);
-            ctx->launches++;
-        }
-        SG_CUDA(cudaGetLastError());
-        DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1);
-        levelA_totals_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p, PA, G, part_total.p);
-        ctx->launches++;
-        SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
-        exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
-        uint64_t I = 0;
-        SG_CUDA(cudaMemcpyAsync(&I, part_start.p + PA, 8, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaStreamSynchronize(st));
-        ctx->times.extract_count += tm.stop();
-        tr.mark("A1 count+totals");
-        // does the pass fit?  X + Y + (worst case) all-distinct output
-        {
-            free_b = ctx->free_bytes();
-            size_t lim = ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(free_b * 0.92);
-            double need = (double)I * W * 2.0 + (double)I * (W + 4) * 0.6 + (64 << 20);
-            if (need > (double)lim && nb > 1) {
-                int mid = b_lo + (b_hi - b_lo) / 2;
-                todo[ti] = {b_lo, mid};
-                todo.insert(todo.begin() + ti + 1, {mid, b_hi});
-                continue;
-            }
-        }
-        ctx->times.passes++;
-        ctx->times.instances += I;
-        // ---- A2: scatter
-        DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
-        tr.mark("alloc X,Y");
-        {
-            DArr<uint64_t> base(ctx, (size_t)G * PA);
-            levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p, PA, G, part_start.p, base.p);
-            ctx->launches++;
-            tm.start();
-            size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
-            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            for (const Src &src : srcs) {
-                if (src.n == 0) continue;
-                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p);
-                ctx->launches++;
-            }
-            SG_CUDA(cudaGetLastError());
-            ctx->times.extract_scatter += tm.stop();
-            tr.mark("A2 scatter");
-        }
-        blk_counts.release();
         // ---- segments + refinement rounds
         uint64_t nsegs = PA;
         DArr<Seg> segs(ctx, nsegs);
-        seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start.p, part_total.p, PA, pa.rA, (uint32_t)b_lo, segs.p);
+        seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start_p, part_total_p, PA, rA_, b_lo, segs.p);
         ctx->launches++;
         RefinePlan rp; rp.cap = CAP; rp.target = TARGET; rp.rmax = 11; rp.total_bits = total_bits;
         DArr<unsigned long long> wcounter(ctx, 4);
@@ -1199,22 +1090,130 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         SG_CHECK(h_stats[0] == 0, 6, "internal: oversize segment with unfixed key bits reached the local sort");
         // ---- compaction into the dense chunk
         Chunk ch;
-        ch.n = (int64_t)D; ch.b_lo = b_lo; ch.b_hi = b_hi; ch.first = first;
+        ch.n = (int64_t)D; ch.b_lo = (int)b_lo; ch.b_hi = b_hi; ch.first = first;
         ch.keys.alloc(ctx, (size_t)D * NW + 2);
         if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1);
         tm.start();
         if (nsegs) {
             compact_k<NW><<<div_up((int64_t)nsegs * 32, 256), 256, 0, st>>>(segs.p, nsegs, ndist.p, dbase.p, X.p, Y.p, K, want_counts ? 1 : 0,
-                                                                         double_selfrc ? 1 : 0, ch.keys.p, ch.counts.p, d_bsz.p);
+                                                                         double_selfrc ? 1 : 0, ch.keys.p, ch.counts.p, d_bsz_p);
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
         }
         ctx->times.compact += tm.stop();
         tr.mark("compact");
-        first += (int64_t)D;
+        ch_out = std::move(ch);
+}
+
+template <int NW, class Src>
+static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
+                             KSet *out) {
+    constexpr int CAP = SortCfg<NW>::CAP;
+    const uint32_t TARGET = CAP * 3 / 8;
+    const int total_bits = 2 * K;
+    // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
+    // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
+    const int G = getenv("SGPU_A_CTAS_PER_SM") ? ctx->num_sms * atoi(getenv("SGPU_A_CTAS_PER_SM")) : ctx->num_sms * 2;
+    const uint32_t PA_MAX = getenv("SGPU_PA_MAX") ? (uint32_t)atoi(getenv("SGPU_PA_MAX")) : 4096;
+    const size_t W = 8 * NW;
+    cudaStream_t st = ctx->stream;
+    Timer tm(st);
+    Trace tr(st);
+
+    out->bsz.assign(B, 0);
+    DArr<unsigned long long> d_bsz(ctx, B);
+    SG_CUDA(cudaMemsetAsync(d_bsz.p, 0, B * sizeof(unsigned long long), st));
+
+    // ---- level-A geometry for the whole job. Partition id = (bucket, top rA key bits). ONE histogram pass over the
+    // source serves every bucket-group pass (the groups are contiguous partition ranges), so a multi-pass job hashes
+    // the source npass+1 times instead of 2*npass times, and passes are planned from exact per-bucket record counts.
+    int rA = 0;
+    {
+        int want = ilog2_floor(est_records / TARGET + 1) + 1;               // total fan-out bits wanted
+        int bbits = ilog2_floor((uint64_t)B) + (((1u << ilog2_floor((uint64_t)B)) < (uint32_t)B) ? 1 : 0);
+        rA = want - bbits;
+        if (rA < 0) rA = 0;
+        while (rA > 0 && ((uint64_t)B << rA) > PA_MAX) --rA;
+        if (rA > total_bits) rA = total_bits;
+        if (rA > 24) rA = 24;
+    }
+    const int SR = 8192 >> rA;                 // buckets per histogram super-range (shared-memory histogram <= 8192 bins)
+    int64_t first = 0;
+    for (int s_lo = 0; s_lo < B; s_lo += SR) {
+    const int s_hi = std::min(B, s_lo + SR);
+    LevelA pa_all;
+    pa_all.K = K; pa_all.B = (uint32_t)B; pa_all.b_lo = (uint32_t)s_lo; pa_all.b_hi = (uint32_t)s_hi; pa_all.rA = rA;
+    pa_all.PA = (uint32_t)(s_hi - s_lo) << rA;
+    const uint32_t PA_all = pa_all.PA;
+    DArr<uint32_t> blk_counts(ctx, (size_t)G * PA_all);
+    DArr<uint64_t> part_total_all(ctx, (size_t)PA_all + 1);
+    std::vector<uint64_t> h_part(PA_all);
+    SG_CUDA(cudaMemsetAsync(blk_counts.p, 0, blk_counts.bytes(), st));
+    tm.start();
+    for (const Src &src : srcs) {
+        if (src.n == 0) continue;
+        levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p);
+        ctx->launches++;
+    }
+    SG_CUDA(cudaGetLastError());
+    levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(blk_counts.p, PA_all, G, part_total_all.p);
+    ctx->launches++;
+    SG_CUDA(cudaMemcpyAsync(h_part.data(), part_total_all.p, (size_t)PA_all * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    ctx->times.extract_count += tm.stop();
+    tr.mark("A1 count+totals");
+    int b_lo = s_lo;
+    while (b_lo < s_hi) {
+        // ---- plan this pass: as many whole buckets as fit next to what is already resident (X + Y + its own output)
+        size_t lim = ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(ctx->free_bytes() * 0.92);
+        int b_hi = b_lo;
+        uint64_t I = 0;
+        while (b_hi < s_hi) {
+            uint64_t ib = 0;
+            for (uint32_t q = 0; q < (1u << rA); ++q) ib += h_part[((size_t)(b_hi - s_lo) << rA) + q];
+            double need = (double)(I + ib) * W * 2.0 + (double)(I + ib) * (W + 4) * 0.6 + (64 << 20);
+            if (b_hi > b_lo && need > (double)lim) break;
+            I += ib; ++b_hi;
+            if ((uint32_t)(b_hi - b_lo) << rA >= 8192u) break;
+        }
+        const uint32_t nb = (uint32_t)(b_hi - b_lo);
+        const uint32_t p_lo = (uint32_t)(b_lo - s_lo) << rA;
+        LevelA pa;
+        pa.K = K; pa.B = (uint32_t)B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = rA; pa.PA = nb << rA;
+        const uint32_t PA = pa.PA;
+        const uint64_t *part_total_p = part_total_all.p + p_lo;
+        DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1);
+        SG_CUDA(cudaMemcpyAsync(part_total.p, part_total_p, (size_t)PA * 8, cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
+        exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
+        ctx->times.passes++;
+        ctx->times.instances += I;
+        // ---- A2: scatter
+        DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
+        tr.mark("alloc X,Y");
+        {
+            DArr<uint64_t> base(ctx, (size_t)G * PA);
+            levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, G, part_start.p, base.p);
+            ctx->launches++;
+            tm.start();
+            size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (const Src &src : srcs) {
+                if (src.n == 0) continue;
+                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p);
+                ctx->launches++;
+            }
+            SG_CUDA(cudaGetLastError());
+            ctx->times.extract_scatter += tm.stop();
+            tr.mark("A2 scatter");
+        }
+        Chunk ch;
+        sort_pass<NW>(ctx, K, X, Y, part_start.p, part_total.p, PA, rA, (uint32_t)b_lo, b_hi, first, want_counts, double_selfrc, d_bsz.p, ch, tm, tr);
+        first += ch.n;
         out->chunks.push_back(std::move(ch));
-        ++ti;
+        b_lo = b_hi;
         tr.mark("pass end (before frees)");
+    }
     }
     std::vector<unsigned long long> hb(B);
     SG_CUDA(cudaMemcpyAsync(hb.data(), d_bsz.p, B * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1299,6 +1298,321 @@ KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B) {
     if (nw == 3 && nws == 4) return kmers_from_kpomers_nw<3, 4>(ctx, kp, B);
     if (nw == 4 && nws == 4) return kmers_from_kpomers_nw<4, 4>(ctx, kp, B);
     throw Error(2, "unsupported k-mer word combination");
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU count. Buckets are the unit of independence (KMerSegmentPolicy is a pure function of the k-mer),
+// so every bucket has one owner GPU. Each rank histograms its own read shard once; the per-partition totals are
+// all-gathered (host plumbing, torch.distributed); then ONE kernel per pass both partitions the shard and performs
+// the exchange: every record is stored straight into its owner GPU's segment through an NVLink peer mapping
+// (cudaIpc), at an offset that is exclusive to (source rank, CTA, partition). No staging copy, no separate all-to-all,
+// no merge pass. The owner then runs the ordinary refinement / local-sort / compaction on what arrived.
+// ------------------------------------------------------------------------------------------------------------
+struct DistPlan {
+    int world = 1, rank = 0, B = 0, rA = 0, npass = 1;
+    uint32_t PA_all = 0;
+    std::vector<int> pass_b;                   // npass+1 bucket boundaries
+    std::vector<uint64_t> tot;                 // PA_all: records per partition summed over ranks
+    uint64_t max_recv = 0;                     // records, max over (pass, rank)
+    int own_lo(int p, int g) const { int nb = pass_b[p + 1] - pass_b[p]; return pass_b[p] + (int)((int64_t)nb * g / world); }
+    uint64_t recv(int p, int g) const {
+        uint64_t s = 0;
+        for (size_t q = (size_t)own_lo(p, g) << rA; q < ((size_t)own_lo(p, g + 1) << rA); ++q) s += tot[q];
+        return s;
+    }
+};
+
+// pure host function (also exported for the CPU/gloo tests): identical on every rank given the same inputs
+void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, size_t W) {
+    pl.world = world; pl.rank = rank; pl.B = B; pl.rA = rA; pl.PA_all = (uint32_t)B << rA;
+    pl.tot.assign(pl.PA_all, 0);
+    for (int s = 0; s < world; ++s)
+        for (uint32_t q = 0; q < pl.PA_all; ++q) pl.tot[q] += cnt_all[(size_t)s * pl.PA_all + q];
+    for (int np = 1;; ++np) {
+        pl.npass = np;
+        pl.pass_b.assign(np + 1, 0);
+        for (int p = 0; p <= np; ++p) pl.pass_b[p] = (int)((int64_t)B * p / np);
+        uint64_t mx = 0;
+        for (int p = 0; p < np; ++p)
+            for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
+        pl.max_recv = mx;
+        // exchange buffer + ping-pong partner + output estimate must fit the budget
+        double need = (double)mx * W * 2.0 + (double)mx * (W + 4) * 0.6 * np + (256 << 20);
+        if (need <= (double)budget_bytes || np >= B || (uint32_t)(((B + np - 1) / np) << rA) <= 1u) break;
+    }
+    // a pass's partitions must also fit the scatter kernel's shared-memory tables
+    while ((((size_t)(B + pl.npass - 1) / pl.npass) << rA) > 4096 && pl.npass < B) {
+        ++pl.npass;
+        pl.pass_b.assign(pl.npass + 1, 0);
+        for (int p = 0; p <= pl.npass; ++p) pl.pass_b[p] = (int)((int64_t)B * p / pl.npass);
+        uint64_t mx = 0;
+        for (int p = 0; p < pl.npass; ++p)
+            for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
+        pl.max_recv = mx;
+    }
+}
+
+struct DistState {
+    Ctx *ctx = nullptr;
+    int K = 0, B = 0, mode = 0, nw = 0, G = 0;
+    DistPlan plan;
+    DArr<uint32_t> blk_counts;               // G x PA_all (local)
+    DArr<uint64_t> part_total_local;         // PA_all
+    DArr<uint64_t> d_cnt_all;                // world x PA_all
+    DArr<uint64_t> xbuf, ybuf;               // exchange buffer (peers write into it) and its ping-pong partner
+    std::vector<uint64_t *> peer;            // world mapped base pointers (own entry = xbuf.p)
+    DArr<uint64_t *> d_peer;
+    DArr<unsigned long long> d_bsz;
+    KSet *out = nullptr;
+    int64_t first = 0;
+    ReadsSrc src;
+    bool want_counts = false, double_selfrc = false;
+};
+
+// bases for the fused kernel: base[g][q] = slot (in the owner's buffer) where CTA g of THIS rank starts writing partition q
+__global__ void dist_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t stride, uint32_t p_lo, uint32_t PA, int G, int rank,
+                             const uint64_t *__restrict__ cnt_all, uint32_t PA_all, const uint64_t *__restrict__ dest_start,
+                             uint64_t *__restrict__ base) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= PA) return;
+    uint64_t run = dest_start[q];
+    for (int s = 0; s < rank; ++s) run += cnt_all[(size_t)s * PA_all + p_lo + q];
+    for (int g = 0; g < G; ++g) {
+        base[(size_t)g * PA + q] = run;
+        run += blk_counts[(size_t)g * stride + p_lo + q];
+    }
+}
+
+template <int NW, class Src>
+__global__ void __launch_bounds__(kAThreads) levelA_scatter_dist_k(Src src, LevelA p, const uint64_t *__restrict__ base, const uint8_t *__restrict__ owner,
+                                                                   uint64_t *const *__restrict__ peer) {
+    extern __shared__ uint32_t sm_dyn[];
+    uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    uint8_t *own = reinterpret_cast<uint8_t *>(cnt + p.PA);             // PA u8
+    __shared__ uint32_t pref[kATile + 1];
+    const uint64_t *mybase = base + (size_t)blockIdx.x * p.PA;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; own[i] = owner[i]; }
+    __syncthreads();
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            int it = find_item(pref, nitems, i);
+            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
+            uint32_t part;
+            if (part_of<NW>(p, k, &part)) {
+                uint32_t slot = atomicAdd(&cnt[part], 1u);
+                store_rec<NW>(peer[own[part]] + (cur_base[part] + slot) * NW, k);     // local or NVLink peer store
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NW>
+static void dist_begin_nw(DistState *d) {
+    Ctx *ctx = d->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t PA_all = d->plan.PA_all;
+    LevelA pa_all;
+    pa_all.K = d->K; pa_all.B = (uint32_t)d->B; pa_all.b_lo = 0; pa_all.b_hi = (uint32_t)d->B; pa_all.rA = d->plan.rA; pa_all.PA = PA_all;
+    d->blk_counts.alloc(ctx, (size_t)d->G * PA_all);
+    d->part_total_local.alloc(ctx, (size_t)PA_all + 1);
+    SG_CUDA(cudaMemsetAsync(d->blk_counts.p, 0, d->blk_counts.bytes(), st));
+    Timer tm(st);
+    tm.start();
+    if (d->src.n) {
+        levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p);
+        ctx->launches++;
+    }
+    levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(d->blk_counts.p, PA_all, d->G, d->part_total_local.p);
+    ctx->launches++;
+    SG_CUDA(cudaGetLastError());
+    ctx->times.extract_count += tm.stop();
+}
+
+template <int NW>
+static void dist_scatter_nw(DistState *d, int p) {
+    Ctx *ctx = d->ctx;
+    cudaStream_t st = ctx->stream;
+    const DistPlan &pl = d->plan;
+    const int b_lo = pl.pass_b[p], b_hi = pl.pass_b[p + 1];
+    const uint32_t p_lo = (uint32_t)b_lo << pl.rA, PA = (uint32_t)(b_hi - b_lo) << pl.rA;
+    // per partition: owner rank and start slot inside the owner's buffer
+    std::vector<uint64_t> dest_start(PA);
+    std::vector<uint8_t> owner(PA);
+    for (int g = 0; g < pl.world; ++g) {
+        uint64_t run = 0;
+        for (size_t Q = (size_t)pl.own_lo(p, g) << pl.rA; Q < ((size_t)pl.own_lo(p, g + 1) << pl.rA); ++Q) {
+            dest_start[Q - p_lo] = run; owner[Q - p_lo] = (uint8_t)g; run += pl.tot[Q];
+        }
+    }
+    DArr<uint64_t> d_dest(ctx, PA + 1), base(ctx, (size_t)d->G * PA);
+    DArr<uint8_t> d_owner(ctx, PA + 1);
+    SG_CUDA(cudaMemcpyAsync(d_dest.p, dest_start.data(), (size_t)PA * 8, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(d_owner.p, owner.data(), PA, cudaMemcpyHostToDevice, st));
+    dist_bases_k<<<div_up(PA, 256), 256, 0, st>>>(d->blk_counts.p, pl.PA_all, p_lo, PA, d->G, pl.rank, d->d_cnt_all.p, pl.PA_all, d_dest.p, base.p);
+    ctx->launches++;
+    LevelA pa;
+    pa.K = d->K; pa.B = (uint32_t)d->B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = pl.rA; pa.PA = PA;
+    Timer tm(st);
+    tm.start();
+    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t) + 1) + 16;
+    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_dist_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (d->src.n) {
+        levelA_scatter_dist_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d_owner.p, d->d_peer.p);
+        ctx->launches++;
+    }
+    SG_CUDA(cudaGetLastError());
+    ctx->times.extract_scatter += tm.stop();      // includes the NVLink traffic: the kernel IS the exchange
+}
+
+template <int NW>
+static void dist_sort_nw(DistState *d, int p) {
+    Ctx *ctx = d->ctx;
+    cudaStream_t st = ctx->stream;
+    const DistPlan &pl = d->plan;
+    const int my_lo = pl.own_lo(p, pl.rank), my_hi = pl.own_lo(p, pl.rank + 1);
+    const uint32_t PA = (uint32_t)(my_hi - my_lo) << pl.rA;
+    const size_t Q0 = (size_t)my_lo << pl.rA;
+    std::vector<uint64_t> tot(PA + 1, 0), start(PA + 1, 0);
+    for (uint32_t q = 0; q < PA; ++q) { tot[q] = pl.tot[Q0 + q]; start[q + 1] = start[q] + tot[q]; }
+    ctx->times.passes++;
+    ctx->times.instances += start[PA];
+    Chunk ch;
+    if (PA) {
+        DArr<uint64_t> d_tot(ctx, PA + 1), d_start(ctx, PA + 1);
+        SG_CUDA(cudaMemcpyAsync(d_tot.p, tot.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(d_start.p, start.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
+        Timer tm(st);
+        Trace tr(st);
+        sort_pass<NW>(ctx, d->K, d->xbuf, d->ybuf, d_start.p, d_tot.p, PA, pl.rA, (uint32_t)my_lo, my_hi, d->first, d->want_counts, d->double_selfrc,
+                      d->d_bsz.p, ch, tm, tr);
+    } else {
+        ch.n = 0; ch.b_lo = my_lo; ch.b_hi = my_hi; ch.first = d->first;
+        ch.keys.alloc(ctx, 2);
+        if (d->want_counts) ch.counts.alloc(ctx, 1);
+    }
+    d->first += ch.n;
+    d->out->chunks.push_back(std::move(ch));
+}
+
+#define DIST_DISPATCH(fn, d, ...)                    \
+    switch ((d)->nw) {                               \
+        case 1: fn<1>(d, ##__VA_ARGS__); break;      \
+        case 2: fn<2>(d, ##__VA_ARGS__); break;      \
+        case 3: fn<3>(d, ##__VA_ARGS__); break;      \
+        default: fn<4>(d, ##__VA_ARGS__); break;     \
+    }
+
+DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
+    SG_CHECK(K >= 1 && K <= 128, 2, "K must be in [1,128]");
+    SG_CHECK(B >= 1 && B <= 8192, 2, "distributed count: num_buckets must be in [1, 8192]");
+    SG_CHECK(world >= 1 && world <= 255 && rank >= 0 && rank < world, 2, "bad world/rank");
+    ensure_reads_on_device(ctx);
+    ctx->times = PhaseTimes();
+    DistState *d = new DistState();
+    d->ctx = ctx; d->K = K; d->B = B; d->mode = mode; d->nw = nwords_of(K);
+    d->G = ctx->num_sms * 2;
+    d->want_counts = (mode == kCanonical); d->double_selfrc = (mode == kCanonical) && (K % 2 == 0);
+    d->src.words = ctx->d_words; d->src.offs = ctx->d_offs; d->src.lens = ctx->d_lens; d->src.n = ctx->n_reads; d->src.K = K; d->src.both = (mode == kAllWindows);
+    int rA = 0;
+    while (rA < 8 && ((uint64_t)B << (rA + 1)) <= 4096 && rA + 1 <= 2 * K) ++rA;      // every rank must use the same geometry: depends on B only
+    d->plan.world = world; d->plan.rank = rank; d->plan.B = B; d->plan.rA = rA; d->plan.PA_all = (uint32_t)B << rA;
+    try { DIST_DISPATCH(dist_begin_nw, d); } catch (...) { delete d; throw; }
+    return d;
+}
+uint32_t dist_num_partitions(const DistState *d) { return d->plan.PA_all; }
+void dist_local_counts(DistState *d, uint64_t *h_out) {
+    SG_CUDA(cudaMemcpyAsync(h_out, d->part_total_local.p, (size_t)d->plan.PA_all * 8, cudaMemcpyDeviceToHost, d->ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
+}
+void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records) {
+    Ctx *ctx = d->ctx;
+    dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, (size_t)8 * d->nw);
+    d->d_cnt_all.alloc(ctx, (size_t)d->plan.world * d->plan.PA_all);
+    SG_CUDA(cudaMemcpyAsync(d->d_cnt_all.p, cnt_all, d->d_cnt_all.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    // exchange buffers come straight from the driver (cudaIpc needs allocation base pointers; the pool hands those out too)
+    d->xbuf.alloc(ctx, (size_t)d->plan.max_recv * d->nw + 2);
+    d->ybuf.alloc(ctx, (size_t)d->plan.max_recv * d->nw + 2);
+    d->d_bsz.alloc(ctx, (size_t)d->B);
+    SG_CUDA(cudaMemsetAsync(d->d_bsz.p, 0, (size_t)d->B * 8, ctx->stream));
+    d->out = new KSet();
+    d->out->ctx = ctx; d->out->K = d->K; d->out->nw = d->nw; d->out->B = d->B; d->out->has_counts = d->want_counts;
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *npass = d->plan.npass; *xchg_records = d->plan.max_recv;
+}
+void dist_ipc_handle(DistState *d, uint8_t *out64) {
+    cudaIpcMemHandle_t h;
+    SG_CUDA(cudaIpcGetMemHandle(&h, d->xbuf.p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &h, 64);
+}
+void dist_open_peers(DistState *d, const uint8_t *handles) {
+    Ctx *ctx = d->ctx;
+    const int world = d->plan.world;
+    d->peer.assign(world, nullptr);
+    for (int g = 0; g < world; ++g) {
+        if (g == d->plan.rank) { d->peer[g] = d->xbuf.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)g * 64, 64);
+        void *p = nullptr;
+        SG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        d->peer[g] = (uint64_t *)p;
+    }
+    d->d_peer.alloc(ctx, (size_t)world);
+    SG_CUDA(cudaMemcpyAsync(d->d_peer.p, d->peer.data(), (size_t)world * sizeof(uint64_t *), cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+void dist_scatter(DistState *d, int p) {
+    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    DIST_DISPATCH(dist_scatter_nw, d, p);
+    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // all of this rank's peer stores have been issued and completed
+}
+void dist_sort(DistState *d, int p) {
+    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    DIST_DISPATCH(dist_sort_nw, d, p);
+    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
+}
+static void dist_close(DistState *d) {
+    for (int g = 0; g < (int)d->peer.size(); ++g)
+        if (g != d->plan.rank && d->peer[g]) cudaIpcCloseMemHandle(d->peer[g]);
+    d->peer.clear();
+}
+KSet *dist_end(DistState *d) {
+    Ctx *ctx = d->ctx;
+    KSet *ks = d->out;
+    const int B = d->B;
+    std::vector<unsigned long long> hb(B);
+    SG_CUDA(cudaMemcpyAsync(hb.data(), d->d_bsz.p, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ks->bsz.assign(B, 0); ks->bstart.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) { ks->bsz[b] = (int64_t)hb[b]; ks->bstart[b + 1] = ks->bstart[b] + ks->bsz[b]; }
+    ks->n = d->first;
+    SG_CHECK(ks->bstart[B] == ks->n, 6, "internal: distributed bucket sizes do not add up");
+    d->out = nullptr;
+    dist_close(d);
+    return ks;
+}
+void dist_free(DistState *d) {
+    if (!d) return;
+    dist_close(d);
+    delete d->out;
+    delete d;
+}
+
+int dist_plan_host(int world, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, int record_bytes, int *pass_b, uint64_t *max_recv) {
+    DistPlan pl;
+    dist_make_plan(pl, world, 0, B, rA, cnt_all, budget_bytes, (size_t)record_bytes);
+    for (int p = 0; p <= pl.npass; ++p) pass_b[p] = pl.pass_b[p];
+    *max_recv = pl.max_recv;
+    return pl.npass;
 }
 
 }  // namespace sg

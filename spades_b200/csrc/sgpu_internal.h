@@ -210,6 +210,22 @@ enum CountMode { kCanonical = 0, kAllWindows = 1 };
 KSet *count_from_reads(Ctx *ctx, int K, int B, int mode);
 KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B);
 
+// distributed count (count.cu)
+struct DistState;
+struct DistPlan;
+DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank);
+uint32_t dist_num_partitions(const DistState *d);
+void dist_local_counts(DistState *d, uint64_t *h_out);
+void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records);
+void dist_ipc_handle(DistState *d, uint8_t *out64);
+void dist_open_peers(DistState *d, const uint8_t *handles);
+void dist_scatter(DistState *d, int p);
+void dist_sort(DistState *d, int p);
+KSet *dist_end(DistState *d);
+void dist_free(DistState *d);
+// pure host planning (exported for CPU tests): returns npass, fills pass boundaries / owner boundaries / totals
+int dist_plan_host(int world, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, int record_bytes, int *pass_b /*B+1 max*/, uint64_t *max_recv);
+
 // mphf.cu
 Mphf *mphf_build(Ctx *ctx, const KSet *ks);
 size_t mphf_serialized_size(const Mphf *m);
