@@ -254,7 +254,7 @@ def main():
     # ---- value: reads resident in HBM
     for _ in range(args.warmup):
         st, idx = step_resident(); idx.free(); st.free()
-    phases = {k: 0.0 for k in ("extract_count_ms", "extract_scatter_ms", "refine_ms", "local_sort_ms", "compact_ms", "mphf_ms")}
+    phases = {k: 0.0 for k in ("extract_count_ms", "extract_scatter_ms", "exchange_ms", "refine_ms", "local_sort_ms", "compact_ms", "mphf_ms")}
     l0 = ctx.times()["launches"]
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
@@ -332,11 +332,12 @@ def main():
             "refine_ms": 2 * I * W,                                          # one read + one write of every record
             "local_sort_ms": I * W + D * (W + 4),                            # records in, distinct records + counts out
             "compact_ms": 2 * D * (W + 4),
+            "exchange_ms": 2 * I * W,
         }
         dom = max(alg, key=lambda k2: per_step[k2])
         achieved = alg[dom] / (per_step[dom] / 1e3) / 1e9 if per_step[dom] > 0 else 0.0
         kernel_names = {"extract_scatter_ms": "levelA_scatter_k (radix partition)", "extract_count_ms": "levelA_count_k", "refine_ms": "refine_k (MSD split)",
-                        "local_sort_ms": "local_sort_k", "compact_ms": "compact_k"}
+                        "local_sort_ms": "local_sort3_k", "compact_ms": "compact_k", "exchange_ms": "dist_pull_k (NVLink exchange+merge)"}
         line = {
             "metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": value, "unit": "Mk-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -344,7 +345,7 @@ def main():
             "config": {"workload": "synthetic %d x 150 bp reads per GPU (uniform genome %d bp, 1%% substitutions, random strand), k=55: canonical (k+1)=56-mers, "
                                    "%d XXH3 buckets, sort/unique/count + boomphf MPHF (extract+count+index)" % (n_reads, genome_len, B),
                        "k": K_GRAPH, "reads_per_gpu": n_reads, "buckets": B, "distinct_kpomers": int(distinct), "instances": int(instances), "passes": int(passes),
-                       "parallelism": ("1 GPU" if world == 1 else "%d GPUs: reads sharded, buckets owned by ranks, partition kernel stores records into the owner over NVLink peer memory" % world),
+                       "parallelism": ("1 GPU" if world == 1 else "%d GPUs: reads sharded, buckets owned by ranks, one pull kernel per rank exchanges + merges the partitions over NVLink peer memory" % world),
                        "l2": "inputs (%.1f GB) and intermediates larger than L2; no flush needed" % (nwords * 8 / 1e9), "peak_hbm_gb": peak / 1e9},
             "clocks": sampler.result(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mk-mers/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -64,7 +64,7 @@ enum {
 /* device-side milliseconds of the last sgpu_count / sgpu_kmers_from_kpomers / sgpu_mphf_build, measured with CUDA events
  * on the context's stream, plus the number of kernels launched since the context was created */
 typedef struct sgpu_times {
-    float extract_count_ms, extract_scatter_ms, refine_ms, local_sort_ms, compact_ms, mphf_ms;
+    float extract_count_ms, extract_scatter_ms, refine_ms, local_sort_ms, compact_ms, mphf_ms, exchange_ms;
     uint64_t instances;   /* records the partition kernel wrote */
     uint64_t passes;      /* bucket-group passes */
     uint64_t launches;    /* kernels launched by this context so far */
@@ -124,11 +124,12 @@ void sgpu_graph_free(sgpu_graph *g);
 
 /* ---- multi-GPU count (one process per GPU). Replaces hpcspades' shared-filesystem + MPI pattern
  * (projects/hpcspades/mpi/stages/construction_mpi.cpp:222-300, mpi/kmer_index/kmer_extension_index_builder_mpi.hpp:87,190):
- * buckets are owned by ranks; sgpu_dist_scatter is ONE kernel that partitions this rank's reads and stores every record
- * directly into its owner GPU's buffer over NVLink peer memory (cudaIpc mappings). The host language only moves the small
- * tables between ranks (torch.distributed / MPI all_gather) and provides the barriers:
+ * buckets are owned by ranks; every rank partitions its own reads into a staging buffer, then sgpu_dist_exchange is ONE
+ * kernel on the owner that pulls its pieces from all peers' staging buffers over NVLink peer memory (cudaIpc mappings)
+ * and merges them partition by partition. The host language only moves the small tables between ranks
+ * (torch.distributed / MPI all_gather) and provides the barriers:
  *   begin -> local_counts -> [all_gather counts] -> plan -> ipc_handle -> [all_gather handles] -> open_peers ->
- *   for each pass: [barrier] scatter [barrier] sort   -> end (k-mer set holding this rank's buckets) */
+ *   for each pass: scatter [barrier] exchange [barrier] sort   -> end (k-mer set holding this rank's buckets) */
 typedef struct sgpu_dist sgpu_dist;
 int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, int rank, sgpu_dist **out);
 int64_t sgpu_dist_num_partitions(const sgpu_dist *d);
@@ -137,7 +138,8 @@ int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_parti
                    int *npass, uint64_t *exchange_records);
 int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64);                 /* 64-byte cudaIpcMemHandle of this rank's exchange buffer */
 int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x 64 bytes */);
-int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* fused partition + NVLink exchange kernel */
+int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* partition this rank's shard into its staging buffer */
+int sgpu_dist_exchange(sgpu_dist *d, int pass);                         /* fused NVLink exchange + merge: pulls the owned pieces from every peer */
 int sgpu_dist_sort(sgpu_dist *d, int pass);                             /* refinement + local sort + compaction of what arrived */
 int sgpu_dist_end(sgpu_dist *d, sgpu_kset **out);
 void sgpu_dist_free(sgpu_dist *d);

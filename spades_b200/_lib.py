@@ -19,7 +19,7 @@ SYMBOLS = [
     "sgpu_graph_build", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
     "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_ipc_handle",
-    "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
+    "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_exchange", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
     "sgpu_selftest",
 ]
 
@@ -30,7 +30,7 @@ class SgpuConfig(C.Structure):
 
 class SgpuTimes(C.Structure):
     _fields_ = [("extract_count_ms", C.c_float), ("extract_scatter_ms", C.c_float), ("refine_ms", C.c_float),
-                ("local_sort_ms", C.c_float), ("compact_ms", C.c_float), ("mphf_ms", C.c_float),
+                ("local_sort_ms", C.c_float), ("compact_ms", C.c_float), ("mphf_ms", C.c_float), ("exchange_ms", C.c_float),
                 ("instances", C.c_uint64), ("passes", C.c_uint64), ("launches", C.c_uint64), ("peak_bytes", C.c_uint64)]
 
 
@@ -89,6 +89,7 @@ def load():
     L.sgpu_dist_ipc_handle.restype = i32; L.sgpu_dist_ipc_handle.argtypes = [vp, vp]
     L.sgpu_dist_open_peers.restype = i32; L.sgpu_dist_open_peers.argtypes = [vp, vp]
     L.sgpu_dist_scatter.restype = i32; L.sgpu_dist_scatter.argtypes = [vp, i32]
+    L.sgpu_dist_exchange.restype = i32; L.sgpu_dist_exchange.argtypes = [vp, i32]
     L.sgpu_dist_sort.restype = i32; L.sgpu_dist_sort.argtypes = [vp, i32]
     L.sgpu_dist_end.restype = i32; L.sgpu_dist_end.argtypes = [vp, pp]
     L.sgpu_dist_free.restype = None; L.sgpu_dist_free.argtypes = [vp]

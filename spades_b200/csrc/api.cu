@@ -62,7 +62,7 @@ int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out) {
     if (!ctx || !out) return SGPU_EINVAL;
     const PhaseTimes &t = ctx->c.times;
     out->extract_count_ms = t.extract_count; out->extract_scatter_ms = t.extract_scatter; out->refine_ms = t.refine;
-    out->local_sort_ms = t.local_sort; out->compact_ms = t.compact; out->mphf_ms = t.mphf;
+    out->local_sort_ms = t.local_sort; out->compact_ms = t.compact; out->mphf_ms = t.mphf; out->exchange_ms = t.exchange;
     out->instances = t.instances; out->passes = t.passes; out->launches = ctx->c.launches; out->peak_bytes = ctx->c.peak;
     return SGPU_OK;
 }
@@ -369,6 +369,10 @@ int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles) {
 int sgpu_dist_scatter(sgpu_dist *d, int pass) {
     if (!d) return SGPU_EINVAL;
     API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_scatter(d->d, pass); })
+}
+int sgpu_dist_exchange(sgpu_dist *d, int pass) {
+    if (!d) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_exchange(d->d, pass); })
 }
 int sgpu_dist_sort(sgpu_dist *d, int pass) {
     if (!d) return SGPU_EINVAL;

@@ -1304,10 +1304,12 @@ KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B) {
 // ------------------------------------------------------------------------------------------------------------
 // multi-GPU count. Buckets are the unit of independence (KMerSegmentPolicy is a pure function of the k-mer),
 // so every bucket has one owner GPU. Each rank histograms its own read shard once; the per-partition totals are
-// all-gathered (host plumbing, torch.distributed); then ONE kernel per pass both partitions the shard and performs
-// the exchange: every record is stored straight into its owner GPU's segment through an NVLink peer mapping
-// (cudaIpc), at an offset that is exclusive to (source rank, CTA, partition). No staging copy, no separate all-to-all,
-// no merge pass. The owner then runs the ordinary refinement / local-sort / compaction on what arrived.
+// all-gathered (host plumbing, torch.distributed). Per pass every rank partitions its shard into a local staging buffer
+// (partition-major), and then ONE kernel on the owner does the exchange AND the merge: it pulls every (source rank,
+// partition) piece out of the sources' staging buffers through NVLink peer mappings (cudaIpc) with coalesced 16-byte
+// loads and lays the pieces of a partition next to each other, ready for the ordinary refinement / local sort /
+// compaction. (A first version pushed each 16-byte record to its owner from inside the partition kernel; remote
+// scattered stores are not write-combined and ran at ~1 GB/s.)
 // ------------------------------------------------------------------------------------------------------------
 struct DistPlan {
     int world = 1, rank = 0, B = 0, rA = 0, npass = 1;
@@ -1315,6 +1317,7 @@ struct DistPlan {
     std::vector<int> pass_b;                   // npass+1 bucket boundaries
     std::vector<uint64_t> tot;                 // PA_all: records per partition summed over ranks
     uint64_t max_recv = 0;                     // records, max over (pass, rank)
+    uint64_t max_send = 0;                     // records a rank partitions locally in one pass, max over (pass, rank)
     int own_lo(int p, int g) const { int nb = pass_b[p + 1] - pass_b[p]; return pass_b[p] + (int)((int64_t)nb * g / world); }
     uint64_t recv(int p, int g) const {
         uint64_t s = 0;
@@ -1337,8 +1340,16 @@ void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint
         for (int p = 0; p < np; ++p)
             for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
         pl.max_recv = mx;
-        // exchange buffer + ping-pong partner + output estimate must fit the budget
-        double need = (double)mx * W * 2.0 + (double)mx * (W + 4) * 0.6 * np + (256 << 20);
+        uint64_t ms = 0;
+        for (int p = 0; p < np; ++p)
+            for (int s = 0; s < world; ++s) {
+                uint64_t t = 0;
+                for (size_t q = (size_t)pl.pass_b[p] << rA; q < ((size_t)pl.pass_b[p + 1] << rA); ++q) t += cnt_all[(size_t)s * pl.PA_all + q];
+                ms = std::max(ms, t);
+            }
+        pl.max_send = ms;
+        // staging buffer (doubles as ping-pong partner) + merged buffer + output estimate must fit the budget
+        double need = (double)std::max(mx, ms) * W * 2.0 + (double)mx * (W + 4) * 0.6 * np + (256 << 20);
         if (need <= (double)budget_bytes || np >= B || (uint32_t)(((B + np - 1) / np) << rA) <= 1u) break;
     }
     // a pass's partitions must also fit the scatter kernel's shared-memory tables
@@ -1346,10 +1357,16 @@ void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint
         ++pl.npass;
         pl.pass_b.assign(pl.npass + 1, 0);
         for (int p = 0; p <= pl.npass; ++p) pl.pass_b[p] = (int)((int64_t)B * p / pl.npass);
-        uint64_t mx = 0;
-        for (int p = 0; p < pl.npass; ++p)
+        uint64_t mx = 0, ms = 0;
+        for (int p = 0; p < pl.npass; ++p) {
             for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
-        pl.max_recv = mx;
+            for (int s = 0; s < world; ++s) {
+                uint64_t t = 0;
+                for (size_t q = (size_t)pl.pass_b[p] << rA; q < ((size_t)pl.pass_b[p + 1] << rA); ++q) t += cnt_all[(size_t)s * pl.PA_all + q];
+                ms = std::max(ms, t);
+            }
+        }
+        pl.max_recv = mx; pl.max_send = ms;
     }
 }
 
@@ -1360,9 +1377,9 @@ struct DistState {
     DArr<uint32_t> blk_counts;               // G x PA_all (local)
     DArr<uint64_t> part_total_local;         // PA_all
     DArr<uint64_t> d_cnt_all;                // world x PA_all
-    DArr<uint64_t> xbuf, ybuf;               // exchange buffer (peers write into it) and its ping-pong partner
-    std::vector<uint64_t *> peer;            // world mapped base pointers (own entry = xbuf.p)
-    DArr<uint64_t *> d_peer;
+    DArr<uint64_t> sbuf, xbuf;               // staging buffer (peers read it; later the ping-pong partner) and the merged buffer
+    std::vector<uint64_t *> peer;            // world mapped staging buffers (own entry = sbuf.p)
+    std::vector<uint64_t> h_cnt_all;         // world x PA_all
     DArr<unsigned long long> d_bsz;
     KSet *out = nullptr;
     int64_t first = 0;
@@ -1370,48 +1387,30 @@ struct DistState {
     bool want_counts = false, double_selfrc = false;
 };
 
-// bases for the fused kernel: base[g][q] = slot (in the owner's buffer) where CTA g of THIS rank starts writing partition q
-__global__ void dist_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t stride, uint32_t p_lo, uint32_t PA, int G, int rank,
-                             const uint64_t *__restrict__ cnt_all, uint32_t PA_all, const uint64_t *__restrict__ dest_start,
-                             uint64_t *__restrict__ base) {
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= PA) return;
-    uint64_t run = dest_start[q];
-    for (int s = 0; s < rank; ++s) run += cnt_all[(size_t)s * PA_all + p_lo + q];
-    for (int g = 0; g < G; ++g) {
-        base[(size_t)g * PA + q] = run;
-        run += blk_counts[(size_t)g * stride + p_lo + q];
-    }
-}
-
-template <int NW, class Src>
-__global__ void __launch_bounds__(kAThreads) levelA_scatter_dist_k(Src src, LevelA p, const uint64_t *__restrict__ base, const uint8_t *__restrict__ owner,
-                                                                   uint64_t *const *__restrict__ peer) {
-    extern __shared__ uint32_t sm_dyn[];
-    uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
-    uint8_t *own = reinterpret_cast<uint8_t *>(cnt + p.PA);             // PA u8
-    __shared__ uint32_t pref[kATile + 1];
-    const uint64_t *mybase = base + (size_t)blockIdx.x * p.PA;
-    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; own[i] = owner[i]; }
-    __syncthreads();
-    const int64_t ntiles = (src.n + kATile - 1) / kATile;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t item0 = t * kATile;
-        const int nitems = (int)min((int64_t)kATile, src.n - item0);
-        const uint32_t total = tile_prefix(src, item0, nitems, pref);
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            int it = find_item(pref, nitems, i);
-            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
-            uint32_t part;
-            if (part_of<NW>(p, k, &part)) {
-                uint32_t slot = atomicAdd(&cnt[part], 1u);
-                store_rec<NW>(peer[own[part]] + (cur_base[part] + slot) * NW, k);     // local or NVLink peer store
-            }
-        }
+// exchange + merge in one kernel: the owner PULLS every (source rank, partition) piece out of the sources' staging buffers
+// through NVLink peer mappings with coalesced 16-byte loads and lays the pieces of a partition next to each other.
+struct PullPiece { const uint64_t *src; uint64_t dst; uint64_t n; };
+template <int NW>
+__global__ void __launch_bounds__(512) dist_pull_k(const PullPiece *__restrict__ pieces, uint64_t npieces, uint64_t *__restrict__ out,
+                                                   unsigned long long *__restrict__ work_counter) {
+    __shared__ unsigned long long s_w;
+    for (;;) {
+        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
         __syncthreads();
+        const uint64_t w = s_w;
+        __syncthreads();
+        if (w >= npieces) return;
+        const PullPiece pc = pieces[w];
+        const uint64_t nwords = pc.n * NW;
+        uint64_t *dst = out + pc.dst * NW;
+        if ((((uintptr_t)pc.src | (uintptr_t)dst) & 15) == 0) {
+            const ulonglong2 *s2 = reinterpret_cast<const ulonglong2 *>(pc.src);
+            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst);
+            for (uint64_t i = threadIdx.x; i < nwords / 2; i += blockDim.x) d2[i] = s2[i];
+            if ((nwords & 1) && threadIdx.x == 0) dst[nwords - 1] = pc.src[nwords - 1];
+        } else {
+            for (uint64_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = pc.src[i];
+        }
     }
 }
 
@@ -1439,38 +1438,64 @@ static void dist_begin_nw(DistState *d) {
 
 template <int NW>
 static void dist_scatter_nw(DistState *d, int p) {
+    // local partition of this rank's shard for the pass's buckets into the staging buffer (partition-major)
     Ctx *ctx = d->ctx;
     cudaStream_t st = ctx->stream;
     const DistPlan &pl = d->plan;
     const int b_lo = pl.pass_b[p], b_hi = pl.pass_b[p + 1];
     const uint32_t p_lo = (uint32_t)b_lo << pl.rA, PA = (uint32_t)(b_hi - b_lo) << pl.rA;
-    // per partition: owner rank and start slot inside the owner's buffer
-    std::vector<uint64_t> dest_start(PA);
-    std::vector<uint8_t> owner(PA);
-    for (int g = 0; g < pl.world; ++g) {
-        uint64_t run = 0;
-        for (size_t Q = (size_t)pl.own_lo(p, g) << pl.rA; Q < ((size_t)pl.own_lo(p, g + 1) << pl.rA); ++Q) {
-            dest_start[Q - p_lo] = run; owner[Q - p_lo] = (uint8_t)g; run += pl.tot[Q];
-        }
-    }
-    DArr<uint64_t> d_dest(ctx, PA + 1), base(ctx, (size_t)d->G * PA);
-    DArr<uint8_t> d_owner(ctx, PA + 1);
-    SG_CUDA(cudaMemcpyAsync(d_dest.p, dest_start.data(), (size_t)PA * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(d_owner.p, owner.data(), PA, cudaMemcpyHostToDevice, st));
-    dist_bases_k<<<div_up(PA, 256), 256, 0, st>>>(d->blk_counts.p, pl.PA_all, p_lo, PA, d->G, pl.rank, d->d_cnt_all.p, pl.PA_all, d_dest.p, base.p);
+    DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1), base(ctx, (size_t)d->G * PA);
+    SG_CUDA(cudaMemcpyAsync(part_total.p, d->part_total_local.p + p_lo, (size_t)PA * 8, cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
+    exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
+    levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(d->blk_counts.p + p_lo, pl.PA_all, PA, d->G, part_start.p, base.p);
     ctx->launches++;
     LevelA pa;
     pa.K = d->K; pa.B = (uint32_t)d->B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = pl.rA; pa.PA = PA;
     Timer tm(st);
     tm.start();
-    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t) + 1) + 16;
-    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_dist_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (d->src.n) {
-        levelA_scatter_dist_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d_owner.p, d->d_peer.p);
+        levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p);
         ctx->launches++;
     }
     SG_CUDA(cudaGetLastError());
-    ctx->times.extract_scatter += tm.stop();      // includes the NVLink traffic: the kernel IS the exchange
+    ctx->times.extract_scatter += tm.stop();
+}
+
+template <int NW>
+static void dist_pull_nw(DistState *d, int p) {
+    Ctx *ctx = d->ctx;
+    cudaStream_t st = ctx->stream;
+    const DistPlan &pl = d->plan;
+    const int world = pl.world;
+    const size_t pass_q0 = (size_t)pl.pass_b[p] << pl.rA;
+    const size_t q0 = (size_t)pl.own_lo(p, pl.rank) << pl.rA, q1 = (size_t)pl.own_lo(p, pl.rank + 1) << pl.rA;
+    // every source's staging layout is partition-major over the whole pass: local_start_s[q] = sum_{q' in pass, q' < q} cnt[s][q']
+    std::vector<uint64_t> src_off(world, 0);
+    for (int s = 0; s < world; ++s)
+        for (size_t q = pass_q0; q < q0; ++q) src_off[s] += d->h_cnt_all[(size_t)s * pl.PA_all + q];
+    std::vector<PullPiece> pieces;
+    uint64_t dst = 0;
+    for (size_t q = q0; q < q1; ++q)
+        for (int s = 0; s < world; ++s) {
+            const uint64_t n = d->h_cnt_all[(size_t)s * pl.PA_all + q];
+            if (n) pieces.push_back(PullPiece{d->peer[s] + src_off[s] * NW, dst, n});
+            src_off[s] += n; dst += n;
+        }
+    if (pieces.empty()) return;
+    DArr<PullPiece> dp(ctx, pieces.size());
+    DArr<unsigned long long> wc(ctx, 1);
+    SG_CUDA(cudaMemcpyAsync(dp.p, pieces.data(), pieces.size() * sizeof(PullPiece), cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemsetAsync(wc.p, 0, 8, st));
+    Timer tm(st);
+    tm.start();
+    int grid = (int)std::min<uint64_t>(pieces.size(), (uint64_t)ctx->num_sms * 4);
+    dist_pull_k<NW><<<grid, 512, 0, st>>>(dp.p, pieces.size(), d->xbuf.p, wc.p);
+    ctx->launches++;
+    SG_CUDA(cudaGetLastError());
+    ctx->times.exchange += tm.stop();
 }
 
 template <int NW>
@@ -1492,7 +1517,7 @@ static void dist_sort_nw(DistState *d, int p) {
         SG_CUDA(cudaMemcpyAsync(d_start.p, start.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
         Timer tm(st);
         Trace tr(st);
-        sort_pass<NW>(ctx, d->K, d->xbuf, d->ybuf, d_start.p, d_tot.p, PA, pl.rA, (uint32_t)my_lo, my_hi, d->first, d->want_counts, d->double_selfrc,
+        sort_pass<NW>(ctx, d->K, d->xbuf, d->sbuf, d_start.p, d_tot.p, PA, pl.rA, (uint32_t)my_lo, my_hi, d->first, d->want_counts, d->double_selfrc,
                       d->d_bsz.p, ch, tm, tr);
     } else {
         ch.n = 0; ch.b_lo = my_lo; ch.b_hi = my_hi; ch.first = d->first;
@@ -1536,11 +1561,10 @@ void dist_local_counts(DistState *d, uint64_t *h_out) {
 void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records) {
     Ctx *ctx = d->ctx;
     dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, (size_t)8 * d->nw);
-    d->d_cnt_all.alloc(ctx, (size_t)d->plan.world * d->plan.PA_all);
-    SG_CUDA(cudaMemcpyAsync(d->d_cnt_all.p, cnt_all, d->d_cnt_all.bytes(), cudaMemcpyHostToDevice, ctx->stream));
-    // exchange buffers come straight from the driver (cudaIpc needs allocation base pointers; the pool hands those out too)
+    d->h_cnt_all.assign(cnt_all, cnt_all + (size_t)d->plan.world * d->plan.PA_all);
+    // staging buffer: exported through cudaIpc (pool blocks are whole driver allocations, as cudaIpcGetMemHandle requires)
+    d->sbuf.alloc(ctx, (size_t)std::max(d->plan.max_recv, d->plan.max_send) * d->nw + 2);
     d->xbuf.alloc(ctx, (size_t)d->plan.max_recv * d->nw + 2);
-    d->ybuf.alloc(ctx, (size_t)d->plan.max_recv * d->nw + 2);
     d->d_bsz.alloc(ctx, (size_t)d->B);
     SG_CUDA(cudaMemsetAsync(d->d_bsz.p, 0, (size_t)d->B * 8, ctx->stream));
     d->out = new KSet();
@@ -1550,7 +1574,7 @@ void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int
 }
 void dist_ipc_handle(DistState *d, uint8_t *out64) {
     cudaIpcMemHandle_t h;
-    SG_CUDA(cudaIpcGetMemHandle(&h, d->xbuf.p));
+    SG_CUDA(cudaIpcGetMemHandle(&h, d->sbuf.p));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(out64, &h, 64);
 }
@@ -1559,21 +1583,24 @@ void dist_open_peers(DistState *d, const uint8_t *handles) {
     const int world = d->plan.world;
     d->peer.assign(world, nullptr);
     for (int g = 0; g < world; ++g) {
-        if (g == d->plan.rank) { d->peer[g] = d->xbuf.p; continue; }
+        if (g == d->plan.rank) { d->peer[g] = d->sbuf.p; continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)g * 64, 64);
         void *p = nullptr;
         SG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         d->peer[g] = (uint64_t *)p;
     }
-    d->d_peer.alloc(ctx, (size_t)world);
-    SG_CUDA(cudaMemcpyAsync(d->d_peer.p, d->peer.data(), (size_t)world * sizeof(uint64_t *), cudaMemcpyHostToDevice, ctx->stream));
-    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    (void)ctx;
 }
 void dist_scatter(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
     DIST_DISPATCH(dist_scatter_nw, d, p);
-    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // all of this rank's peer stores have been issued and completed
+    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // the staging buffer is complete; peers may read it after the next barrier
+}
+void dist_exchange(DistState *d, int p) {
+    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    DIST_DISPATCH(dist_pull_nw, d, p);
+    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // this rank no longer reads any peer's staging buffer
 }
 void dist_sort(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");

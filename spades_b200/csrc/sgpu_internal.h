@@ -62,7 +62,7 @@ struct DArr {
 };
 
 struct PhaseTimes {   // device milliseconds measured with CUDA events on ctx->stream
-    float extract_count = 0, extract_scatter = 0, refine = 0, local_sort = 0, compact = 0, mphf = 0, total = 0;
+    float extract_count = 0, extract_scatter = 0, refine = 0, local_sort = 0, compact = 0, mphf = 0, exchange = 0, total = 0;
     uint64_t launches = 0;
     uint64_t instances = 0;       // records written by the partition kernel
     uint64_t passes = 0;
@@ -220,6 +220,7 @@ void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int
 void dist_ipc_handle(DistState *d, uint8_t *out64);
 void dist_open_peers(DistState *d, const uint8_t *handles);
 void dist_scatter(DistState *d, int p);
+void dist_exchange(DistState *d, int p);
 void dist_sort(DistState *d, int p);
 KSet *dist_end(DistState *d);
 void dist_free(DistState *d);

@@ -1,5 +1,5 @@
 """Multi-GPU k-mer counting: one process per GPU, torch.distributed for the small tables and the barriers,
-the record exchange itself happens inside the fused partition kernel over NVLink peer memory (sgpu_dist_scatter).
+the record exchange itself is one kernel over NVLink peer memory (sgpu_dist_exchange: pull + merge).
 
 Mirrors what hpcspades distributes with MPI tasks + a shared filesystem (projects/hpcspades/mpi/stages/construction_mpi.cpp:222-300):
 every rank reads its own slice of the reads; afterwards every bucket lives on exactly one rank.
@@ -49,9 +49,10 @@ class DistributedKMerCounter:
             handles = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
             ctx.check(L.sgpu_dist_open_peers(h, handles.ctypes.data_as(C.c_void_p)))
             for p in range(npass.value):
-                dist.barrier(group=self.group)          # every owner's buffer is free (previous pass sorted) and mapped
-                ctx.check(L.sgpu_dist_scatter(h, p))    # partition + exchange in one kernel
-                dist.barrier(group=self.group)          # every rank's peer stores have completed
+                ctx.check(L.sgpu_dist_scatter(h, p))    # local partition into the staging buffer
+                dist.barrier(group=self.group)          # every rank's staging buffer is complete
+                ctx.check(L.sgpu_dist_exchange(h, p))   # one kernel: pull my pieces from all peers over NVLink + merge
+                dist.barrier(group=self.group)          # nobody reads my staging buffer any more (it becomes the sort's partner)
                 ctx.check(L.sgpu_dist_sort(h, p))
             dist.barrier(group=self.group)
             ks = C.c_void_p()

@@ -117,4 +117,10 @@ def run_gpu():
 
 
 if __name__ == "__main__":
-    run_gpu()
+    try:
+        run_gpu()
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)
