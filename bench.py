@@ -233,11 +233,15 @@ def main():
     ctx = Context(local_rank, stream=stream.cuda_stream)
     nwords = n_reads * nwr
 
+    dcounter = None
+    if world > 1:
+        from spades_b200.distributed import DistributedKMerCounter
+        dcounter = DistributedKMerCounter(ctx, K)
+
     def count(ctx_):
-        # N>1: buckets are owned by ranks; the exchange is fused into the partition kernel (NVLink peer stores)
+        # N>1: buckets are owned by ranks; one pull kernel per rank does the exchange + merge over NVLink peer memory
         if world > 1:
-            from spades_b200.distributed import DistributedKMerCounter
-            return DistributedKMerCounter(ctx_, K).Count(B)
+            return dcounter.Count(B)
         return KMerDiskCounter(ctx_, DeBruijnReadKMerSplitter(K)).Count(B)
 
     def step_resident():

@@ -69,6 +69,7 @@ typedef struct sgpu_times {
     uint64_t passes;      /* bucket-group passes */
     uint64_t launches;    /* kernels launched by this context so far */
     uint64_t peak_bytes;  /* peak device memory held by this context */
+    uint64_t cached_bytes;/* freed device blocks kept by the context's caching allocator (reusable) */
 } sgpu_times;
 
 int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out);
@@ -136,6 +137,8 @@ int64_t sgpu_dist_num_partitions(const sgpu_dist *d);
 int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out);                 /* num_partitions host entries */
 int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_partitions, rank-major, host */, uint64_t budget_bytes,
                    int *npass, uint64_t *exchange_records);
+/* after plan: take over the buffers and peer mappings of a finished count (returns 1; then skip ipc_handle/open_peers), or 0 */
+int sgpu_dist_adopt(sgpu_dist *d, sgpu_dist *previous);
 int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64);                 /* 64-byte cudaIpcMemHandle of this rank's exchange buffer */
 int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x 64 bytes */);
 int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* partition this rank's shard into its staging buffer */

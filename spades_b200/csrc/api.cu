@@ -63,7 +63,7 @@ int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out) {
     const PhaseTimes &t = ctx->c.times;
     out->extract_count_ms = t.extract_count; out->extract_scatter_ms = t.extract_scatter; out->refine_ms = t.refine;
     out->local_sort_ms = t.local_sort; out->compact_ms = t.compact; out->mphf_ms = t.mphf; out->exchange_ms = t.exchange;
-    out->instances = t.instances; out->passes = t.passes; out->launches = ctx->c.launches; out->peak_bytes = ctx->c.peak;
+    out->instances = t.instances; out->passes = t.passes; out->launches = ctx->c.launches; out->peak_bytes = ctx->c.peak; out->cached_bytes = ctx->c.pool_cached;
     return SGPU_OK;
 }
 
@@ -357,6 +357,10 @@ int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out) {
 int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts, uint64_t budget_bytes, int *npass, uint64_t *exchange_records) {
     if (!d || !all_counts || !npass || !exchange_records) return SGPU_EINVAL;
     API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_plan(d->d, all_counts, budget_bytes, npass, exchange_records); })
+}
+int sgpu_dist_adopt(sgpu_dist *d, sgpu_dist *previous) {
+    if (!d) return 0;
+    try { return dist_adopt(d->d, previous ? previous->d : nullptr); } catch (...) { return 0; }
 }
 int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64) {
     if (!d || !out64) return SGPU_EINVAL;

@@ -1562,9 +1562,7 @@ void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int
     Ctx *ctx = d->ctx;
     dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, (size_t)8 * d->nw);
     d->h_cnt_all.assign(cnt_all, cnt_all + (size_t)d->plan.world * d->plan.PA_all);
-    // staging buffer: exported through cudaIpc (pool blocks are whole driver allocations, as cudaIpcGetMemHandle requires)
-    d->sbuf.alloc(ctx, (size_t)std::max(d->plan.max_recv, d->plan.max_send) * d->nw + 2);
-    d->xbuf.alloc(ctx, (size_t)d->plan.max_recv * d->nw + 2);
+    // buffers are allocated by dist_alloc_buffers() unless adopted from a previous count
     d->d_bsz.alloc(ctx, (size_t)d->B);
     SG_CUDA(cudaMemsetAsync(d->d_bsz.p, 0, (size_t)d->B * 8, ctx->stream));
     d->out = new KSet();
@@ -1573,6 +1571,12 @@ void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int
     *npass = d->plan.npass; *xchg_records = d->plan.max_recv;
 }
 void dist_ipc_handle(DistState *d, uint8_t *out64) {
+    // staging buffer: exported through cudaIpc (pool blocks are whole driver allocations, as cudaIpcGetMemHandle requires);
+    // 10% headroom so that the next count of a similar shard can adopt it
+    if (!d->sbuf.p) {
+        d->sbuf.alloc(d->ctx, (size_t)((double)std::max(d->plan.max_recv, d->plan.max_send) * 1.1) * d->nw + 2);
+        d->xbuf.alloc(d->ctx, (size_t)((double)d->plan.max_recv * 1.1) * d->nw + 2);
+    }
     cudaIpcMemHandle_t h;
     SG_CUDA(cudaIpcGetMemHandle(&h, d->sbuf.p));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1592,6 +1596,19 @@ void dist_open_peers(DistState *d, const uint8_t *handles) {
     }
     (void)ctx;
 }
+// reuse the staging / merged buffers and the opened peer mappings of a finished distributed count (cudaIpcOpenMemHandle of a
+// tens-of-GB buffer is expensive). Every rank takes the same decision: the capacities come from identical plans.
+int dist_adopt(DistState *d, DistState *old) {
+    if (!old || old->plan.world != d->plan.world || old->nw != d->nw || old->peer.empty()) return 0;
+    const size_t need_s = (size_t)std::max(d->plan.max_recv, d->plan.max_send) * d->nw + 2, need_x = (size_t)d->plan.max_recv * d->nw + 2;
+    if (old->sbuf.n < need_s || old->xbuf.n < need_x) return 0;
+    d->sbuf = std::move(old->sbuf);
+    d->xbuf = std::move(old->xbuf);
+    d->peer = std::move(old->peer);
+    old->peer.clear();
+    return 1;
+}
+
 void dist_scatter(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
     DIST_DISPATCH(dist_scatter_nw, d, p);
@@ -1624,7 +1641,6 @@ KSet *dist_end(DistState *d) {
     ks->n = d->first;
     SG_CHECK(ks->bstart[B] == ks->n, 6, "internal: distributed bucket sizes do not add up");
     d->out = nullptr;
-    dist_close(d);
     return ks;
 }
 void dist_free(DistState *d) {

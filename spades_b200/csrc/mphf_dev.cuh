@@ -4,7 +4,7 @@
 
 namespace sg {
 
-static const int kMaxChunks = 32;
+static const int kMaxChunks = 128;
 struct KeyTable {
     int nchunks;
     int64_t first[kMaxChunks + 1];
@@ -13,8 +13,11 @@ struct KeyTable {
 
 template <int NW>
 __device__ __forceinline__ Kmer<NW> table_key(const KeyTable &t, int64_t i) {
-    int c = 0;
-    while (c + 1 < t.nchunks && i >= t.first[c + 1]) ++c;
+    int c = 0, hi = t.nchunks - 1;
+    while (c < hi) {                                  // last chunk whose first record index is <= i
+        const int mid = (c + hi + 1) >> 1;
+        if (t.first[mid] <= i) c = mid; else hi = mid - 1;
+    }
     const uint64_t *p = t.keys[c] + (i - t.first[c]) * NW;
     Kmer<NW> k;
 #pragma unroll

@@ -219,6 +219,7 @@ void dist_local_counts(DistState *d, uint64_t *h_out);
 void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records);
 void dist_ipc_handle(DistState *d, uint8_t *out64);
 void dist_open_peers(DistState *d, const uint8_t *handles);
+int dist_adopt(DistState *d, DistState *old);
 void dist_scatter(DistState *d, int p);
 void dist_exchange(DistState *d, int p);
 void dist_sort(DistState *d, int p);

@@ -16,6 +16,17 @@ class DistributedKMerCounter:
 
     def __init__(self, ctx, K, mode=SGPU_CANONICAL, group=None):
         self.ctx, self.K, self.mode, self.group = ctx, K, mode, group
+        self._prev = None        # the last finished count: owner of reusable buffers and peer mappings
+
+    def close(self):
+        if self._prev is not None:
+            self.ctx.L.sgpu_dist_free(self._prev); self._prev = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def Count(self, num_buckets, budget_bytes=None):
         import torch
@@ -35,19 +46,20 @@ class DistributedKMerCounter:
             dist.all_gather(gathered, t_local, group=self.group)
             all_counts = np.ascontiguousarray(torch.stack(gathered).cpu().numpy().view(np.uint64))
             if budget_bytes is None:
-                free = torch.cuda.mem_get_info()[0] + ctx.times()["peak_bytes"] * 0
+                free = torch.cuda.mem_get_info()[0] + ctx.times()["cached_bytes"]
                 tb = torch.tensor([free], dtype=torch.int64, device=backend_dev)
                 dist.all_reduce(tb, op=dist.ReduceOp.MIN, group=self.group)
                 budget_bytes = int(int(tb.item()) * 0.85)
             npass, xrec = C.c_int(), C.c_uint64()
             ctx.check(L.sgpu_dist_plan(h, all_counts.ctypes.data_as(C.c_void_p), budget_bytes, C.byref(npass), C.byref(xrec)))
-            handle = np.zeros(64, np.uint8)
-            ctx.check(L.sgpu_dist_ipc_handle(h, handle.ctypes.data_as(C.c_void_p)))
-            t_h = torch.from_numpy(handle).to(backend_dev)
-            hs = [torch.empty_like(t_h) for _ in range(world)]
-            dist.all_gather(hs, t_h, group=self.group)
-            handles = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
-            ctx.check(L.sgpu_dist_open_peers(h, handles.ctypes.data_as(C.c_void_p)))
+            if not L.sgpu_dist_adopt(h, self._prev):
+                handle = np.zeros(64, np.uint8)
+                ctx.check(L.sgpu_dist_ipc_handle(h, handle.ctypes.data_as(C.c_void_p)))
+                t_h = torch.from_numpy(handle).to(backend_dev)
+                hs = [torch.empty_like(t_h) for _ in range(world)]
+                dist.all_gather(hs, t_h, group=self.group)
+                handles = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
+                ctx.check(L.sgpu_dist_open_peers(h, handles.ctypes.data_as(C.c_void_p)))
             for p in range(npass.value):
                 ctx.check(L.sgpu_dist_scatter(h, p))    # local partition into the staging buffer
                 dist.barrier(group=self.group)          # every rank's staging buffer is complete
@@ -58,9 +70,14 @@ class DistributedKMerCounter:
             ks = C.c_void_p()
             ctx.check(L.sgpu_dist_end(h, C.byref(ks)))
             self.npass = npass.value
+            if self._prev is not None:
+                L.sgpu_dist_free(self._prev)
+            self._prev = h
+            h = None
             return KMerDiskStorage(ctx, ks)
         finally:
-            L.sgpu_dist_free(h)
+            if h is not None:
+                L.sgpu_dist_free(h)
 
 
 def plan_host(world, num_buckets, key_bits, all_counts, budget_bytes, record_bytes):

@@ -76,11 +76,12 @@ def run_gpu():
     from spades_b200.packing import pack_reads, synthetic_reads
     ctx = Context(lrank)
     fails = []
-    for (K, B, n, budget) in ((56, 40, 6000, None), (22, 7, 4000, None), (78, 64, 3000, 3_000_000), (56, 16, 6000, 40_000_000)):
+    counters = {}
+    for (K, B, n, budget) in ((56, 40, 6000, None), (22, 7, 4000, None), (78, 64, 3000, 300_000_000), (56, 16, 6000, 280_000_000)):
         reads = synthetic_reads(n, 150, 4000, 0.01, seed=K + B)
         mine = reads[rank::world]
         ctx.set_reads(*pack_reads(mine))
-        cnt = DistributedKMerCounter(ctx, K)
+        cnt = counters.setdefault(K, DistributedKMerCounter(ctx, K))
         st = cnt.Count(B, budget_bytes=budget)
         keys, counts, bsz = st.kmers(), st.counts(), st.bucket_sizes()
         idx = KMerIndexBuilder(ctx).BuildIndex(st)            # per-rank index over its own buckets
