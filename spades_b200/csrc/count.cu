@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
     uint32_t *rhist = repcnt + kBins;                     // kBins  residual count -> cursor
     uint16_t *rstart = reinterpret_cast<uint16_t *>(rhist + kBins);           // kBins+2
     uint16_t *rcnt = rstart + kBins + 2;                  // kResCap multiplicity per residual slot
+    uint16_t *dres = rcnt + kResCap;                      // kBins  distinct residual keys per bin
     uint32_t *lsdcnt = rep;                               // fallback only (kSWarps*256 <= 3*kBins)
     __shared__ uint32_t tot[kSWarps + 1];
     __shared__ unsigned long long s_w;
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
         const int lo = (int)s.bits;
         const int r2 = (total_bits - lo) < kBinBits ? (total_bits - lo) : kBinBits;
         const uint32_t nb = 1u << r2;
-        for (uint32_t i = threadIdx.x; i < nb; i += kSThreads) { rep[i] = 0xffffffffu; repcnt[i] = 0; rhist[i] = 0; }
+        for (uint32_t i = threadIdx.x; i < nb; i += kSThreads) { rep[i] = 0xffffffffu; repcnt[i] = 0; rhist[i] = 0; dres[i] = 0; }
         __syncthreads();
         // ---- P1: load, elect representatives
         uint32_t dig[IPT];
@@ -837,26 +838,27 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
             }
         }
         __syncthreads();
-        // ---- P5: dedup + sort each bin's residual (tiny), count distinct keys per bin
-        uint32_t dloc[BPT];
-        uint32_t dsum = 0;
+        // ---- P5: the thread that owns a bin's representative deduplicates + sorts that bin's residual (tiny) and records
+        //          how many distinct residual keys the bin has. Work is per occupied bin, not per bin.
         if (!bad) {
 #pragma unroll
-            for (int q = 0; q < BPT; ++q) {
-                dloc[q] = 0;
-                if (b0 + q >= nb || rep[b0 + q] == 0xffffffffu) continue;
-                const uint32_t bs = rstart[b0 + q], be = rstart[b0 + q + 1];
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t i = threadIdx.x + j * kSThreads;
+                if (i >= n || rep[dig[j]] != i) continue;
+                const uint32_t b = dig[j];
+                const uint32_t bs = rstart[b], be = rstart[b + 1];
+                if (be == bs) continue;
                 uint32_t d = 0;
                 if (be - bs == 1) { rcnt[bs] = 1; d = 1; }
-                else if (be > bs) {
+                else {
                     uint32_t rem_end = be, p = bs, work = 0;
                     while (p < rem_end) {
                         const Kmer<NW> key = load_rec<NW>(R + (size_t)p * NW);
                         uint32_t c = 1, w = p + 1;
-                        for (uint32_t j = p + 1; j < rem_end; ++j) {
-                            const Kmer<NW> x = load_rec<NW>(R + (size_t)j * NW);
+                        for (uint32_t z = p + 1; z < rem_end; ++z) {
+                            const Kmer<NW> x = load_rec<NW>(R + (size_t)z * NW);
                             if (kmer_eq<NW>(x, key)) ++c;
-                            else { if (w != j) store_rec<NW>(R + (size_t)w * NW, x); ++w; }
+                            else { if (w != z) store_rec<NW>(R + (size_t)w * NW, x); ++w; }
                         }
                         work += rem_end - p;
                         rcnt[p] = (uint16_t)c;
@@ -879,8 +881,7 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
                         rcnt[z] = kc;
                     }
                 }
-                dloc[q] = d + 1;
-                dsum += d + 1;
+                dres[b] = (uint16_t)d;
             }
         }
         if (bad) s_flag = 1;
@@ -924,7 +925,14 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
             __syncthreads();
             continue;
         }
-        // ---- P6: output offsets, then every thread writes its bins in key order (representative merged into the residual list)
+        // ---- P6: output offset of every bin (exclusive scan of 1 + residual-distinct over the occupied bins), then the
+        //          representative's owner writes its bin in key order (representative merged into the sorted residual)
+        uint32_t dsum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            loc[q] = (b0 + q < nb && rep[b0 + q] != 0xffffffffu) ? 1u + dres[b0 + q] : 0u;
+            dsum += loc[q];
+        }
         uint32_t dinc = dsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -935,14 +943,24 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
         __syncthreads();
         uint32_t db = 0, all = 0;
         for (int w = 0; w < kSWarps; ++w) { if (w < warp) db += tot[w]; all += tot[w]; }
-        uint32_t o = db + dinc - dsum;
+        {
+            uint32_t run = db + dinc - dsum;
 #pragma unroll
-        for (int q = 0; q < BPT; ++q) {
-            if (!dloc[q]) continue;
-            const uint32_t b = b0 + q;
-            const Kmer<NW> rk = load_rec<NW>(A + (size_t)rep[b] * NW);
+            for (int q = 0; q < BPT; ++q) {
+                if (b0 + q < nb) rhist[b0 + q] = run;        // rhist is free after P4: output offset of the bin
+                run += loc[q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t i = threadIdx.x + j * kSThreads;
+            if (i >= n || rep[dig[j]] != i) continue;
+            const uint32_t b = dig[j];
+            const Kmer<NW> rk = load_rec<NW>(A + (size_t)i * NW);
             const uint32_t rc = repcnt[b] + 1;
-            const uint32_t bs = rstart[b], d = dloc[q] - 1;
+            const uint32_t bs = rstart[b], d = dres[b];
+            uint32_t o = rhist[b];
             bool placed = false;
             for (uint32_t z = 0; z < d; ++z) {
                 const Kmer<NW> x = load_rec<NW>(R + (size_t)(bs + z) * NW);
@@ -951,7 +969,7 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
                 }
                 store_rec<NW>(gsrc + (size_t)o * NW, x); gcnt[o] = rcnt[bs + z]; ++o;
             }
-            if (!placed) { store_rec<NW>(gsrc + (size_t)o * NW, rk); gcnt[o] = rc; ++o; }
+            if (!placed) { store_rec<NW>(gsrc + (size_t)o * NW, rk); gcnt[o] = rc; }
         }
         if (threadIdx.x == 0) ndist[si] = all;
         __syncthreads();
@@ -1015,7 +1033,7 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
                       int rA_, uint32_t b_lo, int b_hi, int64_t first, bool want_counts, bool double_selfrc, unsigned long long *d_bsz_p, Chunk &ch_out,
                       Timer &tm, Trace &tr) {
     constexpr int CAP = SortCfg<NW>::CAP;
-    const uint32_t TARGET = CAP * 3 / 8;
+    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 3) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     cudaStream_t st = ctx->stream;
         // ---- segments + refinement rounds
@@ -1067,7 +1085,7 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
         tm.start();
         {
             size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * kBins * sizeof(uint32_t) +
-                          ((size_t)kBins + 2 + kResCap) * sizeof(uint16_t) + 16;
+                          ((size_t)2 * kBins + 2 + kResCap) * sizeof(uint16_t) + 16;
             SG_CUDA(cudaFuncSetAttribute(local_sort3_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 1;
             SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, local_sort3_k<NW>, kSThreads, smem));
@@ -1109,7 +1127,7 @@ template <int NW, class Src>
 static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
                              KSet *out) {
     constexpr int CAP = SortCfg<NW>::CAP;
-    const uint32_t TARGET = CAP * 3 / 8;
+    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 3) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
     // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
