@@ -1033,7 +1033,7 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
                       int rA_, uint32_t b_lo, int b_hi, int64_t first, bool want_counts, bool double_selfrc, unsigned long long *d_bsz_p, Chunk &ch_out,
                       Timer &tm, Trace &tr) {
     constexpr int CAP = SortCfg<NW>::CAP;
-    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 3) / 8;   // mean segment length aimed for
+    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     cudaStream_t st = ctx->stream;
         // ---- segments + refinement rounds
@@ -1127,7 +1127,7 @@ template <int NW, class Src>
 static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
                              KSet *out) {
     constexpr int CAP = SortCfg<NW>::CAP;
-    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 3) / 8;   // mean segment length aimed for
+    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
     // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
@@ -1180,17 +1180,46 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
     SG_CUDA(cudaStreamSynchronize(st));
     ctx->times.extract_count += tm.stop();
     tr.mark("A1 count+totals");
+    // bucket-group passes: simulate the greedy "as many whole buckets as fit" plan to learn how many passes are needed, then
+    // aim for equally sized passes (a tiny last pass still costs a full scan of the source, and equal sizes let the caching
+    // allocator reuse the X / Y blocks)
+    auto bucket_records = [&](int b) {
+        uint64_t ib = 0;
+        for (uint32_t q = 0; q < (1u << rA); ++q) ib += h_part[((size_t)(b - s_lo) << rA) + q];
+        return ib;
+    };
+    auto bytes_needed = [&](uint64_t recs) { return (double)recs * W * 2.0 + (double)recs * (W + 4) * 0.6 + (64 << 20); };
+    auto current_limit = [&]() {
+        return ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(ctx->free_bytes() * 0.90);
+    };
+    uint64_t total_records = 0;
+    for (int b = s_lo; b < s_hi; ++b) total_records += bucket_records(b);
+    uint64_t pass_target = total_records;
+    {
+        double lim_sim = (double)current_limit();
+        int npass_sim = 0, b = s_lo;
+        while (b < s_hi) {
+            uint64_t I = 0; int b0 = b;
+            while (b < s_hi) {
+                uint64_t ib = bucket_records(b);
+                if (b > b0 && bytes_needed(I + ib) > lim_sim) break;
+                I += ib; ++b;
+                if ((uint32_t)(b - b0) << rA >= 8192u) break;
+            }
+            lim_sim -= (double)I * (W + 4) * 0.5;            // this pass's output stays resident
+            ++npass_sim;
+        }
+        pass_target = total_records / (uint64_t)npass_sim + total_records / 64 + 1;
+    }
     int b_lo = s_lo;
     while (b_lo < s_hi) {
-        // ---- plan this pass: as many whole buckets as fit next to what is already resident (X + Y + its own output)
-        size_t lim = ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(ctx->free_bytes() * 0.92);
+        // ---- plan this pass: whole buckets that fit next to what is already resident (X + Y + its own output)
+        size_t lim = current_limit();
         int b_hi = b_lo;
         uint64_t I = 0;
         while (b_hi < s_hi) {
-            uint64_t ib = 0;
-            for (uint32_t q = 0; q < (1u << rA); ++q) ib += h_part[((size_t)(b_hi - s_lo) << rA) + q];
-            double need = (double)(I + ib) * W * 2.0 + (double)(I + ib) * (W + 4) * 0.6 + (64 << 20);
-            if (b_hi > b_lo && need > (double)lim) break;
+            uint64_t ib = bucket_records(b_hi);
+            if (b_hi > b_lo && (bytes_needed(I + ib) > (double)lim || I + ib > pass_target)) break;
             I += ib; ++b_hi;
             if ((uint32_t)(b_hi - b_lo) << rA >= 8192u) break;
         }

@@ -59,14 +59,70 @@ __global__ void mphf_filter_k(KeyTable t, const uint64_t *__restrict__ alive, ui
         const uint64_t pos = level_pos<NW>(m, k, b, level, &w);
         keep = !((m.bits[w] >> (pos & 63)) & 1ull);
     }
+    // block-aggregated append: one global atomic per CTA (a per-warp atomic on the single counter serialises in L2)
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (mask) {
-        const int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == (__ffs(mask) - 1)) base = atomicAdd(next_n, (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-        const uint64_t slot = base + __popc(mask & ((1u << lane) - 1));
-        if (keep && slot < cap) next[slot] = (uint64_t)ki;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; ++w) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(next_n, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (keep) {
+        const uint64_t slot = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1));
+        if (slot < cap) next[slot] = (uint64_t)ki;
+    }
+}
+
+// fused filter(level) + insert(level+1): a key whose level bit was cleared (it collided) survives; it is appended to the next
+// alive list and, in the same thread, inserted into the next level's bitset (BooPHF.h:616-639 getLevel + insertIntoLevel)
+template <int NW>
+__global__ void mphf_advance_k(KeyTable t, const uint64_t *__restrict__ alive, uint64_t n, int level, MphfDev m, uint64_t *__restrict__ next,
+                               uint64_t cap, unsigned long long *__restrict__ next_n, int do_insert, uint64_t next_level_start,
+                               uint64_t *__restrict__ coll) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    int64_t ki = 0;
+    if (i < n) {
+        ki = alive ? (int64_t)alive[i] : (int64_t)i;
+        Kmer<NW> k = table_key<NW>(t, ki);
+        const uint32_t b = kmer_bucket<NW>(k, m.B);
+        LevelHasher lh(xxh3_128<NW>(k));
+        uint64_t h = 0;
+        for (int l = 0; l <= level; ++l) h = lh.next();
+        size_t p = (size_t)level * m.B + b;
+        uint64_t pos = mulhi64(h, m.dom[p]);
+        keep = !((m.bits[m.woff[p] + (pos >> 6)] >> (pos & 63)) & 1ull);
+        if (keep && do_insert) {
+            h = lh.next();
+            p += m.B;
+            pos = mulhi64(h, m.dom[p]);
+            const uint64_t w = m.woff[p] + (pos >> 6);
+            const unsigned long long bit = 1ull << (pos & 63);
+            unsigned long long old = atomicOr((unsigned long long *)&m.bits[w], bit);
+            if (old & bit) atomicOr((unsigned long long *)&coll[w - next_level_start], bit);
+        }
+    }
+    // block-aggregated append: one global atomic per CTA (a per-warp atomic on the single counter serialises in L2)
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_base;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; ++w) { unsigned c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(next_n, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (keep) {
+        const uint64_t slot = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1));
+        if (slot < cap) next[slot] = (uint64_t)ki;
     }
 }
 
@@ -185,18 +241,25 @@ static void build_nw(Ctx *ctx, const KSet *ks, Mphf *m) {
     DArr<uint64_t> aliveA, aliveB;
     const uint64_t *alive = nullptr;
     uint64_t n_alive = n;
+    // level 0 takes every key; afterwards one fused kernel per level tests the previous level's bit and inserts the
+    // survivors into the next level right away (one key load + one XXH3-128 per key and level instead of two)
+    mphf_insert_k<NW><<<div_up((int64_t)n_alive, 256), 256, 0, st>>>(t, alive, n_alive, 0, md, level_start[0], coll.p);
+    mphf_clear_k<<<div_up((int64_t)l0_words, 256), 256, 0, st>>>(m->bits.p + level_start[0], coll.p, l0_words);
+    ctx->launches += 2;
     for (int l = 0; l < kLevels - 1 && n_alive; ++l) {
-        const uint64_t lw = level_start[l + 1] - level_start[l];
-        mphf_insert_k<NW><<<div_up((int64_t)n_alive, 256), 256, 0, st>>>(t, alive, n_alive, l, md, level_start[l], coll.p);
-        mphf_clear_k<<<div_up((int64_t)lw, 256), 256, 0, st>>>(m->bits.p + level_start[l], coll.p, lw);
-        ctx->launches += 2;
-        // survivors: the expected fraction is ~0.22 of the level's input; size generously for level 0 and reuse after
+        const bool last = (l == kLevels - 2);              // level 23 has no successor bitset: only count what is left
         DArr<uint64_t> &next = (l & 1) ? aliveA : aliveB;
         uint64_t cap = (l == 0) ? n_alive / 2 + 1024 : n_alive;
         if (next.n < cap) next.alloc(ctx, cap);
         SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, st));
-        mphf_filter_k<NW><<<div_up((int64_t)n_alive, 256), 256, 0, st>>>(t, alive, n_alive, l, md, next.p, (uint64_t)next.n, d_cnt.p);
+        mphf_advance_k<NW><<<div_up((int64_t)n_alive, 256), 256, 0, st>>>(t, alive, n_alive, l, md, next.p, (uint64_t)next.n, d_cnt.p,
+                                                                         last ? 0 : 1, last ? 0 : level_start[l + 1], coll.p);
         ctx->launches++;
+        if (!last) {
+            const uint64_t lw = level_start[l + 2] - level_start[l + 1];
+            mphf_clear_k<<<div_up((int64_t)lw, 256), 256, 0, st>>>(m->bits.p + level_start[l + 1], coll.p, lw);
+            ctx->launches++;
+        }
         SG_CUDA(cudaGetLastError());
         unsigned long long c = 0;
         SG_CUDA(cudaMemcpyAsync(&c, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
