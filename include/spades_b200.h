@@ -139,8 +139,9 @@ int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_parti
                    int *npass, uint64_t *exchange_records);
 /* after plan: take over the buffers and peer mappings of a finished count (returns 1; then skip ipc_handle/open_peers), or 0 */
 int sgpu_dist_adopt(sgpu_dist *d, sgpu_dist *previous);
-int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64);                 /* 64-byte cudaIpcMemHandle of this rank's exchange buffer */
-int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x 64 bytes */);
+#define SGPU_IPC_BYTES 72
+int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out /* SGPU_IPC_BYTES: cudaIpcMemHandle_t + offset of the staging buffer */);
+int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x SGPU_IPC_BYTES */);
 int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* partition this rank's shard into its staging buffer */
 int sgpu_dist_exchange(sgpu_dist *d, int pass);                         /* fused NVLink exchange + merge: pulls the owned pieces from every peer */
 int sgpu_dist_sort(sgpu_dist *d, int pass);                             /* refinement + local sort + compaction of what arrived */

@@ -100,9 +100,9 @@ int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, con
     API_TRY(c, {
         SG_CUDA(cudaSetDevice(c->device));
         c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear(); c->staged_dirty = false;
-        if (c->r_words.n < nwords + 4) c->r_words.alloc(c, nwords + 4);
-        if (c->r_offs.n < (size_t)nreads + 1) c->r_offs.alloc(c, (size_t)nreads + 1);
-        if (c->r_lens.n < (size_t)nreads + 1) c->r_lens.alloc(c, (size_t)nreads + 1);
+        if (c->r_words.n < nwords + 4) c->r_words.alloc(c, nwords + 4, true);
+        if (c->r_offs.n < (size_t)nreads + 1) c->r_offs.alloc(c, (size_t)nreads + 1, true);
+        if (c->r_lens.n < (size_t)nreads + 1) c->r_lens.alloc(c, (size_t)nreads + 1, true);
         if (nwords) SG_CUDA(cudaMemcpyAsync(c->r_words.p, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
         if (nreads) {
             SG_CUDA(cudaMemcpyAsync(c->r_offs.p, offs, (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));

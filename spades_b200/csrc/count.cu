@@ -1109,8 +1109,8 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
         // ---- compaction into the dense chunk
         Chunk ch;
         ch.n = (int64_t)D; ch.b_lo = (int)b_lo; ch.b_hi = b_hi; ch.first = first;
-        ch.keys.alloc(ctx, (size_t)D * NW + 2);
-        if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1);
+        ch.keys.alloc(ctx, (size_t)D * NW + 2, true);
+        if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1, true);
         tm.start();
         if (nsegs) {
             compact_k<NW><<<div_up((int64_t)nsegs * 32, 256), 256, 0, st>>>(segs.p, nsegs, ndist.p, dbase.p, X.p, Y.p, K, want_counts ? 1 : 0,
@@ -1426,6 +1426,7 @@ struct DistState {
     DArr<uint64_t> d_cnt_all;                // world x PA_all
     DArr<uint64_t> sbuf, xbuf;               // staging buffer (peers read it; later the ping-pong partner) and the merged buffer
     std::vector<uint64_t *> peer;            // world mapped staging buffers (own entry = sbuf.p)
+    std::vector<void *> peer_base;           // what cudaIpcOpenMemHandle returned (to close)
     std::vector<uint64_t> h_cnt_all;         // world x PA_all
     DArr<unsigned long long> d_bsz;
     KSet *out = nullptr;
@@ -1568,8 +1569,8 @@ static void dist_sort_nw(DistState *d, int p) {
                       d->d_bsz.p, ch, tm, tr);
     } else {
         ch.n = 0; ch.b_lo = my_lo; ch.b_hi = my_hi; ch.first = d->first;
-        ch.keys.alloc(ctx, 2);
-        if (d->want_counts) ch.counts.alloc(ctx, 1);
+        ch.keys.alloc(ctx, 2, true);
+        if (d->want_counts) ch.counts.alloc(ctx, 1, true);
     }
     d->first += ch.n;
     d->out->chunks.push_back(std::move(ch));
@@ -1624,10 +1625,21 @@ void dist_ipc_handle(DistState *d, uint8_t *out64) {
         d->sbuf.alloc(d->ctx, (size_t)((double)std::max(d->plan.max_recv, d->plan.max_send) * 1.1) * d->nw + 2);
         d->xbuf.alloc(d->ctx, (size_t)((double)d->plan.max_recv * 1.1) * d->nw + 2);
     }
+    // the staging buffer is a sub-block of the context's arena (one driver allocation): export the arena's handle and
+    // the offset of the block inside it (72 bytes: cudaIpcMemHandle_t + u64 offset)
+    Ctx *ctx = d->ctx;
     cudaIpcMemHandle_t h;
-    SG_CUDA(cudaIpcGetMemHandle(&h, d->sbuf.p));
+    uint64_t off = 0;
+    const char *sp = (const char *)d->sbuf.p;
+    if (ctx->arena && sp >= ctx->arena && sp < ctx->arena + ctx->arena_size) {
+        SG_CUDA(cudaIpcGetMemHandle(&h, ctx->arena));
+        off = (uint64_t)(sp - ctx->arena);
+    } else {
+        SG_CUDA(cudaIpcGetMemHandle(&h, d->sbuf.p));
+    }
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(out64, &h, 64);
+    memcpy(out64 + 64, &off, 8);
 }
 void dist_open_peers(DistState *d, const uint8_t *handles) {
     Ctx *ctx = d->ctx;
@@ -1636,10 +1648,14 @@ void dist_open_peers(DistState *d, const uint8_t *handles) {
     for (int g = 0; g < world; ++g) {
         if (g == d->plan.rank) { d->peer[g] = d->sbuf.p; continue; }
         cudaIpcMemHandle_t h;
-        memcpy(&h, handles + (size_t)g * 64, 64);
+        uint64_t off = 0;
+        memcpy(&h, handles + (size_t)g * 72, 64);
+        memcpy(&off, handles + (size_t)g * 72 + 64, 8);
         void *p = nullptr;
         SG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        d->peer[g] = (uint64_t *)p;
+        d->peer_base.resize(world, nullptr);
+        d->peer_base[g] = p;
+        d->peer[g] = (uint64_t *)((char *)p + off);
     }
     (void)ctx;
 }
@@ -1652,7 +1668,8 @@ int dist_adopt(DistState *d, DistState *old) {
     d->sbuf = std::move(old->sbuf);
     d->xbuf = std::move(old->xbuf);
     d->peer = std::move(old->peer);
-    old->peer.clear();
+    d->peer_base = std::move(old->peer_base);
+    old->peer.clear(); old->peer_base.clear();
     return 1;
 }
 
@@ -1672,9 +1689,9 @@ void dist_sort(DistState *d, int p) {
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
 }
 static void dist_close(DistState *d) {
-    for (int g = 0; g < (int)d->peer.size(); ++g)
-        if (g != d->plan.rank && d->peer[g]) cudaIpcCloseMemHandle(d->peer[g]);
-    d->peer.clear();
+    for (int g = 0; g < (int)d->peer_base.size(); ++g)
+        if (g != d->plan.rank && d->peer_base[g]) cudaIpcCloseMemHandle(d->peer_base[g]);
+    d->peer.clear(); d->peer_base.clear();
 }
 KSet *dist_end(DistState *d) {
     Ctx *ctx = d->ctx;

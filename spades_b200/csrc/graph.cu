@@ -424,7 +424,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops) {
     const bool have_cov = g->mkp && kp->has_counts;
     MphfDev mkp = have_cov ? mphf_dev(g->mkp) : MphfDev();
     // masks
-    g->masks.alloc(ctx, nk + 8);
+    g->masks.alloc(ctx, nk + 8, true);
     SG_CUDA(cudaMemsetAsync(g->masks.p, 0, g->masks.bytes(), st));
     for (const Chunk &c : kp->chunks) {
         if (!c.n) continue;
@@ -434,7 +434,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops) {
     SG_CUDA(cudaGetLastError());
     // coverage in MPHF order
     if (have_cov) {
-        g->cov.alloc(ctx, (size_t)kp->n + 1);
+        g->cov.alloc(ctx, (size_t)kp->n + 1, true);
         SG_CUDA(cudaMemsetAsync(g->cov.p, 0, g->cov.bytes(), st));
         for (const Chunk &c : kp->chunks) {
             if (!c.n) continue;
@@ -444,7 +444,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops) {
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaStreamSynchronize(st));
-    g->masks_final.alloc(ctx, nk + 8);     // what the reference's ext index holds before unitig extraction mutates it
+    g->masks_final.alloc(ctx, nk + 8, true);     // what the reference's ext index holds before unitig extraction mutates it
     SG_CUDA(cudaMemcpyAsync(g->masks_final.p, g->masks.p, nk, cudaMemcpyDeviceToDevice, st));
     if (nk == 0) { SG_CUDA(cudaStreamSynchronize(st)); return; }
 

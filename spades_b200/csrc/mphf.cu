@@ -223,9 +223,9 @@ static void build_nw(Ctx *ctx, const KSet *ks, Mphf *m) {
     m->lastrank.assign(B, 0);
     const uint64_t total_words = m->total_words;
     const uint64_t nblocks = total_words / 8;
-    m->bits.alloc(ctx, total_words + 8);
-    m->ranks.alloc(ctx, nblocks + 1);
-    m->d_dom.alloc(ctx, m->dom.size()); m->d_woff.alloc(ctx, m->woff.size()); m->d_starts.alloc(ctx, m->starts.size());
+    m->bits.alloc(ctx, total_words + 8, true);
+    m->ranks.alloc(ctx, nblocks + 1, true);
+    m->d_dom.alloc(ctx, m->dom.size(), true); m->d_woff.alloc(ctx, m->woff.size(), true); m->d_starts.alloc(ctx, m->starts.size(), true);
     SG_CUDA(cudaMemsetAsync(m->bits.p, 0, m->bits.bytes(), st));
     SG_CUDA(cudaMemcpyAsync(m->d_dom.p, m->dom.data(), m->dom.size() * 8, cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemcpyAsync(m->d_woff.p, m->woff.data(), m->woff.size() * 8, cudaMemcpyHostToDevice, st));

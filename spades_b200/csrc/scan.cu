@@ -98,9 +98,9 @@ void exclusive_scan_u32_to_u64(Ctx *ctx, const uint32_t *in, uint64_t *out, size
 void ensure_reads_on_device(Ctx *ctx) {
     if (!ctx->staged_dirty) return;
     size_t nw = ctx->h_words.size();
-    ctx->r_words.alloc(ctx, nw + 4);                 // +padding: kmer_window may touch one word past a read
-    ctx->r_offs.alloc(ctx, ctx->h_offs.size());
-    ctx->r_lens.alloc(ctx, ctx->h_lens.size());
+    ctx->r_words.alloc(ctx, nw + 4, true);                 // +padding: kmer_window may touch one word past a read
+    ctx->r_offs.alloc(ctx, ctx->h_offs.size(), true);
+    ctx->r_lens.alloc(ctx, ctx->h_lens.size(), true);
     SG_CUDA(cudaMemsetAsync(ctx->r_words.p + nw, 0, 4 * sizeof(uint64_t), ctx->stream));
     if (nw) SG_CUDA(cudaMemcpyAsync(ctx->r_words.p, ctx->h_words.data(), nw * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->h_offs.empty()) {

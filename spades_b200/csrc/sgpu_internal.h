@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <iterator>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -47,7 +49,7 @@ struct DArr {
     size_t blk = 0;     // bytes of the underlying block
     Ctx *ctx = nullptr;
     DArr() {}
-    DArr(Ctx *c, size_t n_) { alloc(c, n_); }
+    DArr(Ctx *c, size_t n_, bool persistent = false) { alloc(c, n_, persistent); }
     DArr(const DArr &) = delete;
     DArr &operator=(const DArr &) = delete;
     DArr(DArr &&o) noexcept { p = o.p; n = o.n; blk = o.blk; ctx = o.ctx; o.p = nullptr; o.n = 0; o.blk = 0; }
@@ -56,7 +58,7 @@ struct DArr {
         return *this;
     }
     ~DArr() { release(); }
-    void alloc(Ctx *c, size_t n_);
+    void alloc(Ctx *c, size_t n_, bool persistent = false);
     void release();
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -90,67 +92,111 @@ struct Ctx {
     std::vector<uint64_t> h_words, h_offs;   // host staging until first use
     std::vector<uint32_t> h_lens;
     bool staged_dirty = false;
-    // caching device allocator: freed blocks are kept for reuse (a bench step repeats the same sizes), and are
-    // handed back to the driver only under memory pressure or when the context dies
-    std::vector<std::pair<void *, size_t>> pool_free;
-    size_t pool_cached = 0;
-    void *pool_alloc(size_t bytes, size_t *blk);
+    // device memory: one arena reserved from the driver at first use and sub-allocated with a coalescing free list.
+    // cudaMalloc/cudaFree of tens of GB cost 100s of ms and a 100 M-read step turns over ~300 GB of buffers; inside the
+    // arena an allocation is a map lookup. Short-lived buffers (X/Y ping-pong, scratch) grow from the bottom, long-lived
+    // results (k-mer chunks, MPHF, masks) from the top, so the big short-lived blocks keep finding the same hole.
+    char *arena = nullptr;
+    size_t arena_size = 0;
+    std::map<size_t, size_t> arena_free;                     // offset -> size, coalesced
+    std::vector<std::pair<void *, size_t>> direct;           // allocations that did not fit the arena
+    size_t pool_cached = 0;                                  // free bytes inside the arena
+    void arena_init();
+    void *pool_alloc(size_t bytes, size_t *blk, bool persistent);
     void pool_release(void *p, size_t blk);
     void pool_trim();
-    size_t free_bytes();     // driver-free + cached
+    size_t free_bytes();                                     // allocatable bytes (arena free list)
 };
 
-inline void Ctx::pool_trim() {
-    for (auto &b : pool_free) cudaFree(b.first);
-    pool_free.clear();
-    pool_cached = 0;
-}
-inline size_t Ctx::free_bytes() {
+inline void Ctx::arena_init() {
+    if (arena) return;
     size_t f = 0, t = 0;
     cudaMemGetInfo(&f, &t);
-    return f + pool_cached;
+    size_t want = hbm_budget ? hbm_budget : (size_t)((double)f * 0.92);
+    if (getenv("SGPU_ARENA_GB")) want = (size_t)atof(getenv("SGPU_ARENA_GB")) << 30;
+    want &= ~(size_t)((2u << 20) - 1);
+    while (want >= ((size_t)64 << 20)) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, want) == cudaSuccess) { arena = (char *)p; arena_size = want; break; }
+        cudaGetLastError();
+        want = (size_t)((double)want * 0.9) & ~(size_t)((2u << 20) - 1);
+    }
+    if (!arena) throw Error(4, "cannot reserve the device memory arena");
+    arena_free.clear();
+    arena_free[0] = arena_size;
+    pool_cached = arena_size;
 }
-inline void *Ctx::pool_alloc(size_t bytes, size_t *blk) {
-    size_t want = (bytes + 511) & ~(size_t)511;
-    int best = -1;
-    for (int i = 0; i < (int)pool_free.size(); ++i) {
-        size_t sz = pool_free[i].second;
-        if (sz >= want && sz <= want + want / 4 + (1 << 20) && (best < 0 || sz < pool_free[best].second)) best = i;
+inline void Ctx::pool_trim() {
+    if (arena) cudaFree(arena);
+    arena = nullptr; arena_size = 0; arena_free.clear(); pool_cached = 0;
+    for (auto &d : direct) cudaFree(d.first);
+    direct.clear();
+}
+inline size_t Ctx::free_bytes() {
+    if (!arena) arena_init();
+    return pool_cached;
+}
+inline void *Ctx::pool_alloc(size_t bytes, size_t *blk, bool persistent) {
+    if (!arena) arena_init();
+    const size_t want = (bytes + 511) & ~(size_t)511;
+    if (!persistent) {
+        for (auto it = arena_free.begin(); it != arena_free.end(); ++it) {
+            if (it->second >= want) {                         // first fit from the bottom
+                const size_t off = it->first, sz = it->second;
+                arena_free.erase(it);
+                if (sz > want) arena_free[off + want] = sz - want;
+                pool_cached -= want; *blk = want;
+                return arena + off;
+            }
+        }
+    } else {
+        for (auto it = arena_free.rbegin(); it != arena_free.rend(); ++it) {
+            if (it->second >= want) {                         // last fit, carved from the top end of the hole
+                const size_t off = it->first, sz = it->second;
+                if (sz == want) arena_free.erase(std::next(it).base());
+                else it->second = sz - want;
+                pool_cached -= want; *blk = want;
+                return arena + off + (sz - want);
+            }
+        }
     }
-    if (best >= 0) {
-        void *p = pool_free[best].first;
-        *blk = pool_free[best].second;
-        pool_cached -= *blk;
-        pool_free.erase(pool_free.begin() + best);
-        return p;
-    }
+    // does not fit (fragmentation or a request beyond the arena): ask the driver directly
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        pool_trim();
-        e = cudaMalloc(&p, want);
-    }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
         char m[256];
-        snprintf(m, sizeof m, "cudaMalloc(%zu bytes) failed: %s (resident %zu)", want, cudaGetErrorString(e), allocated);
+        snprintf(m, sizeof m, "out of device memory: %zu bytes requested, %zu free in the %zu-byte arena (in use %zu)", want, pool_cached, arena_size, allocated);
         throw Error(4, m);
     }
+    direct.push_back({p, want});
     *blk = want;
     return p;
 }
 inline void Ctx::pool_release(void *p, size_t blk) {
-    pool_free.push_back({p, blk});
-    pool_cached += blk;
+    char *c = (char *)p;
+    if (arena && c >= arena && c < arena + arena_size) {
+        size_t off = (size_t)(c - arena), sz = blk;
+        auto nxt = arena_free.lower_bound(off);
+        if (nxt != arena_free.end() && off + sz == nxt->first) { sz += nxt->second; nxt = arena_free.erase(nxt); }
+        if (nxt != arena_free.begin()) {
+            auto prv = std::prev(nxt);
+            if (prv->first + prv->second == off) { prv->second += sz; pool_cached += blk; return; }
+        }
+        arena_free[off] = sz;
+        pool_cached += blk;
+        return;
+    }
+    for (size_t i = 0; i < direct.size(); ++i)
+        if (direct[i].first == p) { cudaFree(p); direct.erase(direct.begin() + i); return; }
+    cudaFree(p);
 }
-
 template <class T>
-void DArr<T>::alloc(Ctx *c, size_t n_) {
+void DArr<T>::alloc(Ctx *c, size_t n_, bool persistent) {
     release();
     ctx = c; n = n_;
     size_t b = (n_ ? n_ : 1) * sizeof(T);
-    p = (T *)c->pool_alloc(b, &blk);
+    p = (T *)c->pool_alloc(b, &blk, persistent);
     c->allocated += blk;
     if (c->allocated > c->peak) c->peak = c->allocated;
 }

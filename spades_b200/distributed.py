@@ -53,7 +53,7 @@ class DistributedKMerCounter:
             npass, xrec = C.c_int(), C.c_uint64()
             ctx.check(L.sgpu_dist_plan(h, all_counts.ctypes.data_as(C.c_void_p), budget_bytes, C.byref(npass), C.byref(xrec)))
             if not L.sgpu_dist_adopt(h, self._prev):
-                handle = np.zeros(64, np.uint8)
+                handle = np.zeros(72, np.uint8)      # SGPU_IPC_BYTES
                 ctx.check(L.sgpu_dist_ipc_handle(h, handle.ctypes.data_as(C.c_void_p)))
                 t_h = torch.from_numpy(handle).to(backend_dev)
                 hs = [torch.empty_like(t_h) for _ in range(world)]
