@@ -39,15 +39,21 @@ struct ReadsSrc {
         uint32_t w = L >= K ? (uint32_t)(L - K + 1) : 0u;
         return both ? 2u * w : w;
     }
-    template <int NW>
-    __device__ __forceinline__ Kmer<NW> get(int64_t item, uint32_t j) const {
-        const uint64_t *s = words + offs[item];
+    template <int NW, typename Ptr>
+    __device__ __forceinline__ Kmer<NW> get_at(Ptr s, uint32_t j) const {
         uint32_t pos = both ? (j >> 1) : j;
         Kmer<NW> f = kmer_window<NW>(s, (int64_t)pos, K);
         Kmer<NW> r = kmer_rc<NW>(f, K);
         if (both) return (j & 1) ? r : f;
         return kmer_is_minimal<NW>(f, r) ? f : r;
     }
+    template <int NW>
+    __device__ __forceinline__ Kmer<NW> get(int64_t item, uint32_t j) const { return get_at<NW>(words + offs[item], j); }
+    // staging of a tile's packed reads in shared memory
+    static constexpr bool kStage = true;
+    __device__ __forceinline__ uint64_t first_word(int64_t item) const { return offs[item]; }
+    __device__ __forceinline__ uint64_t end_word(int64_t item) const { return offs[item] + (((uint64_t)lens[item] + 31) >> 5); }
+    __device__ __forceinline__ uint64_t stage_word(uint64_t w) const { return words[w]; }
 };
 
 // distinct (K+1)-mers -> their two K-mers in canonical form (DeBruijnKMerKMerSplitter with add_rc + IsMinimal filter)
@@ -57,6 +63,12 @@ struct KpomerSrc {
     int64_t n;
     int K;                  // target K
     __device__ __forceinline__ uint32_t nrec(int64_t) const { return 2u; }
+    static constexpr bool kStage = false;
+    __device__ __forceinline__ uint64_t first_word(int64_t) const { return 0; }
+    __device__ __forceinline__ uint64_t end_word(int64_t) const { return 0; }
+    __device__ __forceinline__ uint64_t stage_word(uint64_t) const { return 0; }
+    template <int NW, typename Ptr>
+    __device__ __forceinline__ Kmer<NW> get_at(Ptr, uint32_t) const { return Kmer<NW>(); }
     template <int NW>
     __device__ __forceinline__ Kmer<NW> get(int64_t item, uint32_t j) const {
         Kmer<NWS> x;
@@ -150,6 +162,54 @@ __device__ __forceinline__ int find_item(const uint32_t *pref, int nitems, uint3
     return lo;
 }
 
+// Stage a tile's packed reads in shared memory (ncu: the partition kernel's L1 hit rate on the read words dropped to 31 %
+// under its own store traffic and "long scoreboard" became its top stall). The reads of a tile are one contiguous word range
+// in every layout this library produces; anything else (or very long reads) falls back to global loads.
+static const int kStageWords = 2560;      // 20 KB: 256 reads x 10 words (<= 320 bp each)
+struct TileStage {
+    uint64_t words[kStageWords];
+    uint32_t off[kATile];
+};
+template <class Src>
+__device__ __forceinline__ bool tile_stage(const Src &src, int64_t item0, int nitems, TileStage &ts) {
+    if (!Src::kStage) return false;
+    __shared__ unsigned s_maxend;
+    const uint64_t w0 = src.first_word(item0);
+    if (threadIdx.x == 0) s_maxend = 0;
+    __syncthreads();
+    bool ok = true;
+    if ((int)threadIdx.x < nitems) {
+        const uint64_t a = src.first_word(item0 + threadIdx.x), b = src.end_word(item0 + threadIdx.x);
+        ok = a >= w0 && b >= a && b - w0 <= (uint64_t)kStageWords;
+        if (ok) { ts.off[threadIdx.x] = (uint32_t)(a - w0); atomicMax(&s_maxend, (unsigned)(b - w0)); }
+    }
+    const bool staged = __syncthreads_and(ok) != 0;
+    if (staged) {
+        const uint32_t nwords = s_maxend;
+        for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) ts.words[i] = src.stage_word(w0 + i);
+    }
+    __syncthreads();
+    return staged;
+}
+template <int NW, class Src>
+__device__ __forceinline__ Kmer<NW> tile_get(const Src &src, bool staged, const TileStage &ts, int64_t item0, int it, uint32_t j) {
+    if (Src::kStage && staged) return src.template get_at<NW>(ts.words + ts.off[it], j);
+    return src.template get<NW>(item0 + it, j);
+}
+// record stores bypass L1 allocation (they are never re-read by this kernel)
+template <int NW>
+__device__ __forceinline__ void store_rec_stream(uint64_t *dst, const Kmer<NW> &k) {
+    if (NW == 2) {
+        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(k.w[0]), "l"(k.w[1]) : "memory");
+    } else if (NW == 4) {
+        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(k.w[0]), "l"(k.w[1]) : "memory");
+        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"(k.w[2]), "l"(k.w[3]) : "memory");
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(dst + q), "l"(k.w[q]) : "memory");
+    }
+}
+
 template <int NW>
 __device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint32_t *part) {
     uint32_t b = kmer_bucket<NW>(k, p.B);
@@ -158,12 +218,27 @@ __device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint
     return true;
 }
 
+// records per tile (kATile items), for the per-record partition-id array
+template <class Src>
+__global__ void tile_totals_k(Src src, int64_t ntiles, uint32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t item0 = t * kATile;
+    uint32_t s = 0;
+    for (int i = lane; i < kATile && item0 + i < src.n; i += 32) s += src.nrec(item0 + i);
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[t] = s;
+}
+
 // items are split statically: CTA g owns tiles [g*tiles_per, ...) so that count and scatter agree
 template <int NW, class Src>
-__global__ void __launch_bounds__(kAThreads) levelA_count_k(Src src, LevelA p, uint32_t *__restrict__ blk_counts) {
+__global__ void __launch_bounds__(kAThreads) levelA_count_k(Src src, LevelA p, uint32_t *__restrict__ blk_counts,
+                                                            const uint64_t *__restrict__ tile_off, uint16_t *__restrict__ ids) {
     extern __shared__ uint32_t sm_dyn[];
     uint32_t *hist = sm_dyn;                  // PA
     __shared__ uint32_t pref[kATile + 1];
+    __shared__ TileStage ts;
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const int64_t ntiles = (src.n + kATile - 1) / kATile;
@@ -173,11 +248,15 @@ __global__ void __launch_bounds__(kAThreads) levelA_count_k(Src src, LevelA p, u
         const int64_t item0 = t * kATile;
         const int nitems = (int)min((int64_t)kATile, src.n - item0);
         const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        const bool staged = tile_stage(src, item0, nitems, ts);
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             int it = find_item(pref, nitems, i);
-            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
-            uint32_t part;
-            if (part_of<NW>(p, k, &part)) atomicAdd(&hist[part], 1u);
+            Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
+            uint32_t part = 0xffffu;
+            if (part_of<NW>(p, k, &part)) atomicAdd(&hist[part], 1u); else part = 0xffffu;
+            // remember the partition of every record: the scatter passes (one per bucket group) then neither hash nor
+            // even extract the records that are not theirs
+            if (ids) ids[tile_off[t] + i] = (uint16_t)part;
         }
         __syncthreads();
     }
@@ -205,11 +284,13 @@ __global__ void levelA_bases_k(const uint32_t *__restrict__ blk_counts, uint32_t
 }
 
 template <int NW, class Src>
-__global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out) {
+__global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
+                                                              const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids, uint32_t id_lo) {
     extern __shared__ uint32_t sm_dyn[];
     uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
     uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
     __shared__ uint32_t pref[kATile + 1];
+    __shared__ TileStage ts;
     uint64_t *mybase = base + (size_t)blockIdx.x * p.PA;
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
     __syncthreads();
@@ -220,18 +301,145 @@ __global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p,
         const int64_t item0 = t * kATile;
         const int nitems = (int)min((int64_t)kATile, src.n - item0);
         const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        const bool staged = tile_stage(src, item0, nitems, ts);
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            int it = find_item(pref, nitems, i);
-            Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
             uint32_t part;
-            if (part_of<NW>(p, k, &part)) {
+            if (ids) {
+                part = (uint32_t)ids[tile_off[t] + i] - id_lo;           // 0xffff - id_lo stays >= PA
+                if (part >= p.PA) continue;
+                int it = find_item(pref, nitems, i);
+                Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
                 uint32_t slot = atomicAdd(&cnt[part], 1u);
-                store_rec<NW>(out + (cur_base[part] + slot) * NW, k);
+                store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+            } else {
+                int it = find_item(pref, nitems, i);
+                Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
+                if (part_of<NW>(p, k, &part)) {
+                    uint32_t slot = atomicAdd(&cnt[part], 1u);
+                    store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+                }
             }
         }
         __syncthreads();
     }
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
+}
+
+// ---- radix-partition kernel, second generation: gather -> sort in shared memory -> coalesced flush -------------------
+// ncu on levelA_scatter_k: 49 GB written + 23 GB read back for 30 GB of records; every 16-byte store opened its own 32-byte
+// sector and partially written lines were evicted before their neighbours arrived (DRAM-random-access bound at ~0.5 TB/s).
+// Here a CTA only looks at the 2-byte partition ids the count pass left behind, extracts the records of the current
+// partition sub-range, collects them in shared memory, counting-sorts a batch by partition and writes every partition's
+// run with consecutive threads -> consecutive addresses, so sectors/lines leave the SM full. The sub-range is kept small
+// (<= kA2MaxParts partitions) so that a batch holds ~10 records per partition; the caller loops over sub-ranges, which is
+// cheap because records outside the sub-range cost one 2-byte load and a compare.
+static const int kA2Threads = 1024;
+static const int kA2Cap = 4096;          // pending records per batch (4096 x 16 B = 64 KB for NW = 2)
+static const int kA2MaxParts = 1024;     // one histogram bin per thread
+
+template <int NW, class Src>
+__global__ void __launch_bounds__(kA2Threads, 2) levelA_scatter2_k(Src src, int K, uint64_t *__restrict__ base /*[G][PA]*/, uint64_t *__restrict__ out,
+                                                                const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
+                                                                uint32_t id_lo, uint32_t PA) {
+    extern __shared__ uint64_t sm64[];
+    uint64_t *pend = sm64;                                                 // kA2Cap * NW
+    uint64_t *cur_base = pend + (size_t)kA2Cap * NW;                       // PA   running global cursor of this CTA
+    uint32_t *hist = reinterpret_cast<uint32_t *>(cur_base + kA2MaxParts); // kA2MaxParts  (-> exclusive offsets -> cursors)
+    uint32_t *off = hist + kA2MaxParts;                                    // kA2MaxParts+1
+    uint16_t *ppart = reinterpret_cast<uint16_t *>(off + kA2MaxParts + 1); // kA2Cap   partition of pending record
+    uint16_t *sidx = ppart + kA2Cap;                                       // kA2Cap   pending index in sorted order
+    __shared__ uint32_t pref[kATile + 1];
+    __shared__ uint32_t npend;
+    __shared__ uint32_t wtot[kA2Threads / 32];
+    uint64_t *mybase = base + (size_t)blockIdx.x * PA;
+    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) cur_base[i] = mybase[i];
+    if (threadIdx.x == 0) npend = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    auto flush = [&]() {
+        // all threads arrive with npend final
+        const uint32_t n = npend;
+        if (threadIdx.x < kA2MaxParts) hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) atomicAdd(&hist[ppart[j]], 1u);
+        __syncthreads();
+        // exclusive scan over PA <= 1024 bins, one per thread
+        uint32_t v = threadIdx.x < PA ? hist[threadIdx.x] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = wtot[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wtot[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t ex = wtot[warp] + inc - v;
+        if (threadIdx.x < PA) { off[threadIdx.x] = ex; hist[threadIdx.x] = ex; }
+        if (threadIdx.x == 0) off[PA] = n;
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) sidx[atomicAdd(&hist[ppart[j]], 1u)] = (uint16_t)j;
+        __syncthreads();
+        // flush in sorted order: thread q writes the q-th record; runs of one partition are contiguous in q AND in memory
+        for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+            const uint32_t j = sidx[q];
+            const uint32_t p = ppart[j];
+            store_rec<NW>(out + (cur_base[p] + (q - off[p])) * NW, load_rec<NW>(pend + (size_t)j * NW));
+        }
+        __syncthreads();
+        if (threadIdx.x < PA) cur_base[threadIdx.x] += off[threadIdx.x + 1] - off[threadIdx.x];
+        if (threadIdx.x == 0) npend = 0;
+        __syncthreads();
+    };
+
+    uint32_t np = 0;      // every thread's copy of the pending count
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        const uint16_t *tid_ids = ids + tile_off[t];
+        for (uint32_t i0 = 0; i0 < total; i0 += blockDim.x) {
+            const uint32_t i = i0 + threadIdx.x;
+            uint32_t part = 0xffffffffu;
+            if (i < total) part = (uint32_t)tid_ids[i] - id_lo;
+            const bool in = part < PA;
+            // one barrier per round: it orders the previous round's shared-memory appends and tells every thread how many
+            // records this round adds, so the flush decision is uniform without re-reading the (moving) counter
+            const uint32_t round_in = (uint32_t)__syncthreads_count(in);
+            if (np + round_in > (uint32_t)kA2Cap) { flush(); np = 0; }
+            np += round_in;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (m) {
+                uint32_t wbase = 0;
+                if (lane == __ffs(m) - 1) wbase = atomicAdd(&npend, (uint32_t)__popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, __ffs(m) - 1);
+                if (in) {
+                    const uint32_t slot = wbase + __popc(m & ((1u << lane) - 1));
+                    const int it = find_item(pref, nitems, i);
+                    const Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
+                    store_rec<NW>(pend + (size_t)slot * NW, k);
+                    ppart[slot] = (uint16_t)part;
+                }
+            }
+        }
+        __syncthreads();       // pref is rewritten by the next tile_prefix
+    }
+    __syncthreads();
+    flush();
+    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i];   // chained launches continue here
+    (void)K;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1167,10 +1375,32 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
     DArr<uint64_t> part_total_all(ctx, (size_t)PA_all + 1);
     std::vector<uint64_t> h_part(PA_all);
     SG_CUDA(cudaMemsetAsync(blk_counts.p, 0, blk_counts.bytes(), st));
+    // per-record partition ids (2 bytes per record), only worth it when it fits comfortably
+    std::vector<DArr<uint64_t>> tile_off(srcs.size());
+    std::vector<DArr<uint16_t>> ids(srcs.size());
+    const bool use_ids = PA_all < 0xffffu && !getenv("SGPU_NO_IDS") && (double)est_records * 2.0 < (double)ctx->free_bytes() * 0.15;
+    if (use_ids) {
+        for (size_t si = 0; si < srcs.size(); ++si) {
+            const Src &src = srcs[si];
+            if (src.n == 0) continue;
+            const int64_t ntiles = (src.n + kATile - 1) / kATile;
+            DArr<uint32_t> ttot(ctx, (size_t)ntiles + 1);
+            tile_off[si].alloc(ctx, (size_t)ntiles + 1);
+            SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
+            tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
+            ctx->launches++;
+            exclusive_scan_u32_to_u64(ctx, ttot.p, tile_off[si].p, (size_t)ntiles + 1);
+            uint64_t nrec_src = 0;
+            SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            ids[si].alloc(ctx, (size_t)nrec_src + 2);
+        }
+    }
     tm.start();
-    for (const Src &src : srcs) {
+    for (size_t si = 0; si < srcs.size(); ++si) {
+        const Src &src = srcs[si];
         if (src.n == 0) continue;
-        levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p);
+        levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
         ctx->launches++;
     }
     SG_CUDA(cudaGetLastError());
@@ -1243,12 +1473,35 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, G, part_start.p, base.p);
             ctx->launches++;
             tm.start();
+            if (use_ids && getenv("SGPU_SCATTER2")) {   // second-generation kernel is opt-in: correct, but slower than the direct scatter so far
+                // sub-ranges of <= kA2MaxParts partitions; each is one launch per source over the 2-byte ids
+                const size_t smem2 = (size_t)kA2Cap * NW * 8 + (size_t)kA2MaxParts * 8 + ((size_t)2 * kA2MaxParts + 1) * 4 + (size_t)2 * kA2Cap * 2 + 16;
+                SG_CUDA(cudaFuncSetAttribute(levelA_scatter2_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                const uint32_t sub_max = getenv("SGPU_A2_PARTS") ? (uint32_t)atoi(getenv("SGPU_A2_PARTS")) : 512u;
+                const uint32_t nsub = (PA + sub_max - 1) / sub_max;
+                for (uint32_t sb = 0; sb < nsub; ++sb) {
+                    const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
+                    if (q_hi == q_lo) continue;
+                    // base rows are [G][PA]: the kernel addresses row g at base + g*PA_sub, so give it a compacted copy
+                    DArr<uint64_t> sub_base(ctx, (size_t)G * (q_hi - q_lo));
+                    SG_CUDA(cudaMemcpy2DAsync(sub_base.p, (size_t)(q_hi - q_lo) * 8, base.p + q_lo, (size_t)PA * 8, (size_t)(q_hi - q_lo) * 8, (size_t)G,
+                                              cudaMemcpyDeviceToDevice, st));
+                    for (size_t si = 0; si < srcs.size(); ++si) {
+                        const Src &src = srcs[si];
+                        if (src.n == 0) continue;
+                        levelA_scatter2_k<NW, Src><<<G, kA2Threads, smem2, st>>>(src, K, sub_base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, q_hi - q_lo);
+                        ctx->launches++;
+                    }
+                }
+            } else {
             size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            for (const Src &src : srcs) {
+            for (size_t si = 0; si < srcs.size(); ++si) {
+                const Src &src = srcs[si];
                 if (src.n == 0) continue;
-                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p);
+                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p, tile_off[si].p, ids[si].p, p_lo);
                 ctx->launches++;
+            }
             }
             SG_CUDA(cudaGetLastError());
             ctx->times.extract_scatter += tm.stop();
@@ -1475,7 +1728,7 @@ static void dist_begin_nw(DistState *d) {
     Timer tm(st);
     tm.start();
     if (d->src.n) {
-        levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p);
+        levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
         ctx->launches++;
     }
     levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(d->blk_counts.p, PA_all, d->G, d->part_total_local.p);
@@ -1505,7 +1758,7 @@ static void dist_scatter_nw(DistState *d, int p) {
     size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
     SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (d->src.n) {
-        levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p);
+        levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u);
         ctx->launches++;
     }
     SG_CUDA(cudaGetLastError());
