@@ -51,6 +51,8 @@ void sgpu_destroy(sgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
+    for (UploadChunk &u : ctx->c.up_chunks) if (u.ev) cudaEventDestroy(u.ev);
+    if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
     ctx->c.pool_trim();
     if (ctx->c.stream && ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
@@ -75,6 +77,8 @@ int sgpu_reads_clear(sgpu_ctx *ctx) {
         c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear();
         c->r_words.release(); c->r_offs.release(); c->r_lens.release();
         c->d_words = nullptr; c->d_offs = nullptr; c->d_lens = nullptr; c->n_reads = 0; c->n_words = 0; c->staged_dirty = false;
+        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
+        c->up_chunks.clear();
     })
 }
 
@@ -91,6 +95,8 @@ int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwor
         }
         c->h_words.insert(c->h_words.end(), words, words + nwords);
         c->staged_dirty = true;
+        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
+        c->up_chunks.clear();
     })
 }
 
@@ -103,10 +109,35 @@ int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, con
         if (c->r_words.n < nwords + 4) c->r_words.alloc(c, nwords + 4, true);
         if (c->r_offs.n < (size_t)nreads + 1) c->r_offs.alloc(c, (size_t)nreads + 1, true);
         if (c->r_lens.n < (size_t)nreads + 1) c->r_lens.alloc(c, (size_t)nreads + 1, true);
-        if (nwords) SG_CUDA(cudaMemcpyAsync(c->r_words.p, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
-        if (nreads) {
-            SG_CUDA(cudaMemcpyAsync(c->r_offs.p, offs, (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));
-            SG_CUDA(cudaMemcpyAsync(c->r_lens.p, lens, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+        // chunked copy on a second stream; every chunk carries an event so that the first pass over the reads (per-chunk
+        // histogram kernels) overlaps the rest of the transfer. The window statistics the planner needs are taken on the
+        // host while the DMA engine works.
+        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
+        c->up_chunks.clear();
+        if (!c->copy_stream) SG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        const int nchunk = nreads >= (1 << 20) ? 8 : 1;
+        cudaEvent_t start_ev;
+        SG_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+        SG_CUDA(cudaEventRecord(start_ev, c->stream));                      // earlier work on the main stream may still read the old set
+        SG_CUDA(cudaStreamWaitEvent(c->copy_stream, start_ev, 0));
+        cudaEventDestroy(start_ev);
+        for (int q = 0; q < nchunk && nreads; ++q) {
+            UploadChunk u;
+            u.r0 = nreads * q / nchunk; u.r1 = nreads * (q + 1) / nchunk;
+            if (u.r1 == u.r0) continue;
+            const uint64_t w0 = offs[u.r0];
+            const uint64_t w1 = (u.r1 < nreads) ? offs[u.r1] : nwords;      // reads are consecutive in `words`
+            SG_CHECK(w1 >= w0 && w1 <= nwords, SGPU_EINVAL, "sgpu_reads_upload needs reads stored consecutively (ascending offsets)");
+            SG_CUDA(cudaMemcpyAsync(c->r_words.p + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            SG_CUDA(cudaMemcpyAsync(c->r_offs.p + u.r0, offs + u.r0, (size_t)(u.r1 - u.r0) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            SG_CUDA(cudaMemcpyAsync(c->r_lens.p + u.r0, lens + u.r0, (size_t)(u.r1 - u.r0) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+            SG_CUDA(cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+            SG_CUDA(cudaEventRecord(u.ev, c->copy_stream));
+            for (int64_t r = u.r0; r < u.r1; ++r) {
+                const uint32_t l = lens[r];
+                if (l < 256) u.hist[l]++; else { u.sum_long += l; u.n_long++; }
+            }
+            c->up_chunks.push_back(u);
         }
         c->d_words = c->r_words.p; c->d_offs = c->r_offs.p; c->d_lens = c->r_lens.p; c->n_reads = nreads; c->n_words = nwords;
     })
@@ -118,6 +149,8 @@ int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwo
     API_TRY(c, {
         c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear(); c->staged_dirty = false;
         c->r_words.release(); c->r_offs.release(); c->r_lens.release();
+        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
+        c->up_chunks.clear();
         c->d_words = d_words; c->d_offs = d_offs; c->d_lens = d_lens; c->n_reads = nreads; c->n_words = nwords;
     })
 }

@@ -1333,7 +1333,7 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
 
 template <int NW, class Src>
 static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
-                             KSet *out) {
+                             KSet *out, const std::vector<cudaEvent_t> *ready = nullptr, const std::vector<uint64_t> *src_records = nullptr) {
     constexpr int CAP = SortCfg<NW>::CAP;
     const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
@@ -1386,13 +1386,17 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             const int64_t ntiles = (src.n + kATile - 1) / kATile;
             DArr<uint32_t> ttot(ctx, (size_t)ntiles + 1);
             tile_off[si].alloc(ctx, (size_t)ntiles + 1);
+            if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));      // this source is still being uploaded
             SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
             tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
             ctx->launches++;
             exclusive_scan_u32_to_u64(ctx, ttot.p, tile_off[si].p, (size_t)ntiles + 1);
             uint64_t nrec_src = 0;
-            SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
-            SG_CUDA(cudaStreamSynchronize(st));
+            if (src_records) nrec_src = (*src_records)[si];                     // known on the host: no sync, the upload keeps overlapping
+            else {
+                SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
+                SG_CUDA(cudaStreamSynchronize(st));
+            }
             ids[si].alloc(ctx, (size_t)nrec_src + 2);
         }
     }
@@ -1400,6 +1404,7 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
     for (size_t si = 0; si < srcs.size(); ++si) {
         const Src &src = srcs[si];
         if (src.n == 0) continue;
+        if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));
         levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
         ctx->launches++;
     }
@@ -1540,6 +1545,24 @@ static KSet *count_reads_nw(Ctx *ctx, int K, int B, int mode) {
     KSet *ks = new KSet();
     ks->ctx = ctx; ks->K = K; ks->nw = NW; ks->B = B; ks->has_counts = (mode == kCanonical);
     try {
+        const bool both = (mode == kAllWindows);
+        if (!ctx->up_chunks.empty()) {
+            // reads are arriving from the host in chunks (sgpu_reads_upload): one source per chunk; each chunk's histogram pass
+            // starts as soon as its copy has landed, so the H2D transfer overlaps the first pass over the reads
+            std::vector<ReadsSrc> srcs;
+            std::vector<cudaEvent_t> ready;
+            std::vector<uint64_t> recs;
+            uint64_t total = 0;
+            for (const UploadChunk &c : ctx->up_chunks) {
+                ReadsSrc src;
+                src.words = ctx->d_words; src.offs = ctx->d_offs + c.r0; src.lens = ctx->d_lens + c.r0; src.n = c.r1 - c.r0; src.K = K; src.both = both;
+                uint64_t w = c.sum_long >= c.n_long * (uint64_t)(K - 1) ? c.sum_long - c.n_long * (uint64_t)(K - 1) : 0;
+                for (int l = K; l < 256; ++l) w += (uint64_t)c.hist[l] * (uint64_t)(l - K + 1);
+                w *= both ? 2 : 1;
+                srcs.push_back(src); ready.push_back(c.ev); recs.push_back(w); total += w;
+            }
+            run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), total, ks, &ready, &recs);
+        } else {
         DArr<unsigned long long> d_w(ctx, 1);
         SG_CUDA(cudaMemsetAsync(d_w.p, 0, 8, ctx->stream));
         if (ctx->n_reads) {
@@ -1550,9 +1573,10 @@ static KSet *count_reads_nw(Ctx *ctx, int K, int B, int mode) {
         SG_CUDA(cudaMemcpyAsync(&wn, d_w.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         SG_CUDA(cudaStreamSynchronize(ctx->stream));
         ReadsSrc src;
-        src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = (mode == kAllWindows);
+        src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = both;
         std::vector<ReadsSrc> srcs{src};
-        run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), (uint64_t)wn * (mode == kAllWindows ? 2 : 1), ks);
+        run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), (uint64_t)wn * (both ? 2 : 1), ks);
+        }
     } catch (...) { delete ks; throw; }
     return ks;
 }
@@ -1653,7 +1677,7 @@ void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint
         if (need <= (double)budget_bytes || np >= B || (uint32_t)(((B + np - 1) / np) << rA) <= 1u) break;
     }
     // a pass's partitions must also fit the scatter kernel's shared-memory tables
-    while ((((size_t)(B + pl.npass - 1) / pl.npass) << rA) > 4096 && pl.npass < B) {
+    while ((((size_t)(B + pl.npass - 1) / pl.npass) << rA) > 8192 && pl.npass < B) {
         ++pl.npass;
         pl.pass_b.assign(pl.npass + 1, 0);
         for (int p = 0; p <= pl.npass; ++p) pl.pass_b[p] = (int)((int64_t)B * p / pl.npass);
@@ -1842,6 +1866,7 @@ DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
     SG_CHECK(B >= 1 && B <= 8192, 2, "distributed count: num_buckets must be in [1, 8192]");
     SG_CHECK(world >= 1 && world <= 255 && rank >= 0 && rank < world, 2, "bad world/rank");
     ensure_reads_on_device(ctx);
+    for (const UploadChunk &u : ctx->up_chunks) SG_CUDA(cudaStreamWaitEvent(ctx->stream, u.ev, 0));   // a chunked upload may still be in flight
     ctx->times = PhaseTimes();
     DistState *d = new DistState();
     d->ctx = ctx; d->K = K; d->B = B; d->mode = mode; d->nw = nwords_of(K);
@@ -1849,7 +1874,9 @@ DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
     d->want_counts = (mode == kCanonical); d->double_selfrc = (mode == kCanonical) && (K % 2 == 0);
     d->src.words = ctx->d_words; d->src.offs = ctx->d_offs; d->src.lens = ctx->d_lens; d->src.n = ctx->n_reads; d->src.K = K; d->src.both = (mode == kAllWindows);
     int rA = 0;
-    while (rA < 8 && ((uint64_t)B << (rA + 1)) <= 4096 && rA + 1 <= 2 * K) ++rA;      // every rank must use the same geometry: depends on B only
+    // every rank must use the same geometry, so it depends on B only. As many level-A partitions as the shared-memory tables allow:
+    // an owner's segment is the union of all ranks' records of a partition, so finer partitions keep refinement at one round
+    while (rA < 8 && ((uint64_t)B << (rA + 1)) <= 8192 && rA + 1 <= 2 * K) ++rA;
     d->plan.world = world; d->plan.rank = rank; d->plan.B = B; d->plan.rA = rA; d->plan.PA_all = (uint32_t)B << rA;
     try { DIST_DISPATCH(dist_begin_nw, d); } catch (...) { delete d; throw; }
     return d;

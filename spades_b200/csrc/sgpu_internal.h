@@ -70,6 +70,13 @@ struct PhaseTimes {   // device milliseconds measured with CUDA events on ctx->s
     uint64_t passes = 0;
 };
 
+struct UploadChunk {      // one piece of a chunked host->device read upload (sgpu_reads_upload)
+    int64_t r0 = 0, r1 = 0;         // reads [r0, r1)
+    cudaEvent_t ev = nullptr;       // recorded on the copy stream when the piece has landed
+    uint64_t sum_long = 0, n_long = 0;   // reads of length >= 256: total bases and count
+    uint32_t hist[256] = {0};       // reads of length < 256 by length (exact window counts for any K without touching the device)
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -92,6 +99,8 @@ struct Ctx {
     std::vector<uint64_t> h_words, h_offs;   // host staging until first use
     std::vector<uint32_t> h_lens;
     bool staged_dirty = false;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<UploadChunk> up_chunks;      // non-empty while the current read set came from a chunked upload
     // device memory: one arena reserved from the driver at first use and sub-allocated with a coalescing free list.
     // cudaMalloc/cudaFree of tens of GB cost 100s of ms and a 100 M-read step turns over ~300 GB of buffers; inside the
     // arena an allocation is a map lookup. Short-lived buffers (X/Y ping-pong, scratch) grow from the bottom, long-lived
