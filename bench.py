@@ -331,7 +331,7 @@ def main():
         # algorithmic bytes per step of each kernel family: I = instances, D = distinct
         I, D = instances, distinct
         alg = {
-            "extract_scatter_ms": n_reads * nwr * 8 + I * W,                 # packed reads in, records out
+            "extract_scatter_ms": max(1, passes) * n_reads * nwr * 8 + I * W,   # packed reads in (once per bucket-group pass), records out
             "extract_count_ms": n_reads * nwr * 8,                           # packed reads in
             "refine_ms": 2 * I * W,                                          # one read + one write of every record
             "local_sort_ms": I * W + D * (W + 4),                            # records in, distinct records + counts out
@@ -356,7 +356,13 @@ def main():
                     "what": "pinned host reads -> sgpu_reads_upload -> sgpu_count -> sgpu_mphf_build -> sgpu_mphf_serialize + bucket sizes to host; sorted (k+1)-mers stay in HBM for the graph phases"},
             "phases_ms_per_step": per_step,
             "roofline": {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_step": int(alg[dom]),
+                         "peak_source": peak_src,
+                         # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_ncu_full_top_kernels_20M.csv,
+                         # 20 M-read workload, one launch): only quoted when the bench runs that workload
+                         "traffic": (73.4e9 if (n_reads == 20_000_000 and world == 1 and dom == "extract_scatter_ms") else None),
+                         "traffic_note": "ncu (20 M reads): levelA_scatter_k moves 25.1 GB read + 48.2 GB written for 31.2 GB algorithmic (2.35x): 16-byte stores force sector fills",
+                         "launches_per_step": int(max(1, passes)) if dom == "extract_scatter_ms" else None,
+                         "algorithmic_bytes_per_step": int(alg[dom]),
                          "all": {kernel_names[k2]: (alg[k2] / (per_step[k2] / 1e3) / 1e9 if per_step[k2] > 0 else None) for k2 in alg}},
         }
         if not args.no_cpu_baseline:
