@@ -220,7 +220,7 @@ __device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint
 
 // records per tile (kATile items), for the per-record partition-id array
 template <class Src>
-__global__ void tile_totals_k(Src src, int64_t ntiles, uint32_t *__restrict__ out) {
+__global__ void tile_totals_k(Src src, int64_t ntiles, uint32_t *__restrict__ out, uint32_t pad) {
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= ntiles) return;
     const int lane = threadIdx.x & 31;
@@ -228,7 +228,7 @@ __global__ void tile_totals_k(Src src, int64_t ntiles, uint32_t *__restrict__ ou
     uint32_t s = 0;
     for (int i = lane; i < kATile && item0 + i < src.n; i += 32) s += src.nrec(item0 + i);
     for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) out[t] = s;
+    if (lane == 0) out[t] = (s + pad - 1) / pad * pad;       // rows of the id array start 2*pad-byte aligned
 }
 
 // items are split statically: CTA g owns tiles [g*tiles_per, ...) so that count and scatter agree
@@ -402,6 +402,11 @@ __global__ void __launch_bounds__(kA2Threads, 2) levelA_scatter2_k(Src src, int 
     };
 
     uint32_t np = 0;      // every thread's copy of the pending count
+    __shared__ uint32_t rsum[3];     // records entering the batch per round, triple buffered (one barrier per round)
+    if (threadIdx.x < 3) rsum[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t round_no = 0;
+    constexpr int V = 4;             // consecutive records per thread and round
     const int64_t ntiles = (src.n + kATile - 1) / kATile;
     const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
@@ -409,28 +414,51 @@ __global__ void __launch_bounds__(kA2Threads, 2) levelA_scatter2_k(Src src, int 
         const int64_t item0 = t * kATile;
         const int nitems = (int)min((int64_t)kATile, src.n - item0);
         const uint32_t total = tile_prefix(src, item0, nitems, pref);
-        const uint16_t *tid_ids = ids + tile_off[t];
-        for (uint32_t i0 = 0; i0 < total; i0 += blockDim.x) {
-            const uint32_t i = i0 + threadIdx.x;
-            uint32_t part = 0xffffffffu;
-            if (i < total) part = (uint32_t)tid_ids[i] - id_lo;
-            const bool in = part < PA;
-            // one barrier per round: it orders the previous round's shared-memory appends and tells every thread how many
-            // records this round adds, so the flush decision is uniform without re-reading the (moving) counter
-            const uint32_t round_in = (uint32_t)__syncthreads_count(in);
+        const uint16_t *tid_ids = ids + tile_off[t];                        // 16-byte aligned row (tile totals are padded to 8)
+        for (uint32_t i0 = 0; i0 < total; i0 += V * blockDim.x, ++round_no) {
+            const uint32_t ib = i0 + V * threadIdx.x;
+            uint32_t part[V];
+            uint32_t c = 0;
+            {
+                ushort4 raw = make_ushort4(0xffff, 0xffff, 0xffff, 0xffff);
+                if (ib < total) raw = *reinterpret_cast<const ushort4 *>(tid_ids + ib);   // may cover row padding: masked below
+                const uint32_t r4[V] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    part[v] = (ib + v < total) ? r4[v] - id_lo : 0xffffffffu;
+                    c += part[v] < PA ? 1u : 0u;
+                }
+            }
+            // warp-inclusive scan of c -> slots of this warp are contiguous; the warp total also feeds the round total
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += x;
+            }
+            const uint32_t wtotal = __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t buf = round_no % 3u;
+            if (lane == 0 && wtotal) atomicAdd(&rsum[buf], wtotal);
+            __syncthreads();                                               // the only barrier of the round
+            const uint32_t round_in = rsum[buf];
+            if (threadIdx.x == 0) rsum[(round_no + 2u) % 3u] = 0;           // last read two rounds ago, next written two rounds ahead
             if (np + round_in > (uint32_t)kA2Cap) { flush(); np = 0; }
             np += round_in;
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (m) {
+            if (wtotal) {
                 uint32_t wbase = 0;
-                if (lane == __ffs(m) - 1) wbase = atomicAdd(&npend, (uint32_t)__popc(m));
-                wbase = __shfl_sync(0xffffffffu, wbase, __ffs(m) - 1);
-                if (in) {
-                    const uint32_t slot = wbase + __popc(m & ((1u << lane) - 1));
-                    const int it = find_item(pref, nitems, i);
-                    const Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
-                    store_rec<NW>(pend + (size_t)slot * NW, k);
-                    ppart[slot] = (uint16_t)part;
+                if (lane == 0) wbase = atomicAdd(&npend, wtotal);
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                uint32_t slot = wbase + inc - c;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (part[v] < PA) {
+                        const uint32_t i = ib + v;
+                        const int it = find_item(pref, nitems, i);
+                        const Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
+                        store_rec<NW>(pend + (size_t)slot * NW, k);
+                        ppart[slot] = (uint16_t)part[v];
+                        ++slot;
+                    }
                 }
             }
         }
@@ -1388,11 +1416,11 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             tile_off[si].alloc(ctx, (size_t)ntiles + 1);
             if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));      // this source is still being uploaded
             SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
-            tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
+            tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p, 8u);
             ctx->launches++;
             exclusive_scan_u32_to_u64(ctx, ttot.p, tile_off[si].p, (size_t)ntiles + 1);
             uint64_t nrec_src = 0;
-            if (src_records) nrec_src = (*src_records)[si];                     // known on the host: no sync, the upload keeps overlapping
+            if (src_records) nrec_src = (*src_records)[si] + 8ull * (uint64_t)ntiles;   // known on the host (+ row padding): no sync, the upload keeps overlapping
             else {
                 SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
                 SG_CUDA(cudaStreamSynchronize(st));
@@ -1478,11 +1506,11 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, G, part_start.p, base.p);
             ctx->launches++;
             tm.start();
-            if (use_ids && getenv("SGPU_SCATTER2")) {   // second-generation kernel is opt-in: correct, but slower than the direct scatter so far
+            if (use_ids && getenv("SGPU_SCATTER2")) {   // coalesced-flush kernel: opt-in. Correct, full-sector stores, but measured slower than the direct scatter
                 // sub-ranges of <= kA2MaxParts partitions; each is one launch per source over the 2-byte ids
                 const size_t smem2 = (size_t)kA2Cap * NW * 8 + (size_t)kA2MaxParts * 8 + ((size_t)2 * kA2MaxParts + 1) * 4 + (size_t)2 * kA2Cap * 2 + 16;
                 SG_CUDA(cudaFuncSetAttribute(levelA_scatter2_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                const uint32_t sub_max = getenv("SGPU_A2_PARTS") ? (uint32_t)atoi(getenv("SGPU_A2_PARTS")) : 512u;
+                const uint32_t sub_max = getenv("SGPU_A2_PARTS") ? (uint32_t)atoi(getenv("SGPU_A2_PARTS")) : 1024u;
                 const uint32_t nsub = (PA + sub_max - 1) / sub_max;
                 for (uint32_t sb = 0; sb < nsub; ++sb) {
                     const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
