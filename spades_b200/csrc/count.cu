@@ -124,13 +124,15 @@ static const int kAThreads = 1024;
 
 // tile prologue: per-item record counts -> exclusive prefix in shared memory; returns the tile total
 template <class Src>
-__device__ __forceinline__ uint32_t tile_prefix(const Src &src, int64_t item0, int nitems, uint32_t *pref /*kATile+1*/) {
+__device__ __forceinline__ uint32_t tile_prefix(const Src &src, int64_t item0, int nitems, uint32_t *pref /*kATile+1*/, uint32_t *uniform = nullptr) {
     // kAThreads >= kATile: thread t owns item t
     uint32_t c = 0;
     if ((int)threadIdx.x < nitems) c = src.nrec(item0 + threadIdx.x);
     // block scan over the first kATile threads (8 warps)
     __shared__ uint32_t wsum[kATile / 32 + 1];
+    __shared__ uint32_t s_c0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_c0 = c;
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -144,14 +146,18 @@ __device__ __forceinline__ uint32_t tile_prefix(const Src &src, int64_t item0, i
         for (int w = 0; w < kATile / 32; ++w) { uint32_t t = wsum[w]; wsum[w] = run; run += t; }
         wsum[kATile / 32] = run;
     }
-    __syncthreads();
+    // every item yields the same number of records (fixed-length reads): item = i / c0 instead of a binary search
+    const uint32_t c0 = s_c0;
+    const int same = __syncthreads_and((int)threadIdx.x >= nitems || c == c0);
     if ((int)threadIdx.x < kATile) pref[threadIdx.x] = wsum[warp] + inc - c;
     uint32_t total = wsum[kATile / 32];
     if (threadIdx.x == 0) pref[kATile] = total;
     __syncthreads();
+    if (uniform) *uniform = (same && c0) ? c0 : 0u;
     return total;
 }
 
+__device__ __forceinline__ int find_item_u(const uint32_t *pref, int nitems, uint32_t i, uint32_t uniform);
 __device__ __forceinline__ int find_item(const uint32_t *pref, int nitems, uint32_t i) {
     // largest t with pref[t] <= i   (pref is exclusive, nitems <= kATile)
     int lo = 0, hi = nitems - 1;
@@ -210,6 +216,10 @@ __device__ __forceinline__ void store_rec_stream(uint64_t *dst, const Kmer<NW> &
     }
 }
 
+__device__ __forceinline__ int find_item_u(const uint32_t *pref, int nitems, uint32_t i, uint32_t uniform) {
+    return uniform ? (int)(i / uniform) : find_item(pref, nitems, i);
+}
+
 template <int NW>
 __device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint32_t *part) {
     uint32_t b = kmer_bucket<NW>(k, p.B);
@@ -247,16 +257,18 @@ __global__ void __launch_bounds__(kAThreads) levelA_count_k(Src src, LevelA p, u
     for (int64_t t = t0; t < t1; ++t) {
         const int64_t item0 = t * kATile;
         const int nitems = (int)min((int64_t)kATile, src.n - item0);
-        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        uint32_t unif = 0;
+        const uint32_t total = tile_prefix(src, item0, nitems, pref, &unif);
         const bool staged = tile_stage(src, item0, nitems, ts);
+        const uint64_t toff = ids ? tile_off[t] : 0;
         for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            int it = find_item(pref, nitems, i);
+            int it = find_item_u(pref, nitems, i, unif);
             Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
             uint32_t part = 0xffffu;
             if (part_of<NW>(p, k, &part)) atomicAdd(&hist[part], 1u); else part = 0xffffu;
             // remember the partition of every record: the scatter passes (one per bucket group) then neither hash nor
             // even extract the records that are not theirs
-            if (ids) ids[tile_off[t] + i] = (uint16_t)part;
+            if (ids) ids[toff + i] = (uint16_t)part;
         }
         __syncthreads();
     }
@@ -300,19 +312,35 @@ __global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p,
     for (int64_t t = t0; t < t1; ++t) {
         const int64_t item0 = t * kATile;
         const int nitems = (int)min((int64_t)kATile, src.n - item0);
-        const uint32_t total = tile_prefix(src, item0, nitems, pref);
+        uint32_t unif = 0;
+        const uint32_t total = tile_prefix(src, item0, nitems, pref, &unif);
         const bool staged = tile_stage(src, item0, nitems, ts);
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            uint32_t part;
-            if (ids) {
-                part = (uint32_t)ids[tile_off[t] + i] - id_lo;           // 0xffff - id_lo stays >= PA
-                if (part >= p.PA) continue;
-                int it = find_item(pref, nitems, i);
-                Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
-                uint32_t slot = atomicAdd(&cnt[part], 1u);
-                store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
-            } else {
-                int it = find_item(pref, nitems, i);
+        if (ids) {
+            // ncu (source view) put 32 % of this kernel's stall samples on the consumer of the per-record 2-byte id load and
+            // 17 % on the binary search: issue four id loads before touching any of them, divide instead of searching
+            const uint16_t *row = ids + tile_off[t];
+            constexpr int U = 4;
+            for (uint32_t i0 = threadIdx.x; i0 < total; i0 += U * blockDim.x) {
+                uint32_t part[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t i = i0 + u * blockDim.x;
+                    part[u] = i < total ? (uint32_t)__ldg(row + i) - id_lo : 0xffffffffu;      // 0xffff - id_lo stays >= PA
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (part[u] >= p.PA) continue;
+                    const uint32_t i = i0 + u * blockDim.x;
+                    const int it = find_item_u(pref, nitems, i, unif);
+                    Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
+                    uint32_t slot = atomicAdd(&cnt[part[u]], 1u);
+                    store_rec_stream<NW>(out + (cur_base[part[u]] + slot) * NW, k);
+                }
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+                uint32_t part;
+                int it = find_item_u(pref, nitems, i, unif);
                 Kmer<NW> k = tile_get<NW>(src, staged, ts, item0, it, i - pref[it]);
                 if (part_of<NW>(p, k, &part)) {
                     uint32_t slot = atomicAdd(&cnt[part], 1u);
