@@ -463,6 +463,30 @@ __host__ __device__ uint64_t selftest_one(int op, int K, uint64_t arg, const uin
         }
     }
 }
+// op 10: the rolling window of the level-A kernels against direct extraction. keys = one packed sequence of n*NW words,
+// arg = its length in bases; unit u walks windows [24u, 24u+24). out[u] = (windows walked << 32) | mismatches.
+template <int NW>
+__host__ __device__ uint64_t selftest_roll_unit(int K, int L, const uint64_t *seq, int64_t u) {
+    const int nwin = L - K + 1;
+    const int64_t j0 = u * 24;
+    if (j0 >= nwin) return 0;
+    const int cnt = nwin - j0 < 24 ? (int)(nwin - j0) : 24;
+    RollState<NW> st;
+    roll_init<NW>(st, seq, (int)j0, K, cnt > 1);
+    uint64_t bad = 0;
+    for (int s = 0; s < cnt; ++s) {
+        if (s) roll_next<NW>(st, seq, K);
+        const Kmer<NW> f = kmer_window<NW>(seq, j0 + s, K);
+        const Kmer<NW> r = kmer_rc<NW>(f, K);
+        if (!kmer_eq<NW>(f, st.f) || !kmer_eq<NW>(r, st.r)) ++bad;
+    }
+    return ((uint64_t)cnt << 32) | bad;
+}
+template <int NW>
+__global__ void selftest_roll_k(int K, int L, const uint64_t *seq, int64_t n, uint64_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = selftest_roll_unit<NW>(K, L, seq, i);
+}
 template <int NW>
 __global__ void selftest_k(int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,14 +494,16 @@ __global__ void selftest_k(int op, int K, uint64_t arg, const uint64_t *keys, in
 }
 template <int NW>
 static void selftest_nw(Ctx *c, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
+    if (op == 10) SG_CHECK((int64_t)arg >= K && (int64_t)arg <= 32 * n * NW, SGPU_EINVAL, "roll self test: bad sequence length");
     if (!on_device) {
-        for (int64_t i = 0; i < n; ++i) out[i] = selftest_one<NW>(op, K, arg, keys + i * NW);
+        for (int64_t i = 0; i < n; ++i) out[i] = op == 10 ? selftest_roll_unit<NW>(K, (int)arg, keys, i) : selftest_one<NW>(op, K, arg, keys + i * NW);
         return;
     }
     SG_CHECK(c, SGPU_EINVAL, "device self test needs a context");
     DArr<uint64_t> dk(c, (size_t)n * NW), dout(c, (size_t)n);
     SG_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * NW * 8, cudaMemcpyHostToDevice, c->stream));
-    selftest_k<NW><<<div_up(n, 256), 256, 0, c->stream>>>(op, K, arg, dk.p, n, dout.p);
+    if (op == 10) selftest_roll_k<NW><<<div_up(n, 256), 256, 0, c->stream>>>(K, (int)arg, dk.p, n, dout.p);
+    else selftest_k<NW><<<div_up(n, 256), 256, 0, c->stream>>>(op, K, arg, dk.p, n, dout.p);
     c->launches++;
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));

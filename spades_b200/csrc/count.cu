@@ -19,6 +19,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "sgpu_internal.h"
 
@@ -351,6 +352,200 @@ __global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p,
         __syncthreads();
     }
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
+}
+
+// ---- level A, rolling generation ------------------------------------------------------------------------------------
+// ncu on the kernels above: 296 (count) and 250 (scatter) thread instructions per window, issue-bound at 74 % / latency-bound
+// at 27 % issue utilisation -- every record re-extracted its window from up to three packed words, re-ran FastRC, divided to
+// find its read and (scatter) waited for a 2-byte id load. Here the unit of work is a CHUNK of kRollC consecutive windows of
+// one read, walked by one thread with a rolling window + rolling reverse complement (kmer_dev.cuh roll_*): one shared-memory
+// word load per 32 bases, ~20 integer instructions per window, and in a bucket-group pass the windows of other groups cost
+// only the roll. The 2-byte partition ids of a chunk are 48 contiguous bytes: written as six 8-byte words by the count pass,
+// fetched as three 16-byte loads before the walk starts by every scatter pass. Reads only (canonical mode).
+static const int kRollC = 24;            // windows per chunk
+static const int kRollThreads = 512;     // 2-3 CTAs per SM; units of a tile are dealt round-robin to the threads
+
+struct RollTile {
+    uint32_t pref[kATile + 1];           // exclusive prefix of chunks per read
+    uint32_t len[kATile];                // read lengths
+};
+
+// per-read chunk counts -> exclusive prefix; returns the tile's chunk total. *uniform = chunks per read when every read of
+// the tile has the same (non-zero) count, else 0.
+__device__ __forceinline__ uint32_t roll_tile_prefix(const ReadsSrc &src, int64_t item0, int nitems, RollTile &rt, uint32_t *uniform) {
+    uint32_t c = 0;
+    if ((int)threadIdx.x < nitems) {
+        const int L = (int)src.lens[item0 + threadIdx.x];
+        rt.len[threadIdx.x] = (uint32_t)L;
+        const uint32_t w = L >= src.K ? (uint32_t)(L - src.K + 1) : 0u;
+        c = (w + kRollC - 1) / kRollC;
+    }
+    __shared__ uint32_t wsum[kATile / 32 + 1];
+    __shared__ uint32_t s_c0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_c0 = c;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (warp < kATile / 32 && lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < kATile / 32; ++w) { uint32_t t = wsum[w]; wsum[w] = run; run += t; }
+        wsum[kATile / 32] = run;
+    }
+    const uint32_t c0 = s_c0;
+    const int same = __syncthreads_and((int)threadIdx.x >= nitems || c == c0);
+    if ((int)threadIdx.x < kATile) rt.pref[threadIdx.x] = wsum[warp] + inc - c;
+    const uint32_t total = wsum[kATile / 32];
+    if (threadIdx.x == 0) rt.pref[kATile] = total;
+    __syncthreads();
+    *uniform = (same && c0) ? c0 : 0u;
+    return total;
+}
+
+// chunks per tile x kRollC = ids per tile (rows of the id array; a multiple of 8 ids = 16 bytes)
+__global__ void roll_tile_ids_k(ReadsSrc src, int64_t ntiles, uint32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t item0 = t * kATile;
+    uint32_t s = 0;
+    for (int i = lane; i < kATile && item0 + i < src.n; i += 32) {
+        const int L = (int)src.lens[item0 + i];
+        const uint32_t w = L >= src.K ? (uint32_t)(L - src.K + 1) : 0u;
+        s += (w + kRollC - 1) / kRollC;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) out[t] = s * kRollC;
+}
+
+// geometry of one unit (chunk): which read, which windows
+struct RollUnit { int it, j0, cnt; };
+__device__ __forceinline__ RollUnit roll_unit(const RollTile &rt, int nitems, uint32_t u, uint32_t unif, int K) {
+    RollUnit q;
+    q.it = find_item_u(rt.pref, nitems, u, unif);
+    q.j0 = (int)(u - rt.pref[q.it]) * kRollC;
+    const int nwin = (int)rt.len[q.it] - K + 1;
+    q.cnt = nwin - q.j0 < kRollC ? nwin - q.j0 : kRollC;
+    return q;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc src, LevelA p, uint32_t *__restrict__ blk_counts,
+                                                                      const uint64_t *__restrict__ tile_off, uint16_t *__restrict__ ids) {
+    extern __shared__ uint32_t sm_dyn[];
+    uint32_t *hist = sm_dyn;                  // PA
+    __shared__ RollTile rt;
+    __shared__ TileStage ts;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int K = p.K;
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        uint32_t unif = 0;
+        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
+        const bool staged = tile_stage(src, item0, nitems, ts);
+        uint64_t *row = ids ? reinterpret_cast<uint64_t *>(ids + tile_off[t]) : nullptr;
+        for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
+            const RollUnit q = roll_unit(rt, nitems, u, unif, K);
+            const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
+            RollState<NW> st;
+            roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
+#pragma unroll 1
+            for (int g = 0; g < kRollC / 4; ++g) {
+                uint64_t acc = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int s = 4 * g + e;
+                    uint32_t id = 0xffffu;
+                    if (s < q.cnt) {
+                        if (s > 0) roll_next<NW>(st, seq, K);
+                        const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                        uint32_t part;
+                        if (part_of<NW>(p, k, &part)) { atomicAdd(&hist[part], 1u); id = part; }
+                    }
+                    acc |= (uint64_t)id << (16 * e);
+                }
+                if (row) row[(size_t)u * (kRollC / 4) + g] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t *out = blk_counts + (size_t)blockIdx.x * p.PA;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) out[i] += hist[i];
+}
+
+template <int NW, bool HAS_IDS>
+__global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
+                                                                        const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
+                                                                        uint32_t id_lo) {
+    extern __shared__ uint32_t sm_dyn[];
+    uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    __shared__ RollTile rt;
+    __shared__ TileStage ts;
+    uint64_t *mybase = base + (size_t)blockIdx.x * p.PA;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
+    __syncthreads();
+    const int K = p.K;
+    const uint32_t PA = p.PA;
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        uint32_t unif = 0;
+        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
+        const bool staged = tile_stage(src, item0, nitems, ts);
+        const ulonglong2 *row = HAS_IDS ? reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]) : nullptr;
+        for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
+            uint64_t idw[kRollC / 4];
+            if (HAS_IDS) {
+                // the chunk's 24 ids, in flight while the window is set up
+#pragma unroll
+                for (int v = 0; v < kRollC / 8; ++v) {
+                    const ulonglong2 x = __ldg(row + (size_t)u * (kRollC / 8) + v);
+                    idw[2 * v] = x.x; idw[2 * v + 1] = x.y;
+                }
+            }
+            const RollUnit q = roll_unit(rt, nitems, u, unif, K);
+            const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
+            RollState<NW> st;
+            roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
+#pragma unroll
+            for (int s = 0; s < kRollC; ++s) {
+                if (s < q.cnt) {
+                    if (s > 0) roll_next<NW>(st, seq, K);
+                    if (HAS_IDS) {
+                        const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;     // 0xffff - id_lo stays >= PA
+                        if (part < PA) {
+                            const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                            const uint32_t slot = atomicAdd(&cnt[part], 1u);
+                            store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+                        }
+                    } else {
+                        const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                        uint32_t part;
+                        if (part_of<NW>(p, k, &part)) {
+                            const uint32_t slot = atomicAdd(&cnt[part], 1u);
+                            store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
 }
 
 // ---- radix-partition kernel, second generation: gather -> sort in shared memory -> coalesced flush -------------------
@@ -1387,6 +1582,13 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
         ch_out = std::move(ch);
 }
 
+// rolling level-A kernels (reads, canonical mode): SGPU_ROLL=0/1 overrides the default
+static const bool kRollDefault = false;
+static bool use_roll() {
+    const char *e = getenv("SGPU_ROLL");
+    return e ? atoi(e) != 0 : kRollDefault;
+}
+
 template <int NW, class Src>
 static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
                              KSet *out, const std::vector<cudaEvent_t> *ready = nullptr, const std::vector<uint64_t> *src_records = nullptr) {
@@ -1401,6 +1603,9 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
     cudaStream_t st = ctx->stream;
     Timer tm(st);
     Trace tr(st);
+    constexpr bool kIsReads = std::is_same<Src, ReadsSrc>::value;
+    bool roll = false;
+    if constexpr (kIsReads) roll = use_roll() && !srcs.empty() && !srcs[0].both;
 
     out->bsz.assign(B, 0);
     DArr<unsigned long long> d_bsz(ctx, B);
@@ -1444,11 +1649,15 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             tile_off[si].alloc(ctx, (size_t)ntiles + 1);
             if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));      // this source is still being uploaded
             SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
-            tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p, 8u);
+            if (roll) {
+                if constexpr (kIsReads) roll_tile_ids_k<<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
+            } else {
+                tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p, 8u);
+            }
             ctx->launches++;
             exclusive_scan_u32_to_u64(ctx, ttot.p, tile_off[si].p, (size_t)ntiles + 1);
             uint64_t nrec_src = 0;
-            if (src_records) nrec_src = (*src_records)[si] + 8ull * (uint64_t)ntiles;   // known on the host (+ row padding): no sync, the upload keeps overlapping
+            if (src_records && !roll) nrec_src = (*src_records)[si] + 8ull * (uint64_t)ntiles;   // known on the host (+ row padding): no sync, the upload keeps overlapping
             else {
                 SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
                 SG_CUDA(cudaStreamSynchronize(st));
@@ -1461,7 +1670,14 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         const Src &src = srcs[si];
         if (src.n == 0) continue;
         if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));
-        levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
+        if (roll) {
+            if constexpr (kIsReads) {
+                SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
+                levelA_count_roll_k<NW><<<G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
+            }
+        } else {
+            levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
+        }
         ctx->launches++;
     }
     SG_CUDA(cudaGetLastError());
@@ -1534,7 +1750,7 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, G, part_start.p, base.p);
             ctx->launches++;
             tm.start();
-            if (use_ids && getenv("SGPU_SCATTER2")) {   // coalesced-flush kernel: opt-in. Correct, full-sector stores, but measured slower than the direct scatter
+            if (use_ids && !roll && getenv("SGPU_SCATTER2")) {   // coalesced-flush kernel: opt-in. Correct, full-sector stores, but measured slower than the direct scatter
                 // sub-ranges of <= kA2MaxParts partitions; each is one launch per source over the 2-byte ids
                 const size_t smem2 = (size_t)kA2Cap * NW * 8 + (size_t)kA2MaxParts * 8 + ((size_t)2 * kA2MaxParts + 1) * 4 + (size_t)2 * kA2Cap * 2 + 16;
                 SG_CUDA(cudaFuncSetAttribute(levelA_scatter2_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -1551,6 +1767,19 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
                         const Src &src = srcs[si];
                         if (src.n == 0) continue;
                         levelA_scatter2_k<NW, Src><<<G, kA2Threads, smem2, st>>>(src, K, sub_base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, q_hi - q_lo);
+                        ctx->launches++;
+                    }
+                }
+            } else if (roll) {
+                if constexpr (kIsReads) {
+                    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    for (size_t si = 0; si < srcs.size(); ++si) {
+                        const Src &src = srcs[si];
+                        if (src.n == 0) continue;
+                        if (use_ids) levelA_scatter_roll_k<NW, true><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, tile_off[si].p, ids[si].p, p_lo);
+                        else levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u);
                         ctx->launches++;
                     }
                 }

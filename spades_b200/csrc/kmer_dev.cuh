@@ -163,6 +163,39 @@ SG_HD void kmer_shl(Kmer<NW> &k, int K, int c) {
 template <int NW>
 SG_HD int kmer_nuc(const Kmer<NW> &k, int i) { return (int)((k.w[i >> 5] >> ((i & 31) << 1)) & 3); }
 
+// ---- rolling window ---------------------------------------------------------------------------------
+// One thread walks consecutive windows of one read keeping the window AND its reverse complement: appending base c is
+// RtSeq::operator<<= on the forward strand (rtseq.hpp:459-476) and "complement enters at position 0, everything moves up
+// one nucleotide, the last one drops out" on the reverse strand (what RtSeq::operator>> of !kmer does, rtseq.hpp:569-588).
+// ~20 integer instructions per window for K <= 64 instead of re-extracting the window and re-running FastRC.
+template <int NW>
+struct RollState {
+    Kmer<NW> f, r;      // window, reverse complement of the window
+    uint64_t cw;        // the packed word the next base comes from, already shifted so that the base is in bits 0..1
+    int pnext;          // position (in the read) of the next base to append
+};
+// window at base j0; `more` = at least one more window follows (then the word holding base j0+K is fetched)
+template <int NW, typename Ptr>
+SG_HD void roll_init(RollState<NW> &st, Ptr seq, int j0, int K, bool more) {
+    st.f = kmer_window<NW>(seq, (int64_t)j0, K);
+    st.r = kmer_rc<NW>(st.f, K);
+    st.pnext = j0 + K;
+    st.cw = more ? (seq[st.pnext >> 5] >> ((st.pnext & 31) << 1)) : 0;
+}
+// advance to the next window; only legal while base `pnext` exists in the read
+template <int NW, typename Ptr>
+SG_HD void roll_next(RollState<NW> &st, Ptr seq, int K) {
+    if ((st.pnext & 31) == 0) st.cw = seq[st.pnext >> 5];
+    const uint64_t c = st.cw & 3;
+    st.cw >>= 2;
+    ++st.pnext;
+    kmer_shl<NW>(st.f, K, (int)c);
+#pragma unroll
+    for (int j = NW - 1; j >= 1; --j) st.r.w[j] = (st.r.w[j] << 2) | (st.r.w[j - 1] >> 62);
+    st.r.w[0] = (st.r.w[0] << 2) | (3 - c);
+    st.r.w[NW - 1] &= last_word_mask<NW>(K);
+}
+
 // prefix (drop last nucleotide) / suffix (drop first) of a (K+1)-mer as K-mers. NWS = words of the source.
 template <int NW, int NWS>
 SG_HD Kmer<NW> kmer_prefix(const Kmer<NWS> &x, int K) {

@@ -68,5 +68,31 @@ def check_all(ctx_h, on_device):
                 assert int(got[i]) == want, (K, pos, r_, i)
 
 
+def check_roll(ctx_h, on_device):
+    """op 10: the rolling window + rolling reverse complement of the level-A kernels (kmer_dev.cuh roll_init/roll_next)
+    against direct window extraction + FastRC, for every window of sequences whose lengths straddle word boundaries."""
+    rng = np.random.default_rng(99)
+    for K in (1, 2, 5, 21, 22, 31, 32, 33, 55, 56, 63, 64, 65, 77, 78, 96, 97, 127, 128):
+        nw = (K + 31) // 32
+        for L in (K, K + 1, K + 23, K + 24, K + 25, 150, 151, 192, 257, 1000):
+            if L < K:
+                continue
+            nwords = (L + 31) // 32
+            nrec = max((nwords + nw - 1) // nw, (L - K + 1 + 23) // 24 + 1)
+            codes = np.zeros(nrec * nw * 32, np.uint64)
+            codes[:L] = rng.integers(0, 4, L, dtype=np.uint64)
+            sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))
+            words = (codes.reshape(-1, 32) << sh).sum(axis=1, dtype=np.uint64).reshape(nrec, nw)
+            out = run_selftest(ctx_h, on_device, 10, K, L, words)
+            nwin = L - K + 1
+            for u in range(nrec):
+                cnt = min(24, max(0, nwin - 24 * u))
+                assert int(out[u]) == (cnt << 32), (K, L, u, hex(int(out[u])))
+
+
+def test_host_roll_matches_direct_extraction():
+    check_roll(None, 0)
+
+
 def test_host_arithmetic_matches_oracle():
     check_all(None, 0)
