@@ -15,6 +15,11 @@ SGPU_ROLL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu --ti
 echo "exit=$?" >> $O/c1_tests_roll.log
 tail -4 $O/c1_tests_roll.log
 
+step "parity, rolling kernels without the id array"
+SGPU_ROLL=1 SGPU_NO_IDS=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 100 -k "oracle_random or medium or ragged" > $O/c1_tests_roll_noids.log 2>&1
+echo "exit=$?" >> $O/c1_tests_roll_noids.log
+tail -3 $O/c1_tests_roll_noids.log
+
 for roll in 1 0; do
   [ $(left) -gt 60 ] || break
   step "bench 20M roll=$roll"
