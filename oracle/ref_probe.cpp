@@ -12,7 +12,8 @@
 // wrapped in RCWrap, the same fixture the reference's own construction_test uses,
 // test/debruijn/test_utils.cpp:128-138).
 //
-// usage: ref_probe <mode: count|graph> <reads.txt> <k> <num_buckets> <nthreads> <outdir>
+// usage: ref_probe <mode: count|graph|bench> <reads.txt> <k> <num_buckets> <nthreads> <outdir>   (env PROBE_EARLY_TC=<bound>: graph mode
+//        also runs EarlyTipClipperProcessor before the unitig extraction)
 //   reads.txt: one ACGT read per line (N-trimming is the ingest layer's job)
 #include "io/reads/vector_reader.hpp"
 #include "io/reads/rc_reader_wrapper.hpp"
@@ -26,6 +27,7 @@
 #include "kmer_index/extension_index/kmer_extension_index_builder.hpp"
 #include "assembly_graph/core/graph.hpp"
 #include "assembly_graph/construction/debruijn_graph_constructor.hpp"
+#include "assembly_graph/construction/early_simplification.hpp"
 #include "assembly_graph/graph_support/coverage_filling.hpp"
 #include "io/graph/gfa_writer.hpp"
 #include "utils/logger/log_writers.hpp"
@@ -182,6 +184,17 @@ int main(int argc, char **argv) {
         dump_index(static_cast<const kmers::IndexWrapper<RtSeq, kmers::slim_kmer_index_traits<RtSeq>>&>(ext), outdir / "kmer_index.bin");
         std::ofstream ms(outdir / "masks.bin", std::ios::binary);
         ms.write(ext.raw_data(), ext.raw_size());
+    }
+
+    // PROBE_EARLY_TC=<length bound>: the pipeline's early tip clipper (stages/construction.cpp:289-302) between the mask
+    // fill and the unitig extraction; masks.bin above is the array before, masks_tc.bin the array after
+    if (const char *tc = getenv("PROBE_EARLY_TC")) {
+        size_t bound = (size_t)atoll(tc);
+        size_t removed = EarlyTipClipperProcessor(ext, bound).ClipTips();
+        std::ofstream ms(outdir / "masks_tc.bin", std::ios::binary);
+        ms.write(ext.raw_data(), ext.raw_size());
+        std::ofstream rs(outdir / "tc_removed.txt");
+        rs << removed << "\n";
     }
 
     unsigned nchunks = 16 * omp_get_max_threads();

@@ -552,6 +552,87 @@ static void remove_seq(gctx_t *g, const uint8_t *s, int64_t n) {
     for (int64_t pos = g->K; pos < n; ++pos) { kmer_shl(km, g->K, s[pos]); g->masks[canon_idx(g->m, km, g->K, &mn)] = 0; }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Early tip clipper: EarlyTipClipperProcessor (assembly_graph/construction/early_simplification.hpp:38-162) +
+ * RemoveInconsistentForwardLinks (:21-36). Works on the mask array in place. Iteration order of the reference with one
+ * thread: k-mers in final_kmers order (index_.kmer_begin), each as seq then !seq (:69-71).
+ *   snapshot == 0 : the reference's sequential semantics (walks see the removals made so far)
+ *   snapshot != 0 : every walk sees the masks as they were before the clipper started (what a data-parallel
+ *                   implementation computes); tests assert both give the same array.
+ * Returns the number of removed k-mers (ClipTips' return value, :57,102-103); *n_tipped / *n_clipped = the two INFO counters.
+ * ---------------------------------------------------------------------------------------------- */
+static int etc_find_forward(const gctx_t *g, const uint64_t *first, int64_t bound, uint64_t *idx_out /* bound+1 */) {
+    /* FindForward, :115-125. returns the tip size (0 = not a tip) and the canonical indices of its vertices */
+    int K = g->K, nw = nwords(K);
+    uint64_t kh[MAXW]; memcpy(kh, first, 8 * nw);
+    int64_t n = 0; int mn;
+    for (;;) {
+        uint8_t m = g_mask(g, kh);
+        if (!(n < bound && m_unique_in(m) >= 0 && m_unique_out(m) >= 0)) break;
+        idx_out[n++] = canon_idx(g->m, kh, K, &mn);
+        kmer_shl(kh, K, m_unique_out(m));
+    }
+    idx_out[n++] = canon_idx(g->m, kh, K, &mn);
+    uint8_t m = g_mask(g, kh);
+    if (m_unique_in(m) < 0 || (m & 15) != 0) return 0;
+    return (int)n;
+}
+int64_t orc_early_tip_clip(const kset_t *km, const mphf_t *mk, uint8_t *masks, int64_t length_bound, int snapshot,
+                           int64_t *n_tipped, int64_t *n_clipped) {
+    int K = km->K, nw = km->nw;
+    uint8_t *view = masks;
+    if (snapshot) { view = (uint8_t *)malloc((size_t)(km->n ? km->n : 1)); memcpy(view, masks, (size_t)km->n); }
+    gctx_t g; g.m = mk; g.K = K; g.masks = view;
+    uint64_t *tips[4];
+    for (int c = 0; c < 4; ++c) tips[c] = (uint64_t *)malloc((size_t)(length_bound + 2) * 8);
+    uint64_t *tj = NULL; int64_t ntj = 0, ctj = 0;          /* tipped junctions: k-mer words */
+    int64_t removed = 0;
+    for (int64_t i = 0; i < km->n; ++i) {
+        for (int o = 0; o < 2; ++o) {
+            uint64_t kh[MAXW];
+            if (o == 0) memcpy(kh, km->keys + i * nw, 8 * nw); else orc_rc(km->keys + i * nw, K, kh);
+            uint8_t m = g_mask(&g, kh);
+            if (__builtin_popcount(m & 15) < 2) continue;
+            /* RemoveForward, :143-155 */
+            size_t max = 0; int sz[4] = {0, 0, 0, 0};
+            for (int c = 0; c < 4; ++c) {
+                if (!(m & (1 << c))) continue;
+                uint64_t khc[MAXW]; memcpy(khc, kh, 8 * nw); kmer_shl(khc, K, c);
+                sz[c] = etc_find_forward(&g, khc, length_bound, tips[c]);
+                size_t len = sz[c] ? (size_t)sz[c] : (size_t)-1;
+                if (len > max) max = len;
+            }
+            int64_t rem = 0;
+            for (int c = 0; c < 4; ++c)
+                if ((size_t)sz[c] < max) { for (int t = 0; t < sz[c]; ++t) masks[tips[c][t]] = 0; rem += sz[c]; }   /* IsolateVertex */
+            removed += rem;
+            if (rem) {
+                if (ntj == ctj) { ctj = ctj ? 2 * ctj : 64; tj = (uint64_t *)realloc(tj, (size_t)ctj * nw * 8); }
+                memcpy(tj + ntj * nw, kh, 8 * nw); ++ntj;
+            }
+        }
+    }
+    /* RemoveInconsistentForwardLinks over the tipped junctions, :21-36,88-96 (sees the final masks) */
+    g.masks = masks;
+    int64_t clipped = 0;
+    for (int64_t j = 0; j < ntj; ++j) {
+        const uint64_t *kh = tj + j * nw;
+        uint8_t m = g_mask(&g, kh);
+        int mn; uint64_t idx = canon_idx(mk, kh, K, &mn);
+        for (int c = 0; c < 4; ++c) {
+            if (!(m & (1 << c))) continue;
+            uint64_t nx[MAXW]; memcpy(nx, kh, 8 * nw); kmer_shl(nx, K, c);
+            if (!(g_mask(&g, nx) & (1 << (4 + getnuc(kh, 0))))) { masks[idx] &= (uint8_t)~(1u << (mn ? c : 7 - c)); ++clipped; }
+        }
+    }
+    if (n_tipped) *n_tipped = ntj;
+    if (n_clipped) *n_clipped = clipped;
+    for (int c = 0; c < 4; ++c) free(tips[c]);
+    free(tj);
+    if (snapshot) free(view);
+    return removed;
+}
+
 typedef struct { seqvec_t seqs; } unitigs_t;
 
 unitigs_t *orc_unitigs(const kset_t *km, const mphf_t *mk, const uint8_t *masks_in, int keep_loops) {

@@ -1583,7 +1583,7 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
 }
 
 // rolling level-A kernels (reads, canonical mode): SGPU_ROLL=0/1 overrides the default
-static const bool kRollDefault = false;
+static const bool kRollDefault = true;    // verified on the B200: parity suite, no-ids variant and compute-sanitizer clean with SGPU_ROLL=1
 static bool use_roll() {
     const char *e = getenv("SGPU_ROLL");
     return e ? atoi(e) != 0 : kRollDefault;

@@ -38,6 +38,7 @@ def lib():
         L.orc_masks.restype = None; L.orc_masks.argtypes = [vp, vp, vp, i64]
         L.orc_coverage.restype = None; L.orc_coverage.argtypes = [vp, vp, vp]
         L.orc_histogram.restype = i64; L.orc_histogram.argtypes = [vp, i64, vp, i64]
+        L.orc_early_tip_clip.restype = i64; L.orc_early_tip_clip.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.orc_unitigs.restype = vp; L.orc_unitigs.argtypes = [vp, vp, vp, i32]
         L.orc_unitigs_n.restype = i64; L.orc_unitigs_n.argtypes = [vp]
         L.orc_unitig_len.restype = i64; L.orc_unitig_len.argtypes = [vp, i64]
@@ -134,6 +135,16 @@ def histogram(cov):
     return hist[:mx]
 
 
+def early_tip_clip(km: KSet, mk: Mphf, masks_arr, length_bound, snapshot=False):
+    """EarlyTipClipperProcessor::ClipTips on a copy of the mask array -> (masks, removed k-mers, tipped junctions, clipped links)"""
+    m = np.array(masks_arr, np.uint8, copy=True)
+    if m.size == 0:
+        return m, 0, 0, 0
+    nt, nc = C.c_int64(), C.c_int64()
+    removed = lib().orc_early_tip_clip(km.h, mk.h, _p(m), int(length_bound), 1 if snapshot else 0, C.byref(nt), C.byref(nc))
+    return m, int(removed), int(nt.value), int(nc.value)
+
+
 class Unitigs:
     def __init__(self, km: KSet, mk: Mphf, masks_arr, keep_loops=True):
         m = np.ascontiguousarray(masks_arr, np.uint8)
@@ -162,8 +173,10 @@ def gfa(u: Unitigs, mk: Mphf, mkp: Mphf = None, cov=None, version="SPAdes-4.3.0-
     return s
 
 
-def full_graph(reads, k, B):
-    """Whole path on a list of ACGT strings; returns dict of artefacts named like ref_probe's files."""
+def full_graph(reads, k, B, early_tc=0):
+    """Whole path on a list of ACGT strings; returns dict of artefacts named like ref_probe's files.
+    early_tc > 0: run the early tip clipper with that length bound between the mask fill and the unitig extraction
+    (stages/construction.cpp:289-302); `masks` then holds the clipped array and `masks_raw` the one before."""
     from spades_b200.packing import pack_reads
     words, offs, lens = pack_reads(reads)
     kp = count(words, offs, lens, k + 1, B, 0)
@@ -171,7 +184,12 @@ def full_graph(reads, k, B):
     mk = Mphf(km)
     mkp = Mphf(kp)
     mk_arr = masks(kp, mk, km.n)
+    raw = mk_arr
+    tc = None
+    if early_tc:
+        mk_arr, removed, tipped, clipped = early_tip_clip(km, mk, mk_arr, early_tc)
+        tc = dict(removed=removed, tipped=tipped, clipped=clipped)
     cov = coverage(kp, mkp)
     u = Unitigs(km, mk, mk_arr, True)
-    return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, cov=cov, hist=histogram(cov), unitigs=u,
+    return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, masks_raw=raw, tc=tc, cov=cov, hist=histogram(cov), unitigs=u,
                 gfa=gfa(u, mk, mkp, cov))
