@@ -315,6 +315,23 @@ int sgpu_graph_build(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *k
         *out = new sgpu_graph{g};
     })
 }
+int sgpu_graph_build_ex(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *kmers, const sgpu_mphf *kmer_index, const sgpu_mphf *kpomer_index,
+                        int keep_perfect_loops, uint64_t early_tip_length_bound, sgpu_graph **out) {
+    if (!ctx || !kpomers || !kmers || !kmer_index || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0,
+                               early_tip_length_bound);
+        *out = new sgpu_graph{g};
+    })
+}
+int sgpu_graph_tip_clipper_stats(const sgpu_graph *g, uint64_t *out3) {
+    if (!g || !out3) return SGPU_EINVAL;
+    for (int i = 0; i < 3; ++i) out3[i] = g->g->tc_stats[i];
+    return SGPU_OK;
+}
 int sgpu_graph_masks(const sgpu_graph *g, uint8_t *out, int64_t n) {
     if (!g || (n && !out)) return SGPU_EINVAL;
     Ctx *c = g->g->ctx;

@@ -250,6 +250,92 @@ __global__ void masks_clear_visited_k(uint8_t *__restrict__ masks, const uint8_t
     if (b && (threadIdx.x & 31) == 0) atomicAdd(remaining, (unsigned long long)__popc(b));
 }
 
+// ---- early tip clipper -------------------------------------------------------------------------------------------------
+// EarlyTipClipperProcessor (assembly_graph/construction/early_simplification.hpp:38-162), run by the pipeline between the
+// mask fill and the unitig extraction (stages/construction.cpp:289-302, length bound = read length - k). The reference walks
+// the junctions one after the other (or racily from several threads) on the live index; the result does not depend on the
+// order (a tip's vertices are reachable from exactly one junction orientation and removals only zero tip vertices -- checked
+// against the unmodified reference with 1 and 8 threads and against the oracle's sequential and snapshot modes, tests/), so
+// here every (k-mer, orientation) with >= 2 outgoing edges is one thread on a snapshot of the masks:
+//   tc_probe_k  FindForward per outgoing edge (:115-125), RemoveTips decision (:133-155), marks the vertices to isolate
+//   tc_apply_k  IsolateVertex for the marked vertices
+//   tc_links_k  RemoveInconsistentForwardLinks over the tipped junctions (:21-36) on the updated masks
+template <int NW, bool MARK>
+__device__ __forceinline__ uint32_t tc_find_forward(const MphfDev &mk, const uint8_t *masks, int K, Kmer<NW> kh, uint32_t bound, uint8_t *mark) {
+    uint32_t n = 0;
+    for (;;) {
+        uint64_t idx;
+        const uint8_t m = oriented_mask<NW>(mk, masks, kh, K, &idx);
+        const int uo = uniq4(m & 15), ui = uniq4(m >> 4);
+        if (MARK) mark[idx] = 1;
+        if (!(n < bound && ui >= 0 && uo >= 0)) {
+            ++n;                                                 // tip.push_back(kh) after the loop (:121)
+            return (ui < 0 || (m & 15) != 0) ? 0u : n;           // branching / not a dead end -> not a tip (:122-125)
+        }
+        ++n;
+        kmer_shl<NW>(kh, K, uo);
+    }
+}
+template <int NW>
+__global__ void tc_probe_k(KeyTable t, int64_t n, int K, MphfDev mk, const uint8_t *__restrict__ masks, uint32_t bound, uint8_t *__restrict__ mark,
+                           uint32_t *__restrict__ tipped /*[2n]*/, unsigned long long *__restrict__ stats) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * n) return;
+    const Kmer<NW> key = table_key<NW>(t, tid >> 1);
+    const int o = (int)(tid & 1);
+    const uint8_t mfw = masks[mphf_lookup_dev<NW>(mk, key)];
+    const uint8_t m = o ? inv_byte(mfw) : mfw;
+    tipped[tid] = 0;
+    if (__popc(m & 15) < 2) return;                              // OutgoingEdgeCount(kh) >= 2 (:72)
+    const Kmer<NW> kh = o ? kmer_rc<NW>(key, K) : key;
+    uint32_t sz[4] = {0, 0, 0, 0}, mx = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!(m & (1u << c))) continue;
+        Kmer<NW> khc = kh;
+        kmer_shl<NW>(khc, K, c);
+        sz[c] = tc_find_forward<NW, false>(mk, masks, K, khc, bound, nullptr);
+        const uint32_t len = sz[c] ? sz[c] : 0xffffffffu;
+        if (len > mx) mx = len;
+    }
+    uint32_t removed = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!sz[c] || sz[c] >= mx) continue;                     // RemoveTips: tip.size() < max (:136-141)
+        Kmer<NW> khc = kh;
+        kmer_shl<NW>(khc, K, c);
+        tc_find_forward<NW, true>(mk, masks, K, khc, bound, mark);
+        removed += sz[c];
+    }
+    if (removed) { tipped[tid] = 1; atomicAdd(&stats[0], (unsigned long long)removed); atomicAdd(&stats[1], 1ull); }
+}
+__global__ void tc_apply_k(uint8_t *__restrict__ masks, const uint8_t *__restrict__ mark, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && mark[i]) masks[i] = 0;
+}
+template <int NW>
+__global__ void tc_links_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__restrict__ masks, const uint32_t *__restrict__ tipped,
+                           unsigned long long *__restrict__ stats) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * n || !tipped[tid]) return;
+    const Kmer<NW> key = table_key<NW>(t, tid >> 1);
+    const Kmer<NW> kh = (tid & 1) ? kmer_rc<NW>(key, K) : key;
+    const CanonIdx<NW> ci = canon_lookup<NW>(mk, kh, K);
+    const uint8_t raw = masks[ci.idx];
+    const uint8_t m = ci.is_min ? raw : inv_byte(raw);
+    const int first = (int)(kh.w[0] & 3);                        // kh[0]
+    for (int c = 0; c < 4; ++c) {
+        if (!(m & (1u << c))) continue;
+        Kmer<NW> nx = kh;
+        kmer_shl<NW>(nx, K, c);
+        if (!(oriented_mask<NW>(mk, masks, nx, K) & (1u << (4 + first)))) {            // !CheckIncoming(next_kh, kh[0])
+            const unsigned bit = 1u << (ci.is_min ? c : 7 - c);                          // DeleteOutgoing(kh, c), inout_mask.hpp:108-114
+            atomicAnd(reinterpret_cast<unsigned *>(masks) + (ci.idx >> 2), ~(bit << (8 * (ci.idx & 3))));
+            atomicAdd(&stats[2], 1ull);
+        }
+    }
+}
+
 // ---- perfect loops (CollectLoops :359-397). Rare; one thread per candidate / per loop is enough. ---------------------
 template <int NW>
 __global__ void loop_pos_k(KeyTable t, int64_t n, MphfDev mk, uint64_t *__restrict__ pos_of_idx) {
@@ -415,7 +501,7 @@ __global__ void loop_write_k(const LoopInfo *__restrict__ info, int64_t nl, int 
 
 // ---- host orchestration ----------------------------------------------------------------------------------------------
 template <int NW, int NWS>
-static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops) {
+static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops, uint64_t early_tc_bound) {
     cudaStream_t st = ctx->stream;
     const KSet *kp = g->kp, *km = g->km;
     const int K = km->K;
@@ -444,6 +530,25 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops) {
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaStreamSynchronize(st));
+    g->tc_stats[0] = g->tc_stats[1] = g->tc_stats[2] = 0;
+    if (early_tc_bound && nk) {
+        KeyTable tt = make_table(km);
+        DArr<uint8_t> mark(ctx, nk + 8);
+        DArr<uint32_t> tipped(ctx, 2 * nk + 1);
+        DArr<unsigned long long> stats(ctx, 4);
+        SG_CUDA(cudaMemsetAsync(mark.p, 0, mark.bytes(), st));
+        SG_CUDA(cudaMemsetAsync(stats.p, 0, 32, st));
+        const uint32_t bound = (uint32_t)std::min<uint64_t>(early_tc_bound, 0x7fffffffu);
+        tc_probe_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, bound, mark.p, tipped.p, stats.p);
+        tc_apply_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(g->masks.p, mark.p, nk);
+        tc_links_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, tipped.p, stats.p);
+        ctx->launches += 3;
+        SG_CUDA(cudaGetLastError());
+        unsigned long long hs[4];
+        SG_CUDA(cudaMemcpyAsync(hs, stats.p, 32, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        g->tc_stats[0] = hs[0]; g->tc_stats[1] = hs[1]; g->tc_stats[2] = hs[2];
+    }
     g->masks_final.alloc(ctx, nk + 8, true);     // what the reference's ext index holds before unitig extraction mutates it
     SG_CUDA(cudaMemcpyAsync(g->masks_final.p, g->masks.p, nk, cudaMemcpyDeviceToDevice, st));
     if (nk == 0) { SG_CUDA(cudaStreamSynchronize(st)); return; }
@@ -589,7 +694,7 @@ void launch_nonzero_flags(Ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t 
     ctx->launches++;
 }
 
-Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops) {
+Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops, uint64_t early_tc_bound) {
     SG_CHECK(kp->K == km->K + 1, 2, "graph: (k+1)-mer / k-mer sets do not match");
     SG_CHECK(mk->n == km->n && mk->B == km->B, 2, "graph: k-mer index does not belong to the k-mer set");
     SG_CHECK(km->K % 2 == 1, 2, "graph: k must be odd (gbuilder.cpp:125)");
@@ -597,13 +702,13 @@ Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, con
     g->ctx = ctx; g->k = km->K; g->kp = kp; g->km = km; g->mk = mk; g->mkp = mkp;
     try {
         const int nw = km->nw, nws = kp->nw;
-        if (nw == 1 && nws == 1) graph_build_nw<1, 1>(ctx, g, keep_loops);
-        else if (nw == 1 && nws == 2) graph_build_nw<1, 2>(ctx, g, keep_loops);
-        else if (nw == 2 && nws == 2) graph_build_nw<2, 2>(ctx, g, keep_loops);
-        else if (nw == 2 && nws == 3) graph_build_nw<2, 3>(ctx, g, keep_loops);
-        else if (nw == 3 && nws == 3) graph_build_nw<3, 3>(ctx, g, keep_loops);
-        else if (nw == 3 && nws == 4) graph_build_nw<3, 4>(ctx, g, keep_loops);
-        else if (nw == 4 && nws == 4) graph_build_nw<4, 4>(ctx, g, keep_loops);
+        if (nw == 1 && nws == 1) graph_build_nw<1, 1>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 1 && nws == 2) graph_build_nw<1, 2>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 2 && nws == 2) graph_build_nw<2, 2>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 2 && nws == 3) graph_build_nw<2, 3>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 3 && nws == 3) graph_build_nw<3, 3>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 3 && nws == 4) graph_build_nw<3, 4>(ctx, g, keep_loops, early_tc_bound);
+        else if (nw == 4 && nws == 4) graph_build_nw<4, 4>(ctx, g, keep_loops, early_tc_bound);
         else throw Error(2, "graph: unsupported word combination");
     } catch (...) { delete g; throw; }
     return g;

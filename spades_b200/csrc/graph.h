@@ -21,9 +21,10 @@ struct Graph {
     std::vector<uint32_t> edge_len;
     std::vector<uint64_t> link_start, link_end;   // LinkRecord::hash_and_mask_ (debruijn_graph_constructor.hpp:422-452)
     std::vector<uint32_t> raw_cov;                // CoverageIndex raw coverage per edge
+    uint64_t tc_stats[3] = {0, 0, 0};             // early tip clipper: removed k-mers, tipped junctions, clipped links
 };
 
-Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops);
+Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops, uint64_t early_tc_bound = 0);
 std::vector<uint64_t> graph_histogram(Ctx *ctx, const Graph *g);
 
 // host_graph.cpp : FastGraphFromSequencesConstructor::ConstructGraph + GFAWriter

@@ -56,12 +56,15 @@ GTEST_CASES = {
 }
 
 
-def run_probe(mode, reads, k, B, T=2):
+def run_probe(mode, reads, k, B, T=2, early_tc=0):
     with tempfile.TemporaryDirectory() as d:
         rf = os.path.join(d, "reads.txt")
         open(rf, "w").write("\n".join(reads) + "\n")
         out = os.path.join(d, "out")
-        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        env = dict(os.environ)
+        if early_tc:
+            env["PROBE_EARLY_TC"] = str(early_tc)      # EarlyTipClipperProcessor between mask fill and unitig extraction
+        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
         res = {}
         for f in os.listdir(out):
             p = os.path.join(out, f)
@@ -70,8 +73,12 @@ def run_probe(mode, reads, k, B, T=2):
         return res
 
 
-def save(name, mode, reads, k, B):
-    res = run_probe(mode, reads, k, B)
+def save(name, mode, reads, k, B, early_tc=0):
+    """mode "tcgraph" = graph mode with the pipeline's early tip clipper (length bound early_tc); masks_bin is the array
+    before the clipper, masks_tc_bin after it, everything downstream (unitigs, GFA) comes from the clipped index."""
+    res = run_probe("graph" if mode == "tcgraph" else mode, reads, k, B, early_tc=early_tc)
+    if early_tc:
+        res["tc_bound"] = np.array([early_tc])
     res["reads"] = np.frombuffer("\n".join(reads).encode(), dtype=np.uint8)
     res["k"] = np.array([k]); res["B"] = np.array([B]); res["mode"] = np.frombuffer(mode.encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
@@ -90,5 +97,11 @@ if __name__ == "__main__":
     save("loops_k21_B10_graph", "graph", loops_reads(), 21, 10)
     save("dense_k5_B4_graph", "graph", synthetic_reads(200, 60, 200, 0.02, seed=3), 5, 4)
     save("dense_k3_B1_graph", "graph", synthetic_reads(100, 40, 100, 0.02, seed=4), 3, 1)
+    # Construction stage with early_tc (stages/construction.cpp:289-302): length bound = read length - k
+    save("ecoli_k21_B40_tcgraph", "tcgraph", ec, 21, 40, early_tc=100 - 21)
+    save("ecoli_k55_B16_tcgraph", "tcgraph", ec[:1500], 55, 16, early_tc=100 - 55)
+    save("syn_k21_B10_tcgraph", "tcgraph", synthetic_reads(2000, 100, 3000, 0.02, seed=6), 21, 10, early_tc=79)
+    save("loops_k21_B10_tcgraph", "tcgraph", loops_reads() + synthetic_reads(300, 120, 700, 0.02, seed=3), 21, 10, early_tc=99)
+    save("dense_k7_B4_tcgraph", "tcgraph", synthetic_reads(800, 60, 400, 0.03, seed=14), 7, 4, early_tc=10)
     for nm, (rd, _) in GTEST_CASES.items():
         save("gtest_" + nm + "_k5", "graph", rd, 5, 2)

@@ -22,6 +22,8 @@ def load(name):
     g = {k: z[k] for k in z.files}
     g["reads"] = g["reads"].tobytes().decode().split("\n")
     g["k"] = int(g["k"][0]); g["B"] = int(g["B"][0]); g["mode"] = g["mode"].tobytes().decode()
+    if "tc_bound" in g:
+        g["tc_bound"] = int(g["tc_bound"][0])
     return g
 
 
@@ -82,8 +84,12 @@ def check_graph(g, art):
         chk("kmer_index", index_equal(strip_uleb_k(g["kmer_index_bin"].tobytes(), k), art["kmer_index"], B))
     if "kpomer_index" in art:
         chk("kpomer_index", index_equal(strip_uleb_k(g["kpomer_index_bin"].tobytes(), k + 1), art["kpomer_index"], B))
-    if "masks" in art:
-        chk("masks", np.array_equal(g["masks_bin"], np.asarray(art["masks"], np.uint8)))
+    if "masks" in art:     # tip-clipper fixtures: `masks` is the array after the clipper (masks_tc.bin)
+        chk("masks", np.array_equal(g["masks_tc_bin"] if "masks_tc_bin" in g else g["masks_bin"], np.asarray(art["masks"], np.uint8)))
+    if "masks_raw" in art and "masks_tc_bin" in g:
+        chk("masks_raw", np.array_equal(g["masks_bin"], np.asarray(art["masks_raw"], np.uint8)))
+    if "tc_removed" in art:
+        chk("tc_removed", int(g["tc_removed_txt"].tobytes().decode().split()[0]) == int(art["tc_removed"]))
     if "cov" in art:
         chk("cov", np.array_equal(np.frombuffer(g["coverage_bin"].tobytes(), np.uint32), np.asarray(art["cov"], np.uint32)))
     if "hist" in art:

@@ -47,6 +47,28 @@ def test_graph_matches_reference_golden(name):
     assert G.check_graph(g, art) == []
 
 
+@pytest.mark.parametrize("name", G.names("tcgraph"))
+def test_early_tip_clipper_matches_reference_golden(name):
+    """sgpu_graph_build_ex with the pipeline's early tip clipper against the unmodified reference's EarlyTipClipperProcessor:
+    clipped mask array, removed-k-mer count, and the unitigs / GFA built from the clipped index"""
+    from gpu_util import gpu_graph_artifacts
+    g = G.load(name)
+    art, gr = gpu_graph_artifacts(g["reads"], g["k"], g["B"], early_tc=g["tc_bound"])
+    assert G.check_graph(g, art) == []
+
+
+@pytest.mark.parametrize("k,B,n,L,glen,err,seed", [(21, 16, 3000, 100, 4000, 0.02, 51), (55, 20, 3000, 150, 4000, 0.02, 52), (77, 3, 1500, 150, 2000, 0.01, 53),
+                                                   (9, 3, 1000, 60, 600, 0.1, 54), (33, 2, 2000, 120, 900, 0.03, 55)])
+def test_early_tip_clipper_matches_oracle_random(k, B, n, L, glen, err, seed):
+    from gpu_util import gpu_graph_artifacts
+    reads = synthetic_reads(n, L, glen, err, seed=seed)
+    art, gr = gpu_graph_artifacts(reads, k, B, early_tc=L - k)
+    r = O.full_graph(reads, k, B, early_tc=L - k)
+    assert r["tc"]["removed"] > 0
+    assert gr.tip_clipper_stats() == (r["tc"]["removed"], r["tc"]["tipped"], r["tc"]["clipped"])
+    assert np.array_equal(art["masks"], r["masks"]) and art["unitigs"] == r["unitigs"].seqs and art["gfa"] == r["gfa"]
+
+
 @pytest.mark.parametrize("name", G.names("count"))
 def test_kmercount_matches_reference_golden(name):
     from gpu_util import gpu_count_artifacts

@@ -12,11 +12,27 @@ import oracle as O
 from spades_b200.packing import pack_reads, revcomp, unpack_kmers
 
 
-def oracle_artifacts(reads, k, B):
-    r = O.full_graph(reads, k, B)
-    return dict(kpomers=r["kp"].keys, kp_bsz=r["kp"].bsz, kmers=r["km"].keys, kmer_index=r["mk"].serialize(),
-                kpomer_index=r["mkp"].serialize(), masks=r["masks"], cov=r["cov"], hist=r["hist"],
-                unitigs=r["unitigs"].seqs, gfa=r["gfa"]), r
+def oracle_artifacts(reads, k, B, early_tc=0):
+    r = O.full_graph(reads, k, B, early_tc=early_tc)
+    art = dict(kpomers=r["kp"].keys, kp_bsz=r["kp"].bsz, kmers=r["km"].keys, kmer_index=r["mk"].serialize(),
+               kpomer_index=r["mkp"].serialize(), masks=r["masks"], cov=r["cov"], hist=r["hist"],
+               unitigs=r["unitigs"].seqs, gfa=r["gfa"])
+    if early_tc:
+        art.update(masks_raw=r["masks_raw"], tc_removed=r["tc"]["removed"])
+    return art, r
+
+
+@pytest.mark.parametrize("name", G.names("tcgraph"))
+def test_oracle_early_tip_clipper_matches_reference_golden(name):
+    """EarlyTipClipperProcessor (early_simplification.hpp:38-162) between mask fill and unitig extraction: clipped masks,
+    removed-k-mer count, unitigs and GFA against the unmodified reference; and the order independence the CUDA version
+    relies on (every walk on a snapshot of the masks gives the same array as the reference's sequential walk)."""
+    g = G.load(name)
+    art, r = oracle_artifacts(g["reads"], g["k"], g["B"], early_tc=g["tc_bound"])
+    assert G.check_graph(g, art) == []
+    assert r["tc"]["removed"] > 0
+    snap = O.early_tip_clip(r["km"], r["mk"], r["masks_raw"], g["tc_bound"], snapshot=True)
+    assert np.array_equal(snap[0], r["masks"]) and snap[1:] == (r["tc"]["removed"], r["tc"]["tipped"], r["tc"]["clipped"])
 
 
 @pytest.mark.parametrize("name", G.names("graph"))

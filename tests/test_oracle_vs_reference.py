@@ -16,12 +16,15 @@ PROBE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/ref_probe not built (make -C oracle ref)")
 
 
-def run_probe(mode, reads, k, B, T=3):
+def run_probe(mode, reads, k, B, T=3, early_tc=0):
     with tempfile.TemporaryDirectory() as d:
         rf = os.path.join(d, "reads.txt")
         open(rf, "w").write("\n".join(reads) + "\n")
         out = os.path.join(d, "out")
-        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        env = dict(os.environ)
+        if early_tc:
+            env["PROBE_EARLY_TC"] = str(early_tc)
+        subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, timeout=600)
         g = {f.replace(".", "_"): np.frombuffer(open(os.path.join(out, f), "rb").read(), np.uint8)
              for f in os.listdir(out) if os.path.isfile(os.path.join(out, f))}
     g.update(k=k, B=B, reads=reads)
@@ -44,3 +47,15 @@ def test_oracle_vs_live_reference_kmercount(k, B, seed):
     words, offs, lens = pack_reads(reads)
     ks = O.count(words, offs, lens, k, B, 1)
     assert G.check_count(g, dict(final_kmers=ks.keys, bsz=ks.bsz)) == []
+
+
+@pytest.mark.parametrize("k,B,n,L,glen,err,seed,T", [(21, 16, 3000, 100, 4000, 0.01, 41, 1), (21, 8, 3000, 100, 2000, 0.03, 42, 8),
+                                                     (55, 30, 3000, 150, 5000, 0.01, 43, 3), (77, 4, 1500, 150, 2000, 0.01, 44, 8),
+                                                     (9, 3, 1000, 60, 600, 0.1, 45, 8)])
+def test_oracle_vs_live_reference_early_tip_clipper(k, B, n, L, glen, err, seed, T):
+    """the reference's clipper runs racily on T threads; its result (and the oracle's) must not depend on T"""
+    reads = synthetic_reads(n, L, glen, err, seed=seed)
+    g = run_probe("graph", reads, k, B, T=T, early_tc=L - k)
+    art, r = oracle_artifacts(reads, k, B, early_tc=L - k)
+    assert G.check_graph(g, art) == []
+    assert r["tc"]["removed"] > 0
