@@ -1,0 +1,93 @@
+// integration/gpu_kmer_counter.hpp -- the reference-side adapters of INTEGRATION.md as compilable code.
+//
+// Header-only C++ that a SPAdes maintainer drops into src/common/kmer_index/kmer_mph/: it implements the reference's OWN
+// interfaces on top of the C ABI of libspades_b200.so (include/spades_b200.h), so everything downstream in SPAdes
+// (KMerDiskStorage::merge, KMerIndexBuilder, DeBruijnExtensionIndexBuilder::BuildExtensionIndexFromKPOMers,
+// CoverageHashMapBuilder, the hammer / ionhammer / mts clients) consumes the result unchanged.
+//
+//   kmers::GpuKMerDiskCounter      kmers::KMerCounter<RtSeq>  (kmer_index/kmer_mph/kmer_index_builder.hpp:259-282)
+//                                  replacing KMerDiskCounter<RtSeq> + its splitter (:284-431, kmer_splitters.hpp:28-136,
+//                                  projects/spades_tools/kmercount.cpp:48-122)
+//   kmers::BuildIndexOnGpu         KMerIndexBuilder<Index>::BuildIndex(index, storage) (:448-498) through
+//                                  KMerIndex::deserialize (kmer_index.hpp:110-124)
+//
+// It is compiled against the UNMODIFIED reference headers by integration/Makefile (build container only, like oracle/_ref).
+#pragma once
+#include <sstream>
+#include <string>
+
+#include "kmer_index/kmer_mph/kmer_index.hpp"
+#include "kmer_index/kmer_mph/kmer_index_builder.hpp"
+#include "sequence/sequence.hpp"
+#include "spades_b200.h"
+
+namespace kmers {
+
+class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
+  public:
+    // mode: SGPU_ALL_WINDOWS = spades-kmercount's splitter (every window of reads + RC, kmercount.cpp:48-122),
+    //       SGPU_CANONICAL   = DeBruijnReadKMerSplitter with the IsMinimal filter (kmer_splitters.hpp:112-136, storing_traits.hpp:92-101)
+    GpuKMerDiskCounter(fs::TmpDir work_dir, unsigned K, sgpu_ctx *ctx, int mode)
+            : KMerCounter<RtSeq>(K), work_dir_(work_dir), ctx_(ctx), mode_(mode) { check(sgpu_reads_clear(ctx_)); }
+    ~GpuKMerDiskCounter() override { if (last_) sgpu_kset_free(last_); }
+
+    // the payload of the reference's binary read records: Sequence::data(), ceil(size/32) words (sequence.hpp:808-830)
+    void AddRead(const Sequence &s) {
+        if (s.size() == 0) return;
+        words_.resize(0);
+        const size_t nw = (s.size() + 31) / 32;
+        words_.resize(nw, 0);
+        for (size_t i = 0; i < s.size(); ++i) words_[i >> 5] |= (uint64_t)s[i] << ((i & 31) << 1);      // rtseq.hpp:379-382 packing
+        const uint64_t off = 0;
+        const uint32_t len = (uint32_t)s.size();
+        check(sgpu_reads_append_packed(ctx_, words_.data(), nw, &off, &len, 1));
+    }
+
+    size_t kmer_size() const override { return RtSeq::GetDataSize(this->k()) * sizeof(RtSeq::DataType); }
+
+    KMerDiskStorage<RtSeq> Count(unsigned num_buckets, unsigned /* num_threads */) override {
+        if (last_) { sgpu_kset_free(last_); last_ = nullptr; }
+        check(sgpu_count(ctx_, (int)this->k(), (int)num_buckets, mode_, &last_));
+        INFO("K-mer counting done on the GPU. There are " << sgpu_kset_size(last_) << " kmers in total. ");
+        KMerDiskStorage<RtSeq> res(work_dir_, this->k(), kmer::KMerSegmentPolicy<RtSeq>(num_buckets));
+        // the storage creates (and keeps owning) the bucket files <prefix>.<i>; the library fills them
+        std::string prefix;
+        for (unsigned i = 0; i < num_buckets; ++i) {
+            auto f = res.create(i);
+            if (i == 0) { prefix = f->file().native(); prefix.resize(prefix.rfind('.')); }
+        }
+        check(sgpu_kset_write_buckets(last_, prefix.c_str()));
+        return res;
+    }
+
+    KMerDiskStorage<RtSeq> CountAll(unsigned num_buckets, unsigned num_threads, bool merge = true) override {
+        auto storage = Count(num_buckets, num_threads);
+        if (merge) storage.merge();
+        return storage;
+    }
+
+    const sgpu_kset *device_set() const { return last_; }      // the same set, still resident in HBM, for the GPU index / graph phases
+
+  private:
+    void check(int rc) const { if (rc) FATAL_ERROR("spades_b200: " << sgpu_last_error(ctx_)); }          // logger.hpp:185-261 convention
+    fs::TmpDir work_dir_;
+    sgpu_ctx *ctx_;
+    int mode_;
+    sgpu_kset *last_ = nullptr;
+    std::vector<uint64_t> words_;
+};
+
+// index: kmers::KMerIndex<traits>. KMerIndex befriends only KMerIndexBuilder (kmer_index.hpp:149-150) but deserialize is public
+// and sgpu_mphf_serialize emits exactly the bytes KMerIndex::serialize writes.
+template<class Index>
+void BuildIndexOnGpu(Index &index, sgpu_ctx *ctx, const sgpu_kset *ks) {
+    sgpu_mphf *m = nullptr;
+    if (sgpu_mphf_build(ctx, ks, &m)) FATAL_ERROR("spades_b200: " << sgpu_last_error(ctx));
+    std::string bytes((size_t)sgpu_mphf_serialized_size(m), '\0');
+    if (sgpu_mphf_serialize(m, (uint8_t *)&bytes[0], (int64_t)bytes.size())) FATAL_ERROR("spades_b200: " << sgpu_last_error(ctx));
+    sgpu_mphf_free(m);
+    std::istringstream is(bytes);
+    index.deserialize(is);
+}
+
+}  // namespace kmers
