@@ -340,7 +340,7 @@ def main():
         }
         dom = max(alg, key=lambda k2: per_step[k2])
         achieved = alg[dom] / (per_step[dom] / 1e3) / 1e9 if per_step[dom] > 0 else 0.0
-        kernel_names = {"extract_scatter_ms": "levelA_scatter_k (radix partition)", "extract_count_ms": "levelA_count_k", "refine_ms": "refine_k (MSD split)",
+        kernel_names = {"extract_scatter_ms": "levelA_scatter_roll_k (radix partition)", "extract_count_ms": "levelA_count_roll_k", "refine_ms": "refine_k (gather + MSD split)",
                         "local_sort_ms": "local_sort3_k", "compact_ms": "compact_k", "exchange_ms": "dist_pull_k (NVLink exchange+merge)"}
         line = {
             "metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": value, "unit": "Mk-mers/s", "n_gpus": world, "steps": args.steps,
@@ -359,8 +359,10 @@ def main():
                          "peak_source": peak_src,
                          # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_ncu_full_top_kernels_20M.csv,
                          # 20 M-read workload, one launch): only quoted when the bench runs that workload
-                         "traffic": (73.4e9 if (n_reads == 20_000_000 and world == 1 and dom == "extract_scatter_ms") else None),
-                         "traffic_note": "ncu (20 M reads): levelA_scatter_k moves 25.1 GB read + 48.2 GB written for 31.2 GB algorithmic (2.35x): 16-byte stores force sector fills",
+                         # no ncu --set full capture of the current dominant kernel exists yet (the capture of the rolling partition kernel failed,
+                         # profiles/README): null rather than a number from an older kernel
+                         "traffic": None,
+                         "traffic_note": "ncu --set full exists for levelA_count_roll_k (profiles/r01b_*) and for the previous generation of the partition / refinement / sort kernels (profiles/r01_*)",
                          "launches_per_step": int(max(1, passes)) if dom == "extract_scatter_ms" else None,
                          "algorithmic_bytes_per_step": int(alg[dom]),
                          "all": {kernel_names[k2]: (alg[k2] / (per_step[k2] / 1e3) / 1e9 if per_step[k2] > 0 else None) for k2 in alg}},

@@ -16,9 +16,11 @@
 #include <sstream>
 #include <string>
 
+#include "sequence/rtseq.hpp"
+#include "sequence/sequence.hpp"
+#include "kmer_index/kmer_mph/kmer_index_traits.hpp"
 #include "kmer_index/kmer_mph/kmer_index.hpp"
 #include "kmer_index/kmer_mph/kmer_index_builder.hpp"
-#include "sequence/sequence.hpp"
 #include "spades_b200.h"
 
 namespace kmers {
