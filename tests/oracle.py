@@ -178,6 +178,8 @@ def full_graph(reads, k, B, early_tc=0):
     early_tc > 0: run the early tip clipper with that length bound between the mask fill and the unitig extraction
     (stages/construction.cpp:289-302); `masks` then holds the clipped array and `masks_raw` the one before."""
     from spades_b200.packing import pack_reads
+    if k % 2 == 0:
+        raise ValueError("k must be odd (projects/spades_tools/gbuilder.cpp:125): with even k a k-mer can be its own reverse complement")
     words, offs, lens = pack_reads(reads)
     kp = count(words, offs, lens, k + 1, B, 0)
     km = kmers_from_kpomers(kp, B)
