@@ -88,6 +88,28 @@ int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, con
 /* use a read set that already lives in device memory (not copied, must stay valid while the context uses it) */
 int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads);
 
+/* ---- read ingest (pure host code: no GPU, no context needed). Replaces the front end of the tools: io::FastaFastqGzParser
+ * over kseq + zlib (io/reads/fasta_fastq_gz_parser.hpp:25-150), io::LongestValid (io/reads/longest_valid_wrapper.hpp:16-53, applied
+ * by io_helper.cpp:30-31 and read_converter.cpp:115,121) and the binary read streams <prefix>.seq / <prefix>.off that
+ * io::BinaryWriter::ToBinary writes and io::BinaryFileStream<SingleReadSeq> reads (io/reads/binary_converter.cpp:84-145,
+ * binary_streams.hpp:54-102; record = Sequence::BinWrite + SingleReadSeq::BinWrite, sequence.hpp:817-830, single_read.hpp:325-338).
+ * A batch holds 2-bit packed reads in the layout sgpu_reads_append_packed / sgpu_reads_upload take. Reads without any valid
+ * base are dropped (they contribute no k-mer). On failure *out is still a batch whose sgpu_read_batch_error() says why. */
+typedef struct sgpu_read_batch sgpu_read_batch;
+int sgpu_fastx_parse(const char *path, int longest_valid, sgpu_read_batch **out);      /* FASTA / FASTQ, plain or gzip */
+int sgpu_seqfile_parse(const char *prefix, sgpu_read_batch **out);                     /* <prefix>.seq of the reference */
+int sgpu_read_batch_write_seqfile(const sgpu_read_batch *b, const char *prefix);       /* <prefix>.seq + <prefix>.off */
+int64_t sgpu_read_batch_num_reads(const sgpu_read_batch *b);
+uint64_t sgpu_read_batch_num_words(const sgpu_read_batch *b);
+const uint64_t *sgpu_read_batch_words(const sgpu_read_batch *b);
+const uint64_t *sgpu_read_batch_offs(const sgpu_read_batch *b);
+const uint32_t *sgpu_read_batch_lens(const sgpu_read_batch *b);
+int sgpu_read_batch_stats(const sgpu_read_batch *b, uint64_t *out3);   /* records in the file, reads trimmed by LongestValid, reads dropped */
+const char *sgpu_read_batch_error(const sgpu_read_batch *b);
+void sgpu_read_batch_free(sgpu_read_batch *b);
+/* sgpu_reads_append_packed of a whole batch */
+int sgpu_reads_append_batch(sgpu_ctx *ctx, const sgpu_read_batch *b);
+
 int sgpu_count(sgpu_ctx *ctx, int K, int num_buckets, int mode, sgpu_kset **out);
 int sgpu_kmers_from_kpomers(sgpu_ctx *ctx, const sgpu_kset *kpomers, int num_buckets, sgpu_kset **out);
 

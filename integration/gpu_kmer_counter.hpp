@@ -45,6 +45,22 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
         check(sgpu_reads_append_packed(ctx_, words_.data(), nw, &off, &len, 1));
     }
 
+    // a whole FASTA / FASTQ (plain or gzip) file through the library's ingest (kseq semantics + LongestValid, like io::EasyStream,
+    // io_helper.cpp:21-35); returns the number of reads taken
+    size_t AddFile(const std::string &path) {
+        sgpu_read_batch *b = nullptr;
+        if (sgpu_fastx_parse(path.c_str(), /* longest_valid */ 1, &b)) {
+            std::string why = sgpu_read_batch_error(b);
+            sgpu_read_batch_free(b);
+            FATAL_ERROR("spades_b200: " << why);
+        }
+        const size_t n = (size_t)sgpu_read_batch_num_reads(b);
+        const int rc = sgpu_reads_append_batch(ctx_, b);
+        sgpu_read_batch_free(b);
+        check(rc);
+        return n;
+    }
+
     size_t kmer_size() const override { return RtSeq::GetDataSize(this->k()) * sizeof(RtSeq::DataType); }
 
     KMerDiskStorage<RtSeq> Count(unsigned num_buckets, unsigned /* num_threads */) override {

@@ -4,8 +4,8 @@
 //
 //   spades_kmercount_gpu <reads.txt> <k> <workdir> [num_buckets=16]
 //
-// reads.txt: one ACGT read per line (the FASTA/FASTQ front end of the original tool -- io::EasyStream + LongestValid -- is the
-// ingest layer; ref_probe takes the same format). Output: <workdir>/final_kmers, byte-identical to the original
+// reads: FASTA / FASTQ, plain or gzip (parsed by the library's ingest with the original tool's semantics: kseq records +
+// LongestValid), or one ACGT read per line (ref_probe's format). Output: <workdir>/final_kmers, byte-identical to the original
 // tool's. It then proves the GPU-written storage is a drop-in for the rest of SPAdes:
 //   1. the reference's OWN KMerIndexBuilder::BuildIndex runs over the GPU-written bucket files,
 //   2. the GPU-built MPHF goes through the reference's OWN KMerIndex::deserialize,
@@ -49,10 +49,17 @@ int main(int argc, char **argv) {
     {
         kmers::GpuKMerDiskCounter counter(fs::tmp::make_temp_dir(workdir, "kmer_counter"), K, ctx, SGPU_ALL_WINDOWS);
         {
-            std::ifstream is(reads_path);
-            std::string line;
-            while (std::getline(is, line))
-                if (!line.empty()) counter.AddRead(Sequence(line));
+            std::ifstream is(reads_path, std::ios::binary);
+            const int c0 = is.get(), c1 = is.get();
+            is.seekg(0);
+            if (c0 == '>' || c0 == '@' || (c0 == 0x1f && c1 == 0x8b)) {       // FASTA / FASTQ / gzip: what the original tool takes
+                is.close();
+                INFO("Parsed " << counter.AddFile(reads_path) << " reads from " << reads_path);
+            } else {                                                            // one ACGT read per line (ref_probe's format)
+                std::string line;
+                while (std::getline(is, line))
+                    if (!line.empty()) counter.AddRead(Sequence(line));
+            }
         }
         auto storage = counter.Count(B, 1);                         // KMerDiskStorage<RtSeq>, buckets written from HBM
         const size_t total = storage.total_kmers();

@@ -19,6 +19,7 @@
 #include "io/reads/rc_reader_wrapper.hpp"
 #include "io/reads/read_stream_vector.hpp"
 #include "io/reads/single_read.hpp"
+#include "io/reads/binary_streams.hpp"
 #include "kmer_index/ph_map/kmer_maps.hpp"
 #include "kmer_index/kmer_mph/kmer_index_builder.hpp"
 #include "kmer_index/kmer_mph/kmer_splitters.hpp"
@@ -110,6 +111,29 @@ int main(int argc, char **argv) {
     }
     std::filesystem::create_directories(outdir / "tmp");
     auto workdir = fs::tmp::make_temp_dir(outdir / "tmp", "probe");
+
+    if (mode == "binreads") {
+        // format pin for the binary read streams: argv[7] = prefix. (1) <prefix>_ref.seq = ReadStreamStat header +
+        // every read of reads.txt through the reference's own SingleReadSeq::BinWrite (what BinaryWriter::ToBinary emits per read,
+        // binary_converter.cpp:96-110); (2) <prefix>.seq/.off -- written by OUR library -- read back through the reference's own
+        // io::BinaryFileStream in T portions (uses the .off index) and dumped as text.
+        std::string prefix = argc > 7 ? argv[7] : argv[6];
+        {
+            std::ofstream os(prefix + "_ref.seq", std::ios::binary);
+            io::ReadStreamStat stat;
+            for (const auto &s : seqs) { stat.read_count++; stat.max_len = std::max(stat.max_len, s.size()); stat.total_len += s.size(); }
+            stat.write(os);
+            for (const auto &s : seqs) io::SingleReadSeq(s).BinWrite(os);
+        }
+        std::ofstream txt(prefix + "_readback.txt");
+        for (unsigned t = 0; t < T; ++t) {
+            io::BinaryFileSingleStream st(prefix, T, t);
+            st.reset();
+            io::SingleReadSeq r;
+            while (!st.eof()) { st >> r; txt << r.sequence().str() << "\n"; }
+        }
+        return 0;
+    }
 
     if (mode == "count") {
         kmers::KMerDiskCounter<RtSeq> counter(workdir, AllWindowsSplitter(workdir, k, seqs));

@@ -12,6 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libspades_b200.so")
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_get_times",
     "sgpu_reads_clear", "sgpu_reads_append_packed", "sgpu_reads_upload", "sgpu_reads_adopt_device",
+    "sgpu_fastx_parse", "sgpu_seqfile_parse", "sgpu_read_batch_write_seqfile", "sgpu_read_batch_num_reads", "sgpu_read_batch_num_words",
+    "sgpu_read_batch_words", "sgpu_read_batch_offs", "sgpu_read_batch_lens", "sgpu_read_batch_stats", "sgpu_read_batch_error", "sgpu_read_batch_free",
+    "sgpu_reads_append_batch",
     "sgpu_count", "sgpu_kmers_from_kpomers",
     "sgpu_kset_size", "sgpu_kset_k", "sgpu_kset_num_buckets", "sgpu_kset_record_bytes", "sgpu_kset_bucket_sizes",
     "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
@@ -55,6 +58,18 @@ def load():
     L.sgpu_reads_append_packed.restype = i32; L.sgpu_reads_append_packed.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_reads_upload.restype = i32; L.sgpu_reads_upload.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_reads_adopt_device.restype = i32; L.sgpu_reads_adopt_device.argtypes = [vp, vp, u64, vp, vp, i64]
+    L.sgpu_fastx_parse.restype = i32; L.sgpu_fastx_parse.argtypes = [C.c_char_p, i32, pp]
+    L.sgpu_seqfile_parse.restype = i32; L.sgpu_seqfile_parse.argtypes = [C.c_char_p, pp]
+    L.sgpu_read_batch_write_seqfile.restype = i32; L.sgpu_read_batch_write_seqfile.argtypes = [vp, C.c_char_p]
+    L.sgpu_read_batch_num_reads.restype = i64; L.sgpu_read_batch_num_reads.argtypes = [vp]
+    L.sgpu_read_batch_num_words.restype = u64; L.sgpu_read_batch_num_words.argtypes = [vp]
+    L.sgpu_read_batch_words.restype = vp; L.sgpu_read_batch_words.argtypes = [vp]
+    L.sgpu_read_batch_offs.restype = vp; L.sgpu_read_batch_offs.argtypes = [vp]
+    L.sgpu_read_batch_lens.restype = vp; L.sgpu_read_batch_lens.argtypes = [vp]
+    L.sgpu_read_batch_stats.restype = i32; L.sgpu_read_batch_stats.argtypes = [vp, vp]
+    L.sgpu_read_batch_error.restype = C.c_char_p; L.sgpu_read_batch_error.argtypes = [vp]
+    L.sgpu_read_batch_free.restype = None; L.sgpu_read_batch_free.argtypes = [vp]
+    L.sgpu_reads_append_batch.restype = i32; L.sgpu_reads_append_batch.argtypes = [vp, vp]
     L.sgpu_count.restype = i32; L.sgpu_count.argtypes = [vp, i32, i32, i32, pp]
     L.sgpu_kmers_from_kpomers.restype = i32; L.sgpu_kmers_from_kpomers.argtypes = [vp, vp, i32, pp]
     L.sgpu_kset_size.restype = i64; L.sgpu_kset_size.argtypes = [vp]

@@ -100,6 +100,12 @@ int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwor
     })
 }
 
+int sgpu_reads_append_batch(sgpu_ctx *ctx, const sgpu_read_batch *b) {
+    if (!ctx || !b) return SGPU_EINVAL;
+    return sgpu_reads_append_packed(ctx, sgpu_read_batch_words(b), sgpu_read_batch_num_words(b), sgpu_read_batch_offs(b), sgpu_read_batch_lens(b),
+                                    sgpu_read_batch_num_reads(b));
+}
+
 int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads) {
     if (!ctx || nreads < 0 || (nreads && (!words || !offs || !lens))) return SGPU_EINVAL;
     Ctx *c = &ctx->c;

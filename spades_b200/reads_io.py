@@ -1,0 +1,73 @@
+"""Host-side mirror of the reference's read front end over the C ABI (pure host code: works without a GPU).
+
+  read_fastx      io::FastaFastqGzParser (kseq + zlib) + io::LongestValid     src/common/io/reads/fasta_fastq_gz_parser.hpp:25-150,
+                                                                              longest_valid_wrapper.hpp:16-53, io_helper.cpp:21-35
+  read_seqfile    io::BinaryFileSingleStream over <prefix>.seq / .off          io/reads/binary_streams.hpp:54-140
+  write_seqfile   io::BinaryWriter::ToBinary (single reads)                   io/reads/binary_converter.cpp:84-145
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class ReadBatch:
+    """2-bit packed reads (words, offs, lens) in the layout Context.set_reads / sgpu_reads_append_packed take."""
+
+    def __init__(self, h):
+        self.h = h
+        L = _lib.load()
+        n, nw = L.sgpu_read_batch_num_reads(h), L.sgpu_read_batch_num_words(h)
+        self.words = np.ctypeslib.as_array(C.cast(L.sgpu_read_batch_words(h), C.POINTER(C.c_uint64)), shape=(nw,)).copy() if nw else np.zeros(0, np.uint64)
+        self.offs = np.ctypeslib.as_array(C.cast(L.sgpu_read_batch_offs(h), C.POINTER(C.c_uint64)), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        self.lens = np.ctypeslib.as_array(C.cast(L.sgpu_read_batch_lens(h), C.POINTER(C.c_uint32)), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        st = np.zeros(3, np.uint64)
+        L.sgpu_read_batch_stats(h, st.ctypes.data_as(C.c_void_p))
+        self.records, self.trimmed, self.dropped = (int(x) for x in st)
+
+    def __len__(self):
+        return len(self.lens)
+
+    def strings(self):
+        out = []
+        for o, l in zip(self.offs, self.lens):
+            w = self.words[int(o):int(o) + (int(l) + 31) // 32]
+            codes = ((w[:, None] >> (np.arange(32, dtype=np.uint64) * np.uint64(2))) & np.uint64(3)).astype(np.uint8).ravel()[:int(l)]
+            out.append(np.frombuffer(b"ACGT", np.uint8)[codes].tobytes().decode())
+        return out
+
+    def write_seqfile(self, prefix):
+        rc = _lib.load().sgpu_read_batch_write_seqfile(self.h, str(prefix).encode())
+        if rc:
+            raise IOError("cannot write %s.seq/.off (error %d)" % (prefix, rc))
+
+    def free(self):
+        if self.h:
+            _lib.load().sgpu_read_batch_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _parse(fn, *args):
+    L = _lib.load()
+    h = C.c_void_p()
+    rc = fn(*args, C.byref(h))
+    if rc:
+        msg = L.sgpu_read_batch_error(h).decode() if h else "error %d" % rc
+        if h:
+            L.sgpu_read_batch_free(h)
+        raise IOError(msg)
+    return ReadBatch(h)
+
+
+def read_fastx(path, longest_valid=True) -> ReadBatch:
+    return _parse(_lib.load().sgpu_fastx_parse, str(path).encode(), 1 if longest_valid else 0)
+
+
+def read_seqfile(prefix) -> ReadBatch:
+    return _parse(_lib.load().sgpu_seqfile_parse, str(prefix).encode())

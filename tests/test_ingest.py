@@ -1,0 +1,132 @@
+"""CPU: the host-side read ingest (spades_b200/csrc/ingest.cpp) -- FASTA/FASTQ(.gz) parsing with kseq semantics, LongestValid,
+2-bit packing, and the reference's binary read-stream format.
+Checked against (1) a line-level Python model on adversarial inputs, (2) the reference's own test data set parsed with Python's
+gzip (build container only), (3) the UNMODIFIED reference reading our .seq/.off through io::BinaryFileSingleStream and writing the
+same reads through SingleReadSeq::BinWrite (oracle/_ref/ref_probe binreads; build container only)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from spades_b200.packing import longest_valid, pack_reads
+from spades_b200.reads_io import read_fastx, read_seqfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+ECOLI = "/root/reference/src/projects/spades/test_dataset"
+
+
+def _model(records):
+    return [s for s in (longest_valid("".join(r).upper()) for r in records) if s]
+
+
+def _canonical_seqfile(path):
+    raw = open(path, "rb").read()
+    out = bytearray(raw[:24])
+    n = int(np.frombuffer(raw[:8], np.uint64)[0])
+    p = 24
+    for _ in range(n):
+        size = int(np.frombuffer(raw[p:p + 8], np.uint64)[0])
+        nw = (size + 31) // 32
+        w = np.frombuffer(raw[p + 8:p + 8 + 8 * nw], np.uint64).copy()
+        if size % 32:
+            w[-1] &= np.uint64((1 << (2 * (size % 32))) - 1)
+        out += raw[p:p + 8] + w.tobytes() + raw[p + 8 + 8 * nw:p + 8 + 8 * nw + 12]
+        p += 8 + 8 * nw + 12
+    assert p == len(raw)
+    return bytes(out)
+
+
+def test_fastq_fasta_variants(tmp_path):
+    rng = np.random.default_rng(1)
+    def rnd(n, pn=0.0, lower=0.0):
+        s = rng.choice(list("ACGT"), n)
+        s = np.where(rng.random(n) < pn, "N", s)
+        s = np.where(rng.random(n) < lower, np.char.lower(s), s)
+        return "".join(s)
+    seqs = [rnd(150), rnd(150, 0.02), rnd(100, 0.0, 0.5), rnd(33, 0.3), "N" * 50, "", rnd(32), rnd(64), rnd(65), rnd(1), "ACGTNNACGTACNNNACGTACGTA",
+            "NACGTN", rnd(1000, 0.005)]
+    seqs += [rnd(int(rng.integers(1, 300)), 0.01) for _ in range(300)]
+    want = _model([[s] for s in seqs])
+    # FASTQ, qualities that start with '@' / '+' / '>' (the classic ambiguity kseq resolves by length)
+    fq = tmp_path / "a.fq"
+    with open(fq, "w") as f:
+        for i, s in enumerate(seqs):
+            q = ("@+>" * (len(s) // 3 + 1))[:len(s)]
+            f.write("@r%d some comment\n%s\n+\n%s\n" % (i, s, q))
+    b = read_fastx(fq)
+    assert b.strings() == want and b.records == len(seqs)
+    assert b.dropped == sum(1 for s in seqs if not longest_valid(s.upper()))
+    # the packed layout is the one pack_reads produces
+    w, o, l = pack_reads(want)
+    assert np.array_equal(b.words, w) and np.array_equal(b.offs, o) and np.array_equal(b.lens, l)
+    # gzip, CRLF, multi-line FASTA with blank lines
+    gz = tmp_path / "a.fq.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(open(fq).read().replace("\n", "\r\n"))
+    assert read_fastx(gz).strings() == want
+    fa = tmp_path / "a.fa"
+    with open(fa, "w") as f:
+        f.write("; leading junk that is not a record\n")
+        for i, s in enumerate(seqs):
+            f.write(">s%d\n" % i)
+            for j in range(0, len(s), 60):
+                f.write(s[j:j + 60] + "\n")
+            if i % 7 == 0:
+                f.write("\n")
+    assert read_fastx(fa).strings() == want
+    # without N handling an invalid read contributes nothing
+    nolv = read_fastx(fq, longest_valid=False).strings()
+    assert nolv == [s.upper() for s in seqs if s and set(s.upper()) <= set("ACGT")]
+    with pytest.raises(IOError):
+        read_fastx(tmp_path / "missing.fq")
+
+
+def test_truncated_fastq_is_an_error(tmp_path):
+    p = tmp_path / "t.fq"
+    open(p, "w").write("@r\nACGTACGT\n+\nIIII")
+    with pytest.raises(IOError):
+        read_fastx(p)
+
+
+@pytest.mark.skipif(not os.path.isdir(ECOLI), reason="reference test data set not present")
+def test_ecoli_test_dataset_matches_python_gzip():
+    for f in ("ecoli_1K_1.fq.gz", "ecoli_1K_2.fq.gz"):
+        lines = gzip.open(os.path.join(ECOLI, f), "rt").read().split("\n")
+        want = _model([[lines[i].strip()] for i in range(1, len(lines), 4)])
+        assert read_fastx(os.path.join(ECOLI, f)).strings() == want
+
+
+def test_seqfile_round_trip(tmp_path):
+    rng = np.random.default_rng(2)
+    reads = ["".join(rng.choice(list("ACGT"), int(n))) for n in rng.integers(1, 400, 731)]
+    fa = tmp_path / "r.fa"
+    open(fa, "w").write("".join(">%d\n%s\n" % (i, s) for i, s in enumerate(reads)))
+    b = read_fastx(fa)
+    b.write_seqfile(tmp_path / "lib")
+    assert os.path.getsize(tmp_path / "lib.off") == 8 * ((len(reads) + 99) // 100)          # one offset per 100 reads
+    back = read_seqfile(tmp_path / "lib")
+    assert back.strings() == reads
+    assert np.array_equal(back.words, b.words) and np.array_equal(back.lens, b.lens)
+
+
+@pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/ref_probe not built")
+def test_seqfile_format_against_the_unmodified_reference(tmp_path):
+    rng = np.random.default_rng(3)
+    reads = ["".join(rng.choice(list("ACGT"), int(n))) for n in rng.integers(1, 300, 457)]
+    txt = tmp_path / "reads.txt"
+    open(txt, "w").write("\n".join(reads) + "\n")
+    fa = tmp_path / "r.fa"
+    open(fa, "w").write("".join(">%d\n%s\n" % (i, s) for i, s in enumerate(reads)))
+    prefix = str(tmp_path / "lib")
+    read_fastx(fa).write_seqfile(prefix)
+    subprocess.check_call([PROBE, "binreads", str(txt), "21", "1", "3", str(tmp_path / "out"), prefix], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # the reference reads our files (3 portions through the .off index) ...
+    assert open(prefix + "_readback.txt").read().split() == reads
+    # ... and writes the same bytes itself, up to the padding bits above the last base of a read: a reference Sequence of <= 60
+    # bases lives inline in 16 bytes whose top byte is its metadata (sequence.hpp:194-262), and Sequence::BinWrite dumps that
+    # byte along with the data; BinRead restores the metadata afterwards (:808-815), so the padding is "don't care" on input
+    assert _canonical_seqfile(prefix + "_ref.seq") == _canonical_seqfile(prefix + ".seq")
+    assert read_seqfile(prefix + "_ref").strings() == reads            # and we read the reference's bytes

@@ -51,3 +51,23 @@ def test_reference_host_code_over_the_c_abi(name):
         fk = np.fromfile(os.path.join(w, "final_kmers"), np.uint8)
     assert np.array_equal(fk, g["final_kmers"])
     assert "reference-built and GPU-built KMerIndex agree" in p.stdout
+
+
+@needs_tool
+@pytest.mark.gpu
+def test_tool_takes_gzipped_fastq_like_the_original():
+    """same reads as a gzipped FASTQ with N-containing reads added: the library's ingest (kseq semantics + LongestValid) in front of
+    the same adapter; the N reads are cut to their longest valid run, which here is shorter than k and so contributes nothing"""
+    import gzip
+    g = G.load("ecoli_k21_B16_count")
+    with tempfile.TemporaryDirectory() as d:
+        fq = os.path.join(d, "reads.fq.gz")
+        with gzip.open(fq, "wt") as f:
+            for i, r in enumerate(g["reads"]):
+                f.write("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+            f.write("@n1\nACGTACGTNNNNACGTACGTACNNNN\n+\nIIIIIIIIIIIIIIIIIIIIIIIIII\n")
+        w = os.path.join(d, "w")
+        p = subprocess.run([TOOL, fq, str(g["k"]), w, str(g["B"])], capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        fk = np.fromfile(os.path.join(w, "final_kmers"), np.uint8)
+    assert np.array_equal(fk, g["final_kmers"])
