@@ -361,8 +361,12 @@ def main():
                          # 20 M-read workload, one launch): only quoted when the bench runs that workload
                          # no ncu --set full capture of the current dominant kernel exists yet (the capture of the rolling partition kernel failed,
                          # profiles/README): null rather than a number from an older kernel
-                         "traffic": None,
-                         "traffic_note": "ncu --set full exists for levelA_count_roll_k (profiles/r01b_*) and for the previous generation of the partition / refinement / sort kernels (profiles/r01_*)",
+                         # per-launch DRAM bytes are only quoted for the workload ncu captured (4 M reads: profiles/r01c_ncu_full_staged_*.csv);
+                         # for other sizes the capture is reported next to it instead of being extrapolated
+                         "traffic": ({"extract_scatter_ms": 14.46e9, "refine_ms": 18.53e9}.get(dom) if (n_reads == 4_000_000 and world == 1) else None),
+                         "traffic_ncu": {"workload": "4 M reads (380 M records, 6.08 GB), one launch", "levelA_scatter_roll_k": {"dram_bytes": 14.46e9, "algorithmic_bytes": 6.24e9},
+                                         "refine_k<2,true>": {"dram_bytes": 18.53e9, "algorithmic_bytes": 12.16e9, "note": "the kernel reads its input twice (histogram, scatter): 18.2 GB expected"},
+                                         "source": "profiles/r01c_ncu_full_staged_scatter_and_gather_refine_4M.csv"},
                          "launches_per_step": int(max(1, passes)) if dom == "extract_scatter_ms" else None,
                          "algorithmic_bytes_per_step": int(alg[dom]),
                          "all": {kernel_names[k2]: (alg[k2] / (per_step[k2] / 1e3) / 1e9 if per_step[k2] > 0 else None) for k2 in alg}},

@@ -1590,7 +1590,10 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
         DArr<Seg> segs(ctx, nsegs);
         seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start_p, part_total_p, PA, rA_, b_lo, segs.p);
         ctx->launches++;
-        RefinePlan rp; rp.cap = CAP; rp.target = TARGET; rp.rmax = 11; rp.total_bits = total_bits;
+        RefinePlan rp; rp.cap = CAP; rp.target = TARGET; rp.total_bits = total_bits;
+        // bins per refinement round = open 128-byte lines per CTA. ncu: at <= 512 bins the kernel's DRAM traffic equals its algorithmic
+        // traffic, at 2048 bins (100 M reads) it is twice as slow per record. SGPU_RMAX trades an extra round for fewer bins.
+        rp.rmax = getenv("SGPU_RMAX") ? (uint32_t)std::min(11, std::max(1, atoi(getenv("SGPU_RMAX")))) : 11u;
         DArr<unsigned long long> wcounter(ctx, 4);
         tm.start();
         for (int round = 0; round < 300; ++round) {
