@@ -985,290 +985,15 @@ __device__ __forceinline__ uint64_t *lsd_sort_range(uint64_t *A, uint64_t *Bf, u
     return A;
 }
 
-template <int NW>
-__global__ void __launch_bounds__(kSThreads) local_sort_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
-                                                         uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
-                                                         unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
-    constexpr int CAP = SortCfg<NW>::CAP;
-    extern __shared__ uint64_t sm64[];
-    uint64_t *A = sm64;                         // CAP*NW
-    uint64_t *Bf = sm64 + (size_t)CAP * NW;     // CAP*NW
-    __shared__ uint32_t cnt[kSWarps * 256];
-    __shared__ uint32_t tot[kSWarps + 1];
-    __shared__ uint32_t heads[CAP + 1];
-    __shared__ unsigned long long s_w;
-    __shared__ int s_flag;
-    const int total_bits = 2 * K;
-    for (;;) {
-        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
-        __syncthreads();
-        const uint64_t si = s_w;
-        __syncthreads();
-        if (si >= nsegs) return;
-        const Seg s = segs[si];
-        uint64_t *gsrc = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
-        uint32_t *gcnt = reinterpret_cast<uint32_t *>(((s.bb & 1) ? buf0 : buf1) + s.start * NW);   // counts live in the partner buffer
-        if (s.len == 0) { if (threadIdx.x == 0) ndist[si] = 0; continue; }
-        if (s.len > (uint64_t)CAP) {
-            // only possible when every key bit is fixed: all records are equal
-            if (threadIdx.x == 0) { gcnt[0] = (uint32_t)s.len; ndist[si] = 1; if (s.bits < (uint32_t)total_bits) atomicAdd(&stats[0], 1ull); }
-            continue;
-        }
-        const uint32_t n = (uint32_t)s.len;
-        for (uint32_t i = threadIdx.x; i < n * NW; i += kSThreads) A[i] = gsrc[i];
-        __syncthreads();
-        uint64_t *S = A;
-        const int lo = (int)s.bits;
-        if (n > 1 && lo < total_bits) {
-            const int hi1 = lo + 32 < total_bits ? lo + 32 : total_bits;
-            S = lsd_sort_range<NW>(A, Bf, n, K, lo, hi1, cnt, tot);
-            if (hi1 < total_bits) {
-                // verify full order; the 32-bit window almost always decides it
-                if (threadIdx.x == 0) s_flag = 0;
-                __syncthreads();
-                int bad = 0;
-                for (uint32_t i = threadIdx.x + 1; i < n; i += kSThreads)
-                    if (kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) > 0) bad = 1;
-                if (bad) s_flag = 1;
-                __syncthreads();
-                if (s_flag) {
-                    if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
-                    uint64_t *O = (S == A) ? Bf : A;
-                    S = lsd_sort_range<NW>(S, O, n, K, lo, total_bits, cnt, tot);
-                }
-            }
-        }
-        // run-length unique: heads[j] = position of the j-th distinct key
-        // each thread owns a contiguous slice so distinct indices come out in order
-        const uint32_t per = (n + kSThreads - 1) / kSThreads;
-        const uint32_t i0 = threadIdx.x * per, i1 = min(n, i0 + per);
-        uint32_t nh = 0;
-        for (uint32_t i = i0; i < i1; ++i)
-            if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) ++nh;
-        // block exclusive scan of nh
-        {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            uint32_t inc = nh;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) tot[warp] = inc;
-            __syncthreads();
-            uint32_t wb = 0, all = 0;
-            for (int w = 0; w < kSWarps; ++w) { if (w < warp) wb += tot[w]; all += tot[w]; }
-            uint32_t j = wb + inc - nh;
-            for (uint32_t i = i0; i < i1; ++i)
-                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) heads[j++] = i;
-            if (threadIdx.x == 0) { heads[all] = n; ndist[si] = all; }
-            __syncthreads();
-            for (uint32_t q = threadIdx.x; q < all; q += kSThreads) {
-                const uint32_t h = heads[q];
-                store_rec<NW>(gsrc + (size_t)q * NW, load_rec<NW>(S + (size_t)h * NW));
-                gcnt[q] = heads[q + 1] - h;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- local sort, second generation -------------------------------------------------------------------------------
-// After level A + MSD refinement a segment holds ~CAP/3 records that agree on their first `bits` key bits. Most of
-// them are copies of a few keys (a genomic (k+1)-mer is seen ~coverage times) plus error singletons. Instead of a
-// full radix sort: ONE counting pass on the next kBinBits key bits into shared-memory bins, then one thread per bin
-// collapses equal keys (bins hold 0, 1 or "c copies of one key" almost always), insertion-sorts the bin's few
-// distinct keys and the bins are concatenated. Bins whose dedup work explodes (many distinct keys sharing a long
-// prefix: low-complexity sequence) make the CTA fall back to the exact LSD radix path above.
+// ---- local sort: representative + residual -----------------------------------------------------------------------------
+// After level A + MSD refinement a segment holds ~CAP*3/4 records that agree on their first `bits` key bits. Most of them are
+// copies of a few keys (a genomic (k+1)-mer is seen ~coverage times) plus error singletons. Two earlier generations (a full LSD
+// radix sort per segment; one counting pass into 2^11 bins with one thread collapsing each bin) were replaced by the kernel
+// below; the LSD passes above survive as its exact fallback.
 static const int kBinBits = 11;
 static const int kBins = 1 << kBinBits;
 
-template <int NW>
-__global__ void __launch_bounds__(kSThreads) local_sort2_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
-                                                          uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
-                                                          unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
-    constexpr int CAP = SortCfg<NW>::CAP;
-    extern __shared__ uint64_t sm64[];
-    uint64_t *A = sm64;                                   // CAP*NW
-    uint64_t *Bf = A + (size_t)CAP * NW;                  // CAP*NW
-    uint32_t *cntB = reinterpret_cast<uint32_t *>(Bf + (size_t)CAP * NW);   // CAP     multiplicity per slot of Bf
-    uint32_t *cntA = cntB + CAP;                          // CAP+1   (also `heads` of the LSD fallback)
-    uint32_t *hist = cntA + CAP + 1;                      // kBins   (also cursor)
-    uint32_t *bstart = hist + kBins;                      // kBins+1
-    uint32_t *lsdcnt = bstart + kBins + 1;                // kSWarps*256
-    __shared__ uint32_t tot[kSWarps + 1];
-    __shared__ unsigned long long s_w;
-    __shared__ int s_flag;
-    const int total_bits = 2 * K;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (;;) {
-        if (threadIdx.x == 0) { s_w = atomicAdd(work_counter, 1ull); s_flag = 0; }
-        __syncthreads();
-        const uint64_t si = s_w;
-        if (si >= nsegs) return;
-        const Seg s = segs[si];
-        uint64_t *gsrc = ((s.bb & 1) ? buf1 : buf0) + s.start * NW;
-        uint32_t *gcnt = reinterpret_cast<uint32_t *>(((s.bb & 1) ? buf0 : buf1) + s.start * NW);
-        if (s.len == 0) { if (threadIdx.x == 0) ndist[si] = 0; __syncthreads(); continue; }
-        if (s.len > (uint64_t)CAP) {
-            if (threadIdx.x == 0) { gcnt[0] = (uint32_t)s.len; ndist[si] = 1; if (s.bits < (uint32_t)total_bits) atomicAdd(&stats[0], 1ull); }
-            __syncthreads();
-            continue;
-        }
-        const uint32_t n = (uint32_t)s.len;
-        const int lo = (int)s.bits;
-        const int r2 = (total_bits - lo) < kBinBits ? (total_bits - lo) : kBinBits;
-        const uint32_t nb = 1u << r2;
-        // ---- phase 1: load + histogram
-        for (uint32_t i = threadIdx.x; i < nb; i += kSThreads) hist[i] = 0;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += kSThreads) {
-            Kmer<NW> k = load_rec<NW>(gsrc + (size_t)i * NW);
-            store_rec<NW>(A + (size_t)i * NW, k);
-            atomicAdd(&hist[r2 ? key_bits<NW>(k, K, lo, r2) : 0u], 1u);
-        }
-        __syncthreads();
-        // ---- phase 2: exclusive scan of the bins (each thread owns kBins/kSThreads consecutive bins)
-        constexpr int BPT = kBins / kSThreads;
-        const uint32_t b0 = threadIdx.x * BPT;
-        uint32_t loc[BPT];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < BPT; ++q) { loc[q] = (b0 + q < nb) ? hist[b0 + q] : 0; sum += loc[q]; }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) tot[warp] = inc;
-        __syncthreads();
-        uint32_t wb = 0;
-        for (int w = 0; w < warp; ++w) wb += tot[w];
-        uint32_t run = wb + inc - sum;
-#pragma unroll
-        for (int q = 0; q < BPT; ++q) {
-            if (b0 + q < nb) { bstart[b0 + q] = run; hist[b0 + q] = run; }
-            run += loc[q];
-        }
-        if (threadIdx.x == kSThreads - 1) bstart[nb] = n;
-        __syncthreads();
-        // ---- phase 3: scatter into bins
-        for (uint32_t i = threadIdx.x; i < n; i += kSThreads) {
-            Kmer<NW> k = load_rec<NW>(A + (size_t)i * NW);
-            const uint32_t pos = atomicAdd(&hist[r2 ? key_bits<NW>(k, K, lo, r2) : 0u], 1u);
-            store_rec<NW>(Bf + (size_t)pos * NW, k);
-        }
-        __syncthreads();
-        // ---- phase 4: per-bin dedup + tiny sort. distinct keys of bin b end up in Bf[bstart[b] .. +d) with cntB
-        uint32_t dloc[BPT];
-        uint32_t dsum = 0;
-        bool bad = false;
-#pragma unroll
-        for (int q = 0; q < BPT; ++q) {
-            dloc[q] = 0;
-            if (b0 + q >= nb) continue;
-            const uint32_t bs = bstart[b0 + q], be = bstart[b0 + q + 1];
-            if (be == bs) continue;
-            if (be - bs == 1) { cntB[bs] = 1; dloc[q] = 1; dsum += 1; continue; }
-            uint32_t rem_end = be, p = bs, work = 0;
-            while (p < rem_end) {
-                const Kmer<NW> key = load_rec<NW>(Bf + (size_t)p * NW);
-                uint32_t c = 1, w = p + 1;
-                for (uint32_t j = p + 1; j < rem_end; ++j) {
-                    const Kmer<NW> x = load_rec<NW>(Bf + (size_t)j * NW);
-                    if (kmer_eq<NW>(x, key)) ++c;
-                    else { if (w != j) store_rec<NW>(Bf + (size_t)w * NW, x); ++w; }
-                }
-                work += rem_end - p;
-                cntB[p] = c;
-                rem_end = w;
-                ++p;
-                if (work > 4096u || p - bs > 24u) { bad = true; break; }
-            }
-            if (bad) break;
-            const uint32_t d = p - bs;
-            for (uint32_t a = bs + 1; a < bs + d; ++a) {             // insertion sort of the d distinct keys
-                const Kmer<NW> key = load_rec<NW>(Bf + (size_t)a * NW);
-                const uint32_t kc = cntB[a];
-                uint32_t z = a;
-                while (z > bs && kmer_word_cmp<NW>(load_rec<NW>(Bf + (size_t)(z - 1) * NW), key) > 0) {
-                    store_rec<NW>(Bf + (size_t)z * NW, load_rec<NW>(Bf + (size_t)(z - 1) * NW));
-                    cntB[z] = cntB[z - 1];
-                    --z;
-                }
-                store_rec<NW>(Bf + (size_t)z * NW, key);
-                cntB[z] = kc;
-            }
-            dloc[q] = d; dsum += d;
-        }
-        if (bad) s_flag = 1;
-        __syncthreads();
-        if (s_flag) {
-            // exact fallback: LSD radix over every remaining key bit, then run-length unique (A still holds the records)
-            if (threadIdx.x == 0) atomicAdd(&stats[1], 1ull);
-            uint64_t *S = lsd_sort_range<NW>(A, Bf, n, K, lo, total_bits, lsdcnt, tot);
-            uint32_t *heads = cntA;
-            const uint32_t per = (n + kSThreads - 1) / kSThreads;
-            const uint32_t i0 = threadIdx.x * per, i1 = min(n, i0 + per);
-            uint32_t nh = 0;
-            for (uint32_t i = i0; i < i1; ++i)
-                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) ++nh;
-            uint32_t hinc = nh;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, hinc, o);
-                if (lane >= o) hinc += t;
-            }
-            if (lane == 31) tot[warp] = hinc;
-            __syncthreads();
-            uint32_t hb = 0, all = 0;
-            for (int w = 0; w < kSWarps; ++w) { if (w < warp) hb += tot[w]; all += tot[w]; }
-            uint32_t j = hb + hinc - nh;
-            for (uint32_t i = i0; i < i1; ++i)
-                if (i == 0 || kmer_word_cmp<NW>(load_rec<NW>(S + (size_t)(i - 1) * NW), load_rec<NW>(S + (size_t)i * NW)) != 0) heads[j++] = i;
-            if (threadIdx.x == 0) { heads[all] = n; ndist[si] = all; }
-            __syncthreads();
-            for (uint32_t q = threadIdx.x; q < all; q += kSThreads) {
-                const uint32_t h = heads[q];
-                store_rec<NW>(gsrc + (size_t)q * NW, load_rec<NW>(S + (size_t)h * NW));
-                gcnt[q] = heads[q + 1] - h;
-            }
-            __syncthreads();
-            continue;
-        }
-        // ---- phase 5: concatenate the bins' distinct keys (A is free now) and write back coalesced
-        uint32_t dinc = dsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, dinc, o);
-            if (lane >= o) dinc += t;
-        }
-        if (lane == 31) tot[warp] = dinc;
-        __syncthreads();
-        uint32_t db = 0, all = 0;
-        for (int w = 0; w < kSWarps; ++w) { if (w < warp) db += tot[w]; all += tot[w]; }
-        uint32_t o = db + dinc - dsum;
-#pragma unroll
-        for (int q = 0; q < BPT; ++q) {
-            if (!dloc[q]) continue;
-            const uint32_t bs = bstart[b0 + q];
-            for (uint32_t z = 0; z < dloc[q]; ++z) {
-                store_rec<NW>(A + (size_t)(o + z) * NW, load_rec<NW>(Bf + (size_t)(bs + z) * NW));
-                cntA[o + z] = cntB[bs + z];
-            }
-            o += dloc[q];
-        }
-        if (threadIdx.x == 0) ndist[si] = all;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < all * NW; i += kSThreads) gsrc[i] = A[i];
-        for (uint32_t i = threadIdx.x; i < all; i += kSThreads) gcnt[i] = cntA[i];
-        __syncthreads();
-    }
-}
-
-// ---- local sort, third generation: representative + residual ------------------------------------------------------
-// ncu on the second generation showed 8.5 active lanes per instruction and barrier stalls on top: one thread chewing
+// ncu on the one-thread-per-bin generation showed 8.5 active lanes per instruction and barrier stalls on top: one thread chewing
 // through the ~coverage copies of a genomic k-mer held up its whole CTA. Here every bin elects a representative (the
 // record with the smallest index, one shared-memory atomicMin per record); records equal to their bin's representative
 // only bump a counter. Only the few records that differ from it (bins holding two or more distinct keys) are scattered
