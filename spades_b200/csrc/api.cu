@@ -532,9 +532,16 @@ static void selftest_nw(Ctx *c, int on_device, int op, int K, uint64_t arg, cons
     SG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     SG_CUDA(cudaStreamSynchronize(c->stream));
 }
+// op 11 (host only): the sector-pairing mailbox protocol of pair_mailbox.cuh under real concurrency, see selftest_host.cpp
+extern "C" int sg_selftest_pair_mailbox(uint64_t arg, int64_t per_thread, uint64_t *out);
+
 extern "C" int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
     if (K < 1 || K > 128 || n < 0 || (n && (!keys || !out))) return SGPU_EINVAL;
     Ctx *c = ctx ? &ctx->c : nullptr;
+    if (op == 11) {
+        if (on_device || n < 3) return SGPU_EINVAL;
+        return sg_selftest_pair_mailbox(arg, (int64_t)keys[0], out);
+    }
     API_TRY(c, {
         if (on_device) SG_CUDA(cudaSetDevice(c->device));
         switch (nwords_of(K)) {

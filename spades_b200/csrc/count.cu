@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "sgpu_internal.h"
+#include "pair_mailbox.cuh"
 
 namespace sg {
 
@@ -486,17 +487,41 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc 
 // base rows are `row_stride` cursors long; this launch handles the partitions [q_lo, q_lo + p.PA) of a row (p.PA = the
 // sub-range's size, id_lo = id of its first partition): a bucket-group pass may be split into partition sub-ranges so that
 // the lines and pages a CTA has open at any time stay few (TLB reach).
-template <int NW, bool HAS_IDS>
+// stores of the pairing variant (pair_mailbox.cuh): one full 32-byte sector for two records of a stream, 16 bytes for a lone record
+struct PairSink {
+    uint64_t *out;
+    __device__ __forceinline__ void pair(uint64_t pos, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1) {
+        asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + pos * 2), "l"(a0), "l"(a1), "l"(b0), "l"(b1) : "memory");
+    }
+    __device__ __forceinline__ void single(uint64_t pos, uint64_t w0, uint64_t w1) {
+        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(out + pos * 2), "l"(w0), "l"(w1) : "memory");
+    }
+};
+template <int NW, bool PAIR>
+__device__ __forceinline__ void emit_rec(uint64_t *out, const uint64_t *cur_base, uint32_t *cnt, PmBox *boxes, uint32_t part, const Kmer<NW> &k) {
+    const uint32_t slot = atomicAdd(&cnt[part], 1u);
+    if constexpr (PAIR && NW == 2) {
+        PairSink sink{out};
+        pm_put(boxes + (size_t)part * kPmDepth, cur_base[part], slot, k.w[0], k.w[1], sink);
+    } else {
+        store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+    }
+}
+
+template <int NW, bool HAS_IDS, bool PAIR>
 __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
                                                                         const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
                                                                         uint32_t id_lo, uint32_t row_stride, uint32_t q_lo) {
     extern __shared__ uint32_t sm_dyn[];
     uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    PmBox *boxes = reinterpret_cast<PmBox *>(cur_base + p.PA);          // PAIR: PA * kPmDepth mailboxes (24 bytes each)
+    uint32_t *cnt = PAIR ? reinterpret_cast<uint32_t *>(boxes + (size_t)p.PA * kPmDepth) : reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
     __shared__ RollTile rt;
     __shared__ TileStage ts;
     uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
+    if (PAIR)
+        for (uint32_t i = threadIdx.x; i < p.PA * kPmDepth; i += blockDim.x) boxes[i].state = 0u;
     __syncthreads();
     const int K = p.K;
     const uint32_t PA = p.PA;
@@ -532,21 +557,22 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
                         const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;     // 0xffff - id_lo stays >= PA
                         if (part < PA) {
                             const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
-                            const uint32_t slot = atomicAdd(&cnt[part], 1u);
-                            store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+                            emit_rec<NW, PAIR>(out, cur_base, cnt, boxes, part, k);
                         }
                     } else {
                         const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
                         uint32_t part;
-                        if (part_of<NW>(p, k, &part)) {
-                            const uint32_t slot = atomicAdd(&cnt[part], 1u);
-                            store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
-                        }
+                        if (part_of<NW>(p, k, &part)) emit_rec<NW, PAIR>(out, cur_base, cnt, boxes, part, k);
                     }
                 }
             }
         }
         __syncthreads();
+    }
+    if constexpr (PAIR && NW == 2) {
+        // every producer is past the barrier that ends the last tile: what is still deposited goes out as single records
+        PairSink sink{out};
+        for (uint32_t i = threadIdx.x; i < PA * kPmDepth; i += blockDim.x) pm_flush_box(&boxes[i], cur_base[i / kPmDepth], sink);
     }
     for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
 }
@@ -1617,8 +1643,13 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
             } else if (roll) {
                 if constexpr (kIsReads) {
                     size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
-                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    // sector pairing (pair_mailbox.cuh): opt-in until measured on the GPU; 16-byte records only, and only while the
+                    // mailboxes of a sub-range fit next to two resident CTAs
+                    const bool want_pair = NW == 2 && use_ids && getenv("SGPU_PAIR") && atoi(getenv("SGPU_PAIR")) != 0;
+                    const size_t pair_bytes = sizeof(uint64_t) + sizeof(uint32_t) + (size_t)kPmDepth * sizeof(PmBox);
+                    if (want_pair) SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 * pair_bytes)));
                     // partition sub-ranges (only with the id array, where a foreign window costs just the roll): fewer lines and pages open per CTA
                     // a sub-range costs one more roll over ALL windows of the source and pays per record written: worth it when the pass
                     // holds most of the job's records (measured: 20 M reads / 1 pass: 46.5 / 36.7 / 31.5 ms with 1 / 2 / 4 sub-ranges;
@@ -1635,8 +1666,10 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
                         for (size_t si = 0; si < srcs.size(); ++si) {
                             const Src &src = srcs[si];
                             if (src.n == 0) continue;
-                            if (use_ids) levelA_scatter_roll_k<NW, true><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo);
-                            else levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u, PA, 0u);
+                            if (use_ids && want_pair && pa_sub.PA <= 1024u)
+                                levelA_scatter_roll_k<NW, true, true><<<G, kRollThreads, pa_sub.PA * pair_bytes, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo);
+                            else if (use_ids) levelA_scatter_roll_k<NW, true, false><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo);
+                            else levelA_scatter_roll_k<NW, false, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u, PA, 0u);
                             ctx->launches++;
                         }
                     }

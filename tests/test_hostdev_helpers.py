@@ -90,6 +90,23 @@ def check_roll(ctx_h, on_device):
                 assert int(out[u]) == (cnt << 32), (K, L, u, hex(int(out[u])))
 
 
+def test_pair_mailbox_protocol_under_host_threads():
+    """op 11: the sector-pairing mailbox protocol (pair_mailbox.cuh; opt-in level-A variant for round 2) hammered by real host
+    threads: whatever the interleaving every position is written exactly once with its own record, and pairs do form."""
+    L = _lib.load()
+    for threads, streams, per_thread in ((8, 64, 200000), (16, 4096, 100000), (8, 1, 100000), (3, 7, 50001), (1, 16, 10000)):
+        keys = np.array([per_thread, 0, 0], np.uint64)
+        out = np.zeros(3, np.uint64)
+        rc = L.sgpu_selftest(None, 0, 11, 21, (threads << 32) | streams, keys.ctypes.data_as(C.c_void_p), 3, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        errors, pairs, singles = (int(x) for x in out)
+        assert errors == 0, (threads, streams, per_thread, errors)
+        assert 2 * pairs + singles == threads * per_thread
+        assert pairs > 0
+        if threads == 1:
+            assert singles <= 3 * streams          # a single producer pairs everything but the odd ends
+
+
 def test_host_roll_matches_direct_extraction():
     check_roll(None, 0)
 
