@@ -15,6 +15,8 @@ step "gpu suite, defaults"
 timeout 200 python -m pytest tests -q -m gpu --timeout 150 > $O/s1_tests.log 2>&1; echo "exit=$?" >> $O/s1_tests.log; tail -3 $O/s1_tests.log
 step "parity, sector pairing"
 SGPU_PAIR=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair.log; tail -3 $O/s1_tests_pair.log
+step "parity, sector pairing in the refinement too"
+SGPU_PAIR=1 SGPU_PAIR_REFINE=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair_refine.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair_refine.log; tail -3 $O/s1_tests_pair_refine.log
 step "parity, three-level split (RMAX=7, PA_MAX=1280)"
 SGPU_RMAX=7 SGPU_PA_MAX=1280 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_rmax7.log 2>&1; echo "exit=$?" >> $O/s1_tests_rmax7.log; tail -3 $O/s1_tests_rmax7.log
 step "sanitizer smoke, pairing"
@@ -30,12 +32,12 @@ for cfg in "0 4 11 4096" "1 4 11 4096" "1 2 11 4096" "1 3 11 4096" "0 4 9 4096" 
   ph $f
 done
 # 100 M reads
-for cfg in "0 11 4096" "1 11 4096" "0 7 1280" "1 7 1280" "0 9 4096" "0 8 2560"; do
-  set -- $cfg
+for cfg in "0 11 4096" "1 11 4096" "2 11 4096" "0 7 1280" "1 7 1280" "0 9 4096" "0 8 2560"; do
+  set -- $cfg          # pair: 0 = off, 1 = level A, 2 = level A + refinement
   [ $(left) -gt 60 ] || break
   step "bench 100M pair=$1 rmax=$2 pamax=$3"
   f=$O/s1_bench100_pair$1_rmax$2_pa$3.json
-  SGPU_PAIR=$1 SGPU_RMAX=$2 SGPU_PA_MAX=$3 timeout 150 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $f 2> ${f%.json}.err
+  SGPU_PAIR=$(( $1 > 0 )) SGPU_PAIR_REFINE=$(( $1 > 1 )) SGPU_RMAX=$2 SGPU_PA_MAX=$3 timeout 150 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $f 2> ${f%.json}.err
   ph $f
 done
 step "done"

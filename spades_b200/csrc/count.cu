@@ -502,7 +502,7 @@ __device__ __forceinline__ void emit_rec(uint64_t *out, const uint64_t *cur_base
     const uint32_t slot = atomicAdd(&cnt[part], 1u);
     if constexpr (PAIR && NW == 2) {
         PairSink sink{out};
-        pm_put(boxes + (size_t)part * kPmDepth, cur_base[part], slot, k.w[0], k.w[1], sink);
+        pm_put<kPmDepth>(boxes + (size_t)part * kPmDepth, cur_base[part], slot, k.w[0], k.w[1], sink);
     } else {
         store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
     }
@@ -827,7 +827,9 @@ static const int kRMaxBins = 2048;
 // one CTA splits one oversize segment by its next r key bits: buf[bb&1] -> buf[(bb&1)^1]
 // PIECED: the segments are level-A partitions whose records lie in G pieces of the CTA-major staging buffer (buf0); segment
 // index == partition. The pieces are read one after the other, the children are written contiguously into buf1.
-template <int NW, bool PIECED>
+// PAIR (opt-in, 16-byte records): the scatter phase pairs the two records of a 32-byte sector through one mailbox per bin
+// (pair_mailbox.cuh) -- at 2048 bins a bin receives a record only every ~8 us and half-written sectors do not survive in L2.
+template <int NW, bool PIECED, bool PAIR>
 __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ segs, const uint64_t *__restrict__ worklist, uint64_t nwork,
                                                      const uint64_t *__restrict__ child_base, RefinePlan rp, int K,
                                                      uint64_t *__restrict__ buf0, uint64_t *__restrict__ buf1, Seg *__restrict__ nsegs,
@@ -837,6 +839,8 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
     __shared__ unsigned long long s_w;
     __shared__ uint64_t pc_start[PIECED ? kMaxPieces : 1];
     __shared__ uint32_t pc_len[PIECED ? kMaxPieces : 1];
+    extern __shared__ uint64_t sm_refine_dyn[];
+    PmBox *boxes = reinterpret_cast<PmBox *>(sm_refine_dyn);           // PAIR: one mailbox per bin
     for (;;) {
         if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
         __syncthreads();
@@ -910,25 +914,35 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
         __syncthreads();
         if (i0 < nb) hist[i0] = ex;
         if (i0 + 1 < nb) hist[i0 + 1] = ex + a;
+        if (PAIR)
+            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) boxes[i].state = 0u;
         __syncthreads();
+        uint64_t *dbuf = (s.bb & 1) ? buf0 : buf1;                    // dst = dbuf + s.start * NW
+        auto put = [&](const Kmer<NW> &k) {
+            const uint32_t bin = key_bits<NW>(k, K, (int)s.bits, r);
+            const uint32_t slot = atomicAdd(&hist[bin], 1u);
+            if constexpr (PAIR && NW == 2) {
+                PairSink sink{dbuf};
+                pm_put<1>(boxes + bin, s.start, slot, k.w[0], k.w[1], sink);
+            } else {
+                store_rec<NW>(dst + (uint64_t)slot * NW, k);
+            }
+        };
         if (PIECED) {
             for (int g = 0; g < pc.G; ++g) {
                 const uint64_t *ps = buf0 + pc_start[g] * NW;
                 const uint32_t n = pc_len[g];
-                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                    Kmer<NW> k = load_rec<NW>(ps + (uint64_t)i * NW);
-                    uint32_t slot = atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
-                    store_rec<NW>(dst + (uint64_t)slot * NW, k);
-                }
+                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) put(load_rec<NW>(ps + (uint64_t)i * NW));
             }
         } else {
-        for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) {
-            Kmer<NW> k = load_rec<NW>(src + i * NW);
-            uint32_t slot = atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
-            store_rec<NW>(dst + (uint64_t)slot * NW, k);
-        }
+            for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) put(load_rec<NW>(src + i * NW));
         }
         __syncthreads();
+        if constexpr (PAIR && NW == 2) {
+            PairSink sink{dbuf};
+            for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) pm_flush_box(&boxes[i], s.start, sink);
+            __syncthreads();
+        }
     }
 }
 
@@ -1370,8 +1384,15 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
             ctx->launches++;
             SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
             int grid = (int)std::min<uint64_t>(tot[1], (uint64_t)ctx->num_sms * 2);
-            if (pieced) refine_k<NW, true><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
-            else refine_k<NW, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
+            const bool pair_refine = NW == 2 && getenv("SGPU_PAIR_REFINE") && atoi(getenv("SGPU_PAIR_REFINE")) != 0;     // opt-in until measured
+            if (pair_refine) {
+                const size_t sm = (size_t)kRMaxBins * sizeof(PmBox);
+                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                if (pieced) refine_k<NW, true, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
+                else refine_k<NW, false, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
+            } else if (pieced) refine_k<NW, true, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
+            else refine_k<NW, false, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
             SG_CUDA(cudaStreamSynchronize(st));

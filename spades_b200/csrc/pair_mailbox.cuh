@@ -39,17 +39,17 @@ static inline uint32_t pm_cas_host(uint32_t *p, uint32_t cmp, uint32_t val) {
 
 namespace sg {
 
-static const int kPmDepth = 2;                   // mailboxes per stream
+static const int kPmDepth = 2;                   // mailboxes per stream in the level-A kernel (the refinement kernel uses 1)
 struct PmBox { uint64_t w0, w1; uint32_t slot; uint32_t state; };      // 24 bytes
 // state: 0 = EMPTY, else ((slot + 1) << 2) | phase of the record the box holds / is receiving
 enum { kPmWriting = 1, kPmFull = 2, kPmTaking = 3 };
 
 // Sink: void pair(uint64_t first_pos, a0, a1, b0, b1)  -- records at first_pos (even) and first_pos + 1
 //       void single(uint64_t pos, w0, w1)
-template <class Sink>
-PM_HD void pm_put(PmBox *boxes /* this stream's kPmDepth boxes */, uint64_t base, uint32_t slot, uint64_t w0, uint64_t w1, Sink &sink) {
+template <int DEPTH, class Sink>
+PM_HD void pm_put(PmBox *boxes /* this stream's DEPTH boxes (DEPTH a power of two) */, uint64_t base, uint32_t slot, uint64_t w0, uint64_t w1, Sink &sink) {
     const uint64_t pos = base + slot;
-    PmBox *bx = boxes + ((pos >> 1) & (kPmDepth - 1));
+    PmBox *bx = boxes + ((pos >> 1) & (uint64_t)(DEPTH - 1));
     const uint32_t mine_w = ((slot + 1u) << 2) | kPmWriting, mine_f = ((slot + 1u) << 2) | kPmFull;
     // partner = the other half of my sector; it exists in this stream only if its slot is >= 0
     const bool odd = (pos & 1) != 0;

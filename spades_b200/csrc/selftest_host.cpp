@@ -55,7 +55,7 @@ extern "C" int sg_selftest_pair_mailbox(uint64_t arg, int64_t per_thread, uint64
             for (uint32_t p : plan[t]) {
                 const uint32_t slot = __atomic_fetch_add(&cnt[p], 1u, __ATOMIC_RELAXED);
                 const uint64_t pos = base[p] + slot;
-                pm_put(boxes.data() + (size_t)p * kPmDepth, base[p], slot, PmTestSink::f0(pos), PmTestSink::f1(pos), sink);
+                pm_put<kPmDepth>(boxes.data() + (size_t)p * kPmDepth, base[p], slot, PmTestSink::f0(pos), PmTestSink::f1(pos), sink);
             }
         });
     for (auto &t : th) t.join();
