@@ -33,63 +33,82 @@ struct sgpu_read_batch {
 
 namespace {
 
-inline int nucl_code(unsigned char c) {      // -1 = not a nucleotide
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: return -1;
-    }
-}
-
 struct GzReader {
     gzFile f = nullptr;
-    std::vector<unsigned char> buf;
+    std::vector<char> buf;
     size_t pos = 0, end = 0;
     bool eof = false;
+    std::string carry;
     bool open(const char *path) {
         f = gzopen(path, "rb");       // transparently reads plain files too
         if (!f) return false;
         gzbuffer(f, 1 << 20);
-        buf.resize(1 << 20);
+        buf.resize(4 << 20);
         return true;
     }
     ~GzReader() { if (f) gzclose(f); }
-    int get() {
-        if (pos == end) {
-            if (eof) return -1;
-            int n = gzread(f, buf.data(), (unsigned)buf.size());
-            if (n <= 0) { eof = true; return -1; }
-            pos = 0; end = (size_t)n;
+    bool refill() {
+        if (eof) return false;
+        const int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n <= 0) { eof = true; return false; }
+        pos = 0; end = (size_t)n;
+        return true;
+    }
+    // next line without its '\n'; the view is valid until the next call. false at end of input.
+    bool getline(const char *&p, size_t &n) {
+        carry.clear();
+        bool have_carry = false;
+        for (;;) {
+            if (pos == end && !refill()) {
+                if (!have_carry) return false;
+                p = carry.data(); n = carry.size();
+                return true;
+            }
+            const char *nl = (const char *)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                const size_t len = (size_t)(nl - (buf.data() + pos));
+                if (have_carry) { carry.append(buf.data() + pos, len); p = carry.data(); n = carry.size(); }
+                else { p = buf.data() + pos; n = len; }
+                pos += len + 1;
+                return true;
+            }
+            carry.append(buf.data() + pos, end - pos);
+            have_carry = true;
+            pos = end;
         }
-        return buf[pos++];
     }
-    int peek() {
-        int c = get();
-        if (c >= 0) --pos;
-        return c;
-    }
+};
+
+static const int8_t kCode[256] = {
+#define X16 -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1
+    X16, X16, X16, X16,
+    -1, 0, -1, 1, -1, -1, -1, 2, -1, -1, -1, -1, -1, -1, -1, -1,  -1, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,     // @ A..O, P..
+    -1, 0, -1, 1, -1, -1, -1, 2, -1, -1, -1, -1, -1, -1, -1, -1,  -1, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,     // ` a..o, p..
+    X16, X16, X16, X16, X16, X16, X16, X16
+#undef X16
 };
 
 void add_read(sgpu_read_batch *b, const std::string &seq, bool longest_valid) {
     ++b->records;
-    size_t from = 0, to = seq.size();
+    const unsigned char *s = (const unsigned char *)seq.data();
+    const size_t sz = seq.size();
+    size_t from = 0, to = sz;
     if (longest_valid) {
         // first longest run of nucleotides (LongestValidCoords)
         size_t best_len = 0, best_pos = 0, run = 0;
-        for (size_t i = 0; i <= seq.size(); ++i) {
-            if (i < seq.size() && nucl_code((unsigned char)seq[i]) >= 0) ++run;
+        for (size_t i = 0; i < sz; ++i) {
+            if (kCode[s[i]] >= 0) ++run;
             else {
                 if (run > best_len) { best_len = run; best_pos = i - run; }
                 run = 0;
             }
         }
+        if (run > best_len) { best_len = run; best_pos = sz - run; }
         from = best_pos; to = best_pos + best_len;
-        if (best_len < seq.size()) ++b->trimmed;
+        if (best_len < sz) ++b->trimmed;
     } else {
-        for (size_t i = 0; i < seq.size(); ++i)
-            if (nucl_code((unsigned char)seq[i]) < 0) { from = to = 0; break; }      // without N handling an invalid read contributes nothing
+        for (size_t i = 0; i < sz; ++i)
+            if (kCode[s[i]] < 0) { from = to = 0; break; }      // without N handling an invalid read contributes nothing
     }
     const size_t len = to - from;
     if (len == 0) { ++b->dropped; return; }
@@ -97,43 +116,63 @@ void add_read(sgpu_read_batch *b, const std::string &seq, bool longest_valid) {
     const size_t w0 = b->words.size();
     b->words.resize(w0 + nw, 0);
     uint64_t *w = b->words.data() + w0;
-    for (size_t i = 0; i < len; ++i) w[i >> 5] |= (uint64_t)nucl_code((unsigned char)seq[from + i]) << ((i & 31) << 1);
+    const unsigned char *q = s + from;
+    for (size_t j = 0; j < nw; ++j) {
+        const size_t m = len - 32 * j < 32 ? len - 32 * j : 32;
+        uint64_t x = 0;
+        for (size_t i = 0; i < m; ++i) x |= (uint64_t)kCode[q[32 * j + i]] << (2 * i);
+        w[j] = x;
+    }
     b->offs.push_back((uint64_t)w0);
     b->lens.push_back((uint32_t)len);
 }
 
-// kseq_read semantics (ext/include/kseq/kseq.h): skip to the next '>' / '@'; name up to the first space; the rest of the header
-// line is the comment; sequence lines are concatenated (blanks skipped) until a line starts with '>', '@' or '+'; after '+' the
-// quality is read until it is at least as long as the sequence
+// kseq_read as vendored by the reference (ext/include/kseq/kseq.h:171-213), line by line:
+//  * a record starts at the next '>' or '@' found ANYWHERE in the stream (:177) -- after a FASTQ record; after a FASTA record the
+//    marker line that ended the sequence is the header (:196);
+//  * sequence: every following line that does not start with '>', '@' or '+' is appended whole -- blanks included, they are
+//    just invalid characters for LongestValid -- minus ONE trailing '\r' when the sequence so far is longer than 1 (:136,189-195);
+//    empty lines are skipped;
+//  * quality ('+'): whole lines are appended until the quality is at least as long as the sequence (at least one line is read),
+//    and any other length is an error (:206-209).
 bool parse_fastx(const char *path, bool longest_valid, sgpu_read_batch *b) {
     GzReader in;
     if (!in.open(path)) { b->err = std::string("cannot open ") + path; return false; }
-    int c;
+    const char *p;
+    size_t n;
     std::string seq;
-    // find the first header
-    while ((c = in.get()) >= 0 && c != '>' && c != '@') {}
-    while (c >= 0) {
-        // header line
-        while ((c = in.get()) >= 0 && c != '\n') {}
+    bool scan = true;            // true: look for '>' / '@' anywhere; false: the line in (p, n) is the header
+    bool have = false;
+    for (;;) {
+        if (scan) {
+            have = false;
+            while (in.getline(p, n)) {
+                if (memchr(p, '>', n) || memchr(p, '@', n)) { have = true; break; }
+            }
+            if (!have) break;
+        }
+        // (p, n) is a header line: name / comment are not needed
         seq.clear();
-        // sequence lines
-        bool at_line_start = true;
-        for (;;) {
-            c = in.get();
-            if (c < 0) break;
-            if (at_line_start && (c == '>' || c == '@' || c == '+')) break;
-            if (c == '\n') { at_line_start = true; continue; }
-            at_line_start = false;
-            if (c == '\r' || c == ' ' || c == '\t') continue;          // kseq keeps only isgraph() characters
-            seq.push_back((char)c);
+        int stop = -1;           // the character that ended the sequence, -1 = end of input
+        while (in.getline(p, n)) {
+            if (n == 0) continue;
+            if (p[0] == '>' || p[0] == '@' || p[0] == '+') { stop = p[0]; break; }
+            seq.append(p, n);
+            if (seq.size() > 1 && seq.back() == '\r') seq.pop_back();
         }
         add_read(b, seq, longest_valid);
-        if (c == '+') {
-            while ((c = in.get()) >= 0 && c != '\n') {}                  // rest of the '+' line
+        if (stop < 0) break;
+        if (stop == '+') {
             size_t q = 0;
-            while (q < seq.size() && (c = in.get()) >= 0) if (c != '\n' && c != '\r') ++q;
-            if (q < seq.size()) { b->err = "truncated quality string"; return false; }
-            while ((c = in.get()) >= 0 && c != '>' && c != '@') {}      // next header
+            do {
+                if (!in.getline(p, n)) { b->err = "truncated quality string"; return false; }
+                q += n;
+                if (q > 1 && n && p[n - 1] == '\r') --q;
+            } while (q < seq.size());
+            if (q != seq.size()) { b->err = "quality string is of a different length than the sequence"; return false; }
+            scan = true;
+        } else {
+            scan = false;
         }
     }
     return true;

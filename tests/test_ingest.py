@@ -84,6 +84,23 @@ def test_fastq_fasta_variants(tmp_path):
         read_fastx(tmp_path / "missing.fq")
 
 
+def test_kseq_corner_semantics(tmp_path):
+    """the vendored kseq keeps blanks inside a sequence line (they are invalid characters for LongestValid), strips one trailing CR
+    per line, skips empty lines, finds the next record at the next '>' / '@' anywhere after a FASTQ record, and rejects a
+    quality string of another length (ext/include/kseq/kseq.h:171-213)"""
+    p = tmp_path / "c.fq"
+    open(p, "wb").write(b"junk line\nmore >r0 header found mid-line\nACGT ACGTA\n\nAC\tGGGGGG\r\n+\nIIIIIIIIII\nIIIIIIIII\n"
+                        b"trailing junk @r1\nacgtnacg\n+r1\nIIIIIIII\n>r2\nAAAA\nCCCC\n>r3\n>r4\nTTTT")
+    b = read_fastx(p)
+    # r0: "ACGT ACGTA" + "AC\tGGGGGG" -> longest valid run "GGGGGG"; r1: "ACGTNACG" -> "ACGT"; r2: "AAAACCCC"; r3: empty (dropped); r4: "TTTT"
+    assert b.strings() == ["ACGTAAC", "ACGT", "AAAACCCC", "TTTT"]
+    assert (b.records, b.dropped) == (5, 1)
+    bad = tmp_path / "bad.fq"
+    open(bad, "w").write("@r\nACGTACGT\n+\nIIIIIIIIII\n")
+    with pytest.raises(IOError):
+        read_fastx(bad)
+
+
 def test_truncated_fastq_is_an_error(tmp_path):
     p = tmp_path / "t.fq"
     open(p, "w").write("@r\nACGTACGT\n+\nIIII")
