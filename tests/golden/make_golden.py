@@ -85,7 +85,43 @@ def save(name, mode, reads, k, B, early_tc=0):
     print(name, {a: len(b) for a, b in res.items() if a not in ("k", "B", "mode")})
 
 
+REF_FASTX = os.path.join(ROOT, "oracle", "_ref", "ref_fastx")
+
+
+def ingest_case_files():
+    """small FASTA/FASTQ files that exercise the vendored kseq's corner semantics (see tests/test_ingest.py)"""
+    rng = np.random.default_rng(11)
+    def rnd(n, pn=0.0, lower=0.0):
+        s = rng.choice(list("ACGT"), n)
+        s = np.where(rng.random(n) < pn, "N", s)
+        s = np.where(rng.random(n) < lower, np.char.lower(s), s)
+        return "".join(s)
+    seqs = [rnd(int(rng.integers(1, 200)), 0.03, 0.2) for _ in range(120)] + ["", "NNNN", "n", "ACGT ACGTA"]
+    fq = "".join("@r%d c\n%s\n+\n%s\n" % (i, s, ("@>+I" * (len(s) // 4 + 1))[:len(s)]) for i, s in enumerate(seqs))
+    fa = "junk before the first record\n" + "".join(">s%d\n%s\n%s" % (i, "\n".join(s[j:j + 40] for j in range(0, len(s), 40)), "\n" if i % 4 == 0 else "")
+                                                    for i, s in enumerate(seqs)) + ">last\nACGTTGCA"
+    mq = "".join("@m%d\n%s\n+m%d\n%s\nnoise without markers\n" % (i, "\n".join((s or "A")[j:j + 30] for j in range(0, len(s or "A"), 30)), i,
+                                                                      "\n".join(("I" * len(s or "A"))[j:j + 30] for j in range(0, len(s or "A"), 30)))
+                 for i, s in enumerate(seqs[:60]))
+    return {"fastq": fq.encode(), "fastq_crlf_gz": gzip.compress(fq.replace("\n", "\r\n").encode()), "fasta_multiline": fa.encode(), "fastq_multiline": mq.encode()}
+
+
+def save_ingest():
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, data in ingest_case_files().items():
+            f = os.path.join(d, name + (".gz" if name.endswith("_gz") else ".txt"))
+            open(f, "wb").write(data)
+            out = os.path.join(d, "out.txt")
+            subprocess.check_call([REF_FASTX, f, out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            res["file_" + name] = np.frombuffer(data, np.uint8)
+            res["parsed_" + name] = np.frombuffer(open(out, "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ingest_cases.npz"), **res)
+    print("ingest_cases", {a: len(b) for a, b in res.items()})
+
+
 if __name__ == "__main__":
+    save_ingest()
     ec = ecoli_reads()
     save("ecoli_k21_B40_graph", "graph", ec, 21, 40)          # BASELINE.json configs[0]
     save("ecoli_k21_B16_count", "count", ec, 21, 16)          # spades-kmercount defaults (kmercount.cpp:220)

@@ -15,6 +15,7 @@ from spades_b200.reads_io import read_fastx, read_seqfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+REF_FASTX = os.path.join(ROOT, "oracle", "_ref", "ref_fastx")
 ECOLI = "/root/reference/src/projects/spades/test_dataset"
 
 
@@ -147,3 +148,81 @@ def test_seqfile_format_against_the_unmodified_reference(tmp_path):
     # byte along with the data; BinRead restores the metadata afterwards (:808-815), so the padding is "don't care" on input
     assert _canonical_seqfile(prefix + "_ref.seq") == _canonical_seqfile(prefix + ".seq")
     assert read_seqfile(prefix + "_ref").strings() == reads            # and we read the reference's bytes
+
+
+def _ref_parse(path, tmp_path):
+    out = str(tmp_path / "ref_parsed.txt")
+    subprocess.check_call([REF_FASTX, str(path), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(out).read().split("\n")
+    recs = int([l for l in lines if l.startswith("#records")][0].split()[1])
+    return [l for l in lines if l and not l.startswith("#")], recs
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FASTX), reason="oracle/_ref/ref_fastx not built")
+def test_parser_against_the_unmodified_reference_parser(tmp_path):
+    """our ingest against io::FastaFastqGzParser (the reference's vendored kseq + zlib) + io::LongestValid, run live (oracle/_ref/ref_fastx)
+    on well-formed and on deliberately awkward files"""
+    rng = np.random.default_rng(7)
+    def rnd(n, pn=0.0, lower=0.0):
+        s = rng.choice(list("ACGT"), n)
+        s = np.where(rng.random(n) < pn, "N", s)
+        s = np.where(rng.random(n) < lower, np.char.lower(s), s)
+        return "".join(s)
+    files = []
+    # 1. plain FASTQ, qualities full of marker characters, some N / lowercase reads, an empty read
+    seqs = [rnd(int(rng.integers(1, 250)), 0.02, 0.2) for _ in range(400)] + ["", "NNNN", "n"]
+    p = tmp_path / "a.fq"
+    with open(p, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write("@r%d c\n%s\n+\n%s\n" % (i, s, ("@>+I" * (len(s) // 4 + 1))[:len(s)]))
+    files.append(p)
+    # 2. the same gzipped with CRLF line ends
+    gz = tmp_path / "a_crlf.fq.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(p, "rb").read().replace(b"\n", b"\r\n"))
+    files.append(gz)
+    # 3. multi-line FASTA with blank lines, blanks inside lines, leading junk, no final newline
+    fa = tmp_path / "b.fa"
+    with open(fa, "w") as f:
+        f.write("junk before the first record\n")
+        for i, s in enumerate(seqs[:200]):
+            f.write(">s%d\n" % i)
+            for j in range(0, len(s), 50):
+                f.write(s[j:j + 50] + ("  " if j % 100 == 0 else "") + "\n")
+            if i % 5 == 0:
+                f.write("\n")
+        f.write(">last\nACGTTGCA")
+    files.append(fa)
+    # 4. multi-line FASTQ (sequence and quality wrapped), junk between records
+    mq = tmp_path / "c.fq"
+    with open(mq, "w") as f:
+        for i, s in enumerate(seqs[:100]):
+            s = s or "A"
+            f.write("@m%d\n" % i + "\n".join(s[j:j + 30] for j in range(0, len(s), 30)) + "\n+m%d\n" % i)
+            q = "I" * len(s)
+            f.write("\n".join(q[j:j + 30] for j in range(0, len(s), 30)) + "\nnoise without markers\n")
+    files.append(mq)
+    # 5. the reference's own test data
+    if os.path.isdir(ECOLI):
+        files += [os.path.join(ECOLI, "ecoli_1K_1.fq.gz"), os.path.join(ECOLI, "ecoli_1K_2.fq.gz")]
+    for f in files:
+        want, recs = _ref_parse(f, tmp_path)
+        b = read_fastx(f)
+        assert b.strings() == want, str(f)
+        assert b.records == recs, str(f)
+
+
+def test_parser_against_reference_golden(tmp_path):
+    """tests/golden/ingest_cases.npz: awkward input files and what the unmodified reference's parser + LongestValid made of them
+    (generated by tests/golden/make_golden.py::save_ingest through oracle/_ref/ref_fastx)"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ingest_cases.npz"))
+    names = [k[5:] for k in z.files if k.startswith("file_")]
+    assert len(names) >= 4
+    for name in names:
+        f = tmp_path / (name + (".gz" if name.endswith("_gz") else ".txt"))
+        open(f, "wb").write(z["file_" + name].tobytes())
+        lines = z["parsed_" + name].tobytes().decode().split("\n")
+        want = [l for l in lines if l and not l.startswith("#")]
+        recs = int([l for l in lines if l.startswith("#records")][0].split()[1])
+        b = read_fastx(f)
+        assert b.strings() == want and b.records == recs, name
