@@ -19,6 +19,8 @@ step "parity, sector pairing in the refinement too"
 SGPU_PAIR=1 SGPU_PAIR_REFINE=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair_refine.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair_refine.log; tail -3 $O/s1_tests_pair_refine.log
 step "parity, three-level split (RMAX=7, PA_MAX=1280)"
 SGPU_RMAX=7 SGPU_PA_MAX=1280 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_rmax7.log 2>&1; echo "exit=$?" >> $O/s1_tests_rmax7.log; tail -3 $O/s1_tests_rmax7.log
+step "parity, 1024 local-sort bins"
+SGPU_BINBITS=10 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_bins10.log 2>&1; echo "exit=$?" >> $O/s1_tests_bins10.log; tail -3 $O/s1_tests_bins10.log
 step "sanitizer smoke, pairing"
 SGPU_PAIR=1 timeout 100 compute-sanitizer --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/s1_sanitizer_pair.log 2>&1; echo "exit=$?" >> $O/s1_sanitizer_pair.log; tail -2 $O/s1_sanitizer_pair.log
 
@@ -31,6 +33,8 @@ for cfg in "0 4 11 4096" "1 4 11 4096" "1 2 11 4096" "1 3 11 4096" "0 4 9 4096" 
   SGPU_PAIR=$1 SGPU_A_SUB=$2 SGPU_RMAX=$3 SGPU_PA_MAX=$4 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $f 2> ${f%.json}.err
   ph $f
 done
+[ $(left) -gt 40 ] && { step "bench 20M binbits=10"; SGPU_BINBITS=10 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10.json 2> $O/s1_bench20_bins10.err; ph $O/s1_bench20_bins10.json; }
+[ $(left) -gt 40 ] && { step "bench 20M binbits=10 target=7/8"; SGPU_BINBITS=10 SGPU_TARGET_8THS=7 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10_t7.json 2> $O/s1_bench20_bins10_t7.err; ph $O/s1_bench20_bins10_t7.json; }
 # 100 M reads
 for cfg in "0 11 4096" "1 11 4096" "2 11 4096" "0 7 1280" "1 7 1280" "0 9 4096" "0 8 2560"; do
   set -- $cfg          # pair: 0 = off, 1 = level A, 2 = level A + refinement

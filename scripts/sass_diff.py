@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Compare the SASS of the kernels in spades_b200/csrc/build/count.o with a build of another commit (default: the last commit whose
 kernels ran on the GPU). Used when refactoring without GPU access: identical SASS of the default kernels == nothing to re-verify.
-    python scripts/sass_diff.py <commit> [substring-of-old-name=substring-of-new-name ...]"""
+    python scripts/sass_diff.py <commit> ['regex=>replacement' ...]      (renames applied to the old mangled names, e.g. new template arguments)
+    python scripts/sass_diff.py 8f22764 'local_sort3_kILi(\\d)EEE=>local_sort3_kILi\\1ELi11EEE' 'levelA_scatter_roll_kILi(\\d)ELb(\\d)EEE=>levelA_scatter_roll_kILi\\1ELb\\2ELb0EEE' \\
+                                        'refine_kILi(\\d)ELb(\\d)EEE=>refine_kILi\\1ELb\\2ELb0EEE'"""
 import re
 import subprocess
 import sys
@@ -24,7 +26,7 @@ def sass(obj):
 
 def main():
     commit = sys.argv[1]
-    renames = dict(a.split("=") for a in sys.argv[2:])
+    renames = [a.split("=>") for a in sys.argv[2:]]
     with tempfile.TemporaryDirectory() as d:
         subprocess.check_call("git archive %s spades_b200/csrc include | tar -x -C %s" % (commit, d), shell=True)
         subprocess.check_call(["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-c", "count.cu",
@@ -34,14 +36,14 @@ def main():
     bad = 0
     for name, body in sorted(old.items()):
         want = name
-        for a, b in renames.items():
-            want = want.replace(a, b)
+        for a, b in renames:
+            want = re.sub(a, b, want)
         if want not in new:
             print("gone     ", name); continue
         same = body == new[want]
         bad += not same
         print("%-9s %s" % ("identical" if same else "DIFFERENT", name))
-    print("new kernels:", len(set(new) - set(old) - set(renames.values())))
+    print("kernels in the old build: %d, in the new build: %d" % (len(old), len(new)))
     return 1 if bad else 0
 
 

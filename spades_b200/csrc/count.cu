@@ -1030,8 +1030,8 @@ __device__ __forceinline__ uint64_t *lsd_sort_range(uint64_t *A, uint64_t *Bf, u
 // copies of a few keys (a genomic (k+1)-mer is seen ~coverage times) plus error singletons. Two earlier generations (a full LSD
 // radix sort per segment; one counting pass into 2^11 bins with one thread collapsing each bin) were replaced by the kernel
 // below; the LSD passes above survive as its exact fallback.
-static const int kBinBits = 11;
-static const int kBins = 1 << kBinBits;
+static const int kBinBitsDefault = 11;       // SGPU_BINBITS = 9 | 10 | 11: fewer bins = less per-segment bookkeeping (init + two scans over the
+                                            // bins), more keys sharing a bin (more residual work, earlier fallback)
 
 // ncu on the one-thread-per-bin generation showed 8.5 active lanes per instruction and barrier stalls on top: one thread chewing
 // through the ~coverage copies of a genomic k-mer held up its whole CTA. Here every bin elects a representative (the
@@ -1042,12 +1042,14 @@ static const int kBins = 1 << kBinBits;
 // uses the segment's region in the partner buffer as scratch.
 static const int kResCap = 512;
 
-template <int NW>
+template <int NW, int kBinBits>
 __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
                                                           uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
                                                           unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
     constexpr int CAP = SortCfg<NW>::CAP;
+    constexpr int kBins = 1 << kBinBits;
     constexpr int BPT = kBins / kSThreads;
+    static_assert(3 * kBins >= SortCfg<NW>::CAP + 1 && 3 * kBins >= kSWarps * 256, "rep/repcnt/rhist double as scratch of the LSD fallback");
     constexpr int IPT = CAP / kSThreads;                  // records per thread
     extern __shared__ uint64_t sm64[];
     uint64_t *A = sm64;                                   // CAP*NW   the segment
@@ -1410,15 +1412,20 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
         SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
         tm.start();
         {
-            size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * kBins * sizeof(uint32_t) +
-                          ((size_t)2 * kBins + 2 + kResCap) * sizeof(uint16_t) + 16;
-            SG_CUDA(cudaFuncSetAttribute(local_sort3_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int occ = 1;
-            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, local_sort3_k<NW>, kSThreads, smem));
-            if (occ < 1) occ = 1;
-            int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
-            if (grid < 1) grid = 1;
-            local_sort3_k<NW><<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+            auto launch_sort = [&](auto kernel, int bins) {
+                size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * bins * sizeof(uint32_t) +
+                              ((size_t)2 * bins + 2 + kResCap) * sizeof(uint16_t) + 16;
+                SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ = 1;
+                SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSThreads, smem));
+                if (occ < 1) occ = 1;
+                int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
+                if (grid < 1) grid = 1;
+                kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+            };
+            const int binbits = getenv("SGPU_BINBITS") ? atoi(getenv("SGPU_BINBITS")) : kBinBitsDefault;
+            if (binbits == 10) launch_sort(local_sort3_k<NW, 10>, 1 << 10);
+            else launch_sort(local_sort3_k<NW, 11>, 1 << 11);
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
         }
