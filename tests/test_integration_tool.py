@@ -17,6 +17,7 @@ import golden_util as G
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOOL = os.path.join(ROOT, "integration", "_build", "spades_kmercount_gpu")
+GBUILDER = os.path.join(ROOT, "integration", "_build", "spades_gbuilder_gpu")
 needs_tool = pytest.mark.skipif(not os.path.exists(TOOL), reason="integration/_build/spades_kmercount_gpu not built (make -C integration; needs /root/reference)")
 
 
@@ -71,3 +72,40 @@ def test_tool_takes_gzipped_fastq_like_the_original():
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         fk = np.fromfile(os.path.join(w, "final_kmers"), np.uint8)
     assert np.array_equal(fk, g["final_kmers"])
+
+
+@pytest.mark.skipif(not os.path.exists(GBUILDER), reason="integration/_build/spades_gbuilder_gpu not built")
+def test_gbuilder_tool_refuses_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "r.txt")
+        open(rf, "w").write("ACGTACGTACGTAGCTAGCTAGCTAGCATCGATCGATCAGCTAGC\n")
+        p = subprocess.run([GBUILDER, rf, "21", os.path.join(d, "w")], capture_output=True, text=True)
+    assert p.returncode == 3 and "no CPU fallback" in p.stderr
+
+
+# written after the last GPU session of round 1: runs for the first time in round 2 (scripts/gpu_round2_sweep.sh sets the variable),
+# afterwards the guard goes away
+first_run_pending = pytest.mark.skipif(os.environ.get("SGPU_RUN_NEW") is None, reason="first GPU run pending (set SGPU_RUN_NEW=1)")
+
+
+@pytest.mark.skipif(not os.path.exists(GBUILDER), reason="integration/_build/spades_gbuilder_gpu not built")
+@first_run_pending
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,early_tc", [("ecoli_k21_B40_graph", 0), ("loops_k21_B10_graph", 0), ("ecoli_k55_B16_graph", 0), ("syn_k21_B10_tcgraph", 79)])
+def test_reference_graph_construction_over_gpu_arrays(name, early_tc):
+    """spades-gbuilder's flow with the hot path on the GPU and the UNMODIFIED reference doing everything downstream on the GPU's
+    arrays (its own KMerIndexBuilder over the GPU-written buckets, UnbranchingPathExtractor over the GPU's masks, graph
+    constructor, coverage filler, GFA writer): the tool exits 0 iff the reference reproduces the GPU's unitigs and GFA, and the GFA
+    must also be the golden one (the reference end to end on the CPU)."""
+    g = G.load(name)
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        open(rf, "w").write("\n".join(g["reads"]) + "\n")
+        w = os.path.join(d, "w")
+        p = subprocess.run([GBUILDER, rf, str(g["k"]), w, str(g["B"]), str(early_tc)], capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+        gfa = open(os.path.join(w, "graph.gfa")).read()
+    assert gfa == g["graph_gfa"].tobytes().decode()
