@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libspades_b200.so")
 SYMBOLS = [
     "sgpu_create", "sgpu_destroy", "sgpu_last_error", "sgpu_get_times",
     "sgpu_reads_clear", "sgpu_reads_append_packed", "sgpu_reads_upload", "sgpu_reads_adopt_device",
-    "sgpu_fastx_parse", "sgpu_seqfile_parse", "sgpu_read_batch_write_seqfile", "sgpu_read_batch_num_reads", "sgpu_read_batch_num_words",
+    "sgpu_fastx_parse", "sgpu_fastx_parse_threads", "sgpu_seqfile_parse", "sgpu_read_batch_write_seqfile", "sgpu_read_batch_num_reads", "sgpu_read_batch_num_words",
     "sgpu_read_batch_words", "sgpu_read_batch_offs", "sgpu_read_batch_lens", "sgpu_read_batch_stats", "sgpu_read_batch_error", "sgpu_read_batch_free",
     "sgpu_reads_append_batch",
     "sgpu_count", "sgpu_kmers_from_kpomers",
@@ -59,6 +59,7 @@ def load():
     L.sgpu_reads_upload.restype = i32; L.sgpu_reads_upload.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_reads_adopt_device.restype = i32; L.sgpu_reads_adopt_device.argtypes = [vp, vp, u64, vp, vp, i64]
     L.sgpu_fastx_parse.restype = i32; L.sgpu_fastx_parse.argtypes = [C.c_char_p, i32, pp]
+    L.sgpu_fastx_parse_threads.restype = i32; L.sgpu_fastx_parse_threads.argtypes = [C.c_char_p, i32, i32, pp]
     L.sgpu_seqfile_parse.restype = i32; L.sgpu_seqfile_parse.argtypes = [C.c_char_p, pp]
     L.sgpu_read_batch_write_seqfile.restype = i32; L.sgpu_read_batch_write_seqfile.argtypes = [vp, C.c_char_p]
     L.sgpu_read_batch_num_reads.restype = i64; L.sgpu_read_batch_num_reads.argtypes = [vp]

@@ -12,11 +12,16 @@
 //                                  then per read {u64 size, ceil(size/32) u64 words, u16 left_offset, u16 right_offset, u64 tag}
 //                                  (Sequence::BinWrite sequence.hpp:817-830, SingleReadSeq::BinWrite single_read.hpp:325-338);
 //                                  <prefix>.off = u64 file offset of every 100th read (BinaryWriter::CHUNK, binary_converter.cpp:96-110)
+#include <fcntl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/spades_b200.h"
@@ -135,37 +140,63 @@ void add_read(sgpu_read_batch *b, const std::string &seq, bool longest_valid) {
 //    empty lines are skipped;
 //  * quality ('+'): whole lines are appended until the quality is at least as long as the sequence (at least one line is read),
 //    and any other length is an error (:206-209).
-bool parse_fastx(const char *path, bool longest_valid, sgpu_read_batch *b) {
-    GzReader in;
-    if (!in.open(path)) { b->err = std::string("cannot open ") + path; return false; }
+// Line sources. Both give lines without their '\n', and the offset at which the line starts in the (uncompressed) input.
+struct MemLines {
+    const char *d; size_t pos, end;
+    bool getline(const char *&p, size_t &n, size_t &at) {
+        if (pos >= end) return false;
+        const char *nl = (const char *)memchr(d + pos, '\n', end - pos);
+        const size_t len = nl ? (size_t)(nl - (d + pos)) : end - pos;
+        p = d + pos; n = len; at = pos;
+        pos += len + (nl ? 1 : 0);
+        return true;
+    }
+};
+struct GzLines {
+    GzReader r;
+    size_t consumed = 0;
+    bool getline(const char *&p, size_t &n, size_t &at) {
+        if (!r.getline(p, n)) return false;
+        at = consumed; consumed += n + 1;
+        return true;
+    }
+};
+
+// The state machine over a line source. Starts either looking for a marker (scan) or ON a header line whose first character
+// is the marker (`pending` = a line already fetched by the caller is not supported: a worker that starts on a header simply
+// positions the source at the start of that line and passes scan = true -- the first marker found is then that line's first
+// character). Stops before starting a record whose header line begins at or after `stop_at`; *next = where that line begins
+// (or the input size at end of input), *next_is_scan = whether the following record would have been looked for by scanning.
+template <class Lines>
+bool parse_lines(Lines &in, bool longest_valid, size_t stop_at, sgpu_read_batch *b, size_t *next, size_t input_size) {
     const char *p;
-    size_t n;
+    size_t n, at = 0;
     std::string seq;
     bool scan = true;            // true: look for '>' / '@' anywhere; false: the line in (p, n) is the header
-    bool have = false;
     for (;;) {
         if (scan) {
-            have = false;
-            while (in.getline(p, n)) {
+            bool have = false;
+            while (in.getline(p, n, at)) {
                 if (memchr(p, '>', n) || memchr(p, '@', n)) { have = true; break; }
             }
-            if (!have) break;
+            if (!have) { *next = input_size; return true; }
         }
+        if (at >= stop_at) { *next = at; return true; }
         // (p, n) is a header line: name / comment are not needed
         seq.clear();
         int stop = -1;           // the character that ended the sequence, -1 = end of input
-        while (in.getline(p, n)) {
+        while (in.getline(p, n, at)) {
             if (n == 0) continue;
             if (p[0] == '>' || p[0] == '@' || p[0] == '+') { stop = p[0]; break; }
             seq.append(p, n);
             if (seq.size() > 1 && seq.back() == '\r') seq.pop_back();
         }
         add_read(b, seq, longest_valid);
-        if (stop < 0) break;
+        if (stop < 0) { *next = input_size; return true; }
         if (stop == '+') {
             size_t q = 0;
             do {
-                if (!in.getline(p, n)) { b->err = "truncated quality string"; return false; }
+                if (!in.getline(p, n, at)) { b->err = "truncated quality string"; return false; }
                 q += n;
                 if (q > 1 && n && p[n - 1] == '\r') --q;
             } while (q < seq.size());
@@ -175,7 +206,103 @@ bool parse_fastx(const char *path, bool longest_valid, sgpu_read_batch *b) {
             scan = false;
         }
     }
+}
+
+void append_batch(sgpu_read_batch *dst, const sgpu_read_batch &src) {
+    const uint64_t w0 = dst->words.size();
+    dst->words.insert(dst->words.end(), src.words.begin(), src.words.end());
+    dst->lens.insert(dst->lens.end(), src.lens.begin(), src.lens.end());
+    dst->offs.reserve(dst->offs.size() + src.offs.size());
+    for (uint64_t o : src.offs) dst->offs.push_back(o + w0);
+    dst->records += src.records; dst->trimmed += src.trimmed; dst->dropped += src.dropped;
+}
+
+// A plain (uncompressed) file in parallel, exactly: the file is cut at guessed record starts (a line that begins with '@' and
+// looks like the first line of a four-line FASTQ record, or any line that begins with '>'), every worker runs the SAME state
+// machine from its cut to the next one, and the pieces are accepted only if every worker stopped exactly on the next worker's
+// cut -- i.e. if the sequential parser would have been in "find the next record" position there. Anything else (multi-line
+// FASTQ whose cuts were guessed wrong, markers in the middle of junk lines, errors) falls back to the sequential parse.
+bool parse_plain_parallel(const char *d, size_t size, bool longest_valid, int nthreads, sgpu_read_batch *b) {
+    const size_t chunk = size / (size_t)nthreads;
+    std::vector<size_t> cut((size_t)nthreads + 1, size);
+    cut[0] = 0;
+    for (int i = 1; i < nthreads; ++i) {
+        // first line start at or after i*chunk ...
+        size_t pos = (size_t)i * chunk;
+        const char *nl = (const char *)memchr(d + pos, '\n', size - pos);
+        pos = nl ? (size_t)(nl - d) + 1 : size;
+        // ... that begins a record
+        size_t found = size;
+        for (int tries = 0; pos < size && tries < 64; ++tries) {
+            MemLines ml{d, pos, size};
+            const char *p[5]; size_t n[5], at[5];
+            int got = 0;
+            while (got < 5 && ml.getline(p[got], n[got], at[got])) ++got;
+            if (got == 0) break;
+            if (n[0] && p[0][0] == '>') { found = pos; break; }
+            if (got >= 4 && n[0] && p[0][0] == '@' && n[2] && p[2][0] == '+' && n[1] == n[3] && n[1] && p[1][0] != '@' && p[1][0] != '>' && p[1][0] != '+' &&
+                (got == 4 || (n[4] && p[4][0] == '@'))) { found = pos; break; }
+            pos = got >= 2 ? at[1] : size;              // next line
+        }
+        cut[(size_t)i] = found;
+    }
+    for (int i = 1; i <= nthreads; ++i) if (cut[(size_t)i] < cut[(size_t)i - 1]) cut[(size_t)i] = cut[(size_t)i - 1];
+    std::vector<sgpu_read_batch> part((size_t)nthreads);
+    std::vector<size_t> next((size_t)nthreads, 0);
+    std::vector<char> ok((size_t)nthreads, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < nthreads; ++i)
+        th.emplace_back([&, i]() {
+            if (cut[(size_t)i] >= cut[(size_t)i + 1] && i > 0) { next[(size_t)i] = cut[(size_t)i]; ok[(size_t)i] = 1; return; }     // empty piece
+            MemLines ml{d, cut[(size_t)i], size};
+            ok[(size_t)i] = parse_lines(ml, longest_valid, cut[(size_t)i + 1], &part[(size_t)i], &next[(size_t)i], size) ? 1 : 0;
+        });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < nthreads; ++i) {
+        if (!ok[(size_t)i]) return false;
+        if (next[(size_t)i] != cut[(size_t)i + 1]) return false;          // the sequential parser would not have been at the next cut
+    }
+    for (int i = 0; i < nthreads; ++i) append_batch(b, part[(size_t)i]);
     return true;
+}
+
+bool parse_fastx(const char *path, bool longest_valid, int nthreads, sgpu_read_batch *b) {
+    // gzip (or unreadable through mmap): one sequential stream
+    bool gz = false;
+    size_t size = 0;
+    {
+        FILE *f = fopen(path, "rb");
+        if (!f) { b->err = std::string("cannot open ") + path; return false; }
+        unsigned char m[2] = {0, 0};
+        const size_t got = fread(m, 1, 2, f);
+        gz = got == 2 && m[0] == 0x1f && m[1] == 0x8b;
+        fseek(f, 0, SEEK_END);
+        size = (size_t)ftell(f);
+        fclose(f);
+    }
+    if (nthreads <= 0) {
+        nthreads = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("SGPU_INGEST_THREADS")) nthreads = atoi(e);
+        if (nthreads > 64) nthreads = 64;
+    }
+    if (!gz && nthreads > 1 && size >= ((size_t)nthreads << 16)) {
+        const int fd = open(path, O_RDONLY);
+        if (fd >= 0) {
+            void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            close(fd);
+            if (m != MAP_FAILED) {
+                sgpu_read_batch tmp;
+                const bool ok = parse_plain_parallel((const char *)m, size, longest_valid, nthreads, &tmp);
+                munmap(m, size);
+                if (ok) { append_batch(b, tmp); return true; }
+                // fall through: the exact sequential parse decides (and reports errors)
+            }
+        }
+    }
+    GzLines in;
+    if (!in.r.open(path)) { b->err = std::string("cannot open ") + path; return false; }
+    size_t next = 0;
+    return parse_lines(in, longest_valid, (size_t)-1, b, &next, (size_t)-1);
 }
 
 bool parse_seqfile(const char *prefix, sgpu_read_batch *b) {
@@ -209,12 +336,13 @@ bool parse_seqfile(const char *prefix, sgpu_read_batch *b) {
 
 extern "C" {
 
-int sgpu_fastx_parse(const char *path, int longest_valid, sgpu_read_batch **out) {
+int sgpu_fastx_parse_threads(const char *path, int longest_valid, int nthreads, sgpu_read_batch **out) {
     if (!path || !out) return SGPU_EINVAL;
     sgpu_read_batch *b = new sgpu_read_batch();
     *out = b;                                   // returned even on failure so that sgpu_read_batch_error() can be read
-    return parse_fastx(path, longest_valid != 0, b) ? SGPU_OK : SGPU_EIO;
+    return parse_fastx(path, longest_valid != 0, nthreads, b) ? SGPU_OK : SGPU_EIO;
 }
+int sgpu_fastx_parse(const char *path, int longest_valid, sgpu_read_batch **out) { return sgpu_fastx_parse_threads(path, longest_valid, 0, out); }
 int sgpu_seqfile_parse(const char *prefix, sgpu_read_batch **out) {
     if (!prefix || !out) return SGPU_EINVAL;
     sgpu_read_batch *b = new sgpu_read_batch();

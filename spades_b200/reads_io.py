@@ -65,8 +65,10 @@ def _parse(fn, *args):
     return ReadBatch(h)
 
 
-def read_fastx(path, longest_valid=True) -> ReadBatch:
-    return _parse(_lib.load().sgpu_fastx_parse, str(path).encode(), 1 if longest_valid else 0)
+def read_fastx(path, longest_valid=True, threads=0) -> ReadBatch:
+    """threads: 0 = all hardware threads for uncompressed files (exact: pieces are only accepted where the sequential parser
+    provably stands at the same place), 1 = sequential"""
+    return _parse(_lib.load().sgpu_fastx_parse_threads, str(path).encode(), 1 if longest_valid else 0, int(threads))
 
 
 def read_seqfile(prefix) -> ReadBatch:

@@ -226,3 +226,37 @@ def test_parser_against_reference_golden(tmp_path):
         recs = int([l for l in lines if l.startswith("#records")][0].split()[1])
         b = read_fastx(f)
         assert b.strings() == want and b.records == recs, name
+
+
+def test_parallel_parse_is_exact(tmp_path):
+    """uncompressed files are parsed in parallel pieces that are only accepted where the sequential parser provably stands at the
+    same place: the result must be identical to the sequential parse on four-line FASTQ (qualities full of marker characters),
+    wrapped FASTQ, multi-line FASTA and on files with junk between the records"""
+    rng = np.random.default_rng(21)
+    def rnd(n, pn=0.01):
+        s = rng.choice(list("ACGT"), n)
+        return "".join(np.where(rng.random(n) < pn, "N", s))
+    seqs = [rnd(int(rng.integers(50, 251))) for _ in range(12000)]
+    quals = ["".join(rng.choice(list("@+>I#5"), len(s))) for s in seqs]
+    files = {}
+    files["four_line.fq"] = "".join("@r%d\n%s\n+\n%s\n" % (i, s, q) for i, (s, q) in enumerate(zip(seqs, quals)))
+    files["wrapped.fq"] = "".join("@w%d\n%s\n+\n%s\n" % (i, "\n".join(s[j:j + 60] for j in range(0, len(s), 60)), "\n".join(q[j:j + 60] for j in range(0, len(q), 60)))
+                                  for i, (s, q) in enumerate(zip(seqs, quals)))
+    files["multi.fa"] = "".join(">s%d desc\n%s\n" % (i, "\n".join(s[j:j + 70] for j in range(0, len(s), 70))) for i, s in enumerate(seqs))
+    files["junk.fq"] = "".join("@j%d\n%s\n+\n%s\n%s" % (i, s, q, "noise, no markers\n" if i % 3 == 0 else "") for i, (s, q) in enumerate(zip(seqs, quals)))
+    for name, text in files.items():
+        p = tmp_path / name
+        open(p, "w").write(text)
+        assert os.path.getsize(p) > (8 << 16)
+        one = read_fastx(p, threads=1)
+        many = read_fastx(p, threads=8)
+        assert one.records == len(seqs), name
+        assert many.records == one.records and many.trimmed == one.trimmed and many.dropped == one.dropped, name
+        assert np.array_equal(many.words, one.words) and np.array_equal(many.offs, one.offs) and np.array_equal(many.lens, one.lens), name
+        three = read_fastx(p, threads=3)
+        assert np.array_equal(three.words, one.words) and np.array_equal(three.lens, one.lens), name
+    # an error inside a piece is reported by the sequential parse
+    bad = tmp_path / "bad.fq"
+    open(bad, "w").write(files["four_line.fq"] + "@last\nACGT\n+\nII\n")
+    with pytest.raises(IOError):
+        read_fastx(bad, threads=8)
