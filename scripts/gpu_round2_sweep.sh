@@ -21,6 +21,8 @@ step "parity, sector pairing in the refinement too"
 SGPU_PAIR=1 SGPU_PAIR_REFINE=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair_refine.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair_refine.log; tail -3 $O/s1_tests_pair_refine.log
 step "parity, three-level split (RMAX=7, PA_MAX=1280)"
 SGPU_RMAX=7 SGPU_PA_MAX=1280 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_rmax7.log 2>&1; echo "exit=$?" >> $O/s1_tests_rmax7.log; tail -3 $O/s1_tests_rmax7.log
+step "parity, staging for every source (k-mers from (k+1)-mers, all-windows mode)"
+SGPU_STAGE_ALL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_stage_all.log 2>&1; echo "exit=$?" >> $O/s1_tests_stage_all.log; tail -3 $O/s1_tests_stage_all.log
 step "parity, 1024 local-sort bins"
 SGPU_BINBITS=10 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_bins10.log 2>&1; echo "exit=$?" >> $O/s1_tests_bins10.log; tail -3 $O/s1_tests_bins10.log
 step "sanitizer smoke, pairing"

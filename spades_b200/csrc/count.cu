@@ -1628,7 +1628,10 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
         tr.mark("alloc X,Y");
         // CTA-major staging (see `Pieces`): level A writes every CTA's records into the CTA's own region of X, the first
         // refinement round gathers the partitions into Y
-        const bool stage = roll && use_ids && use_stage() && G <= kMaxPieces;
+        // (the first-generation kernels write wherever `base` points, so staging also works for the (k+1)-mer source and the
+        // all-windows mode: SGPU_STAGE_ALL=1, opt-in until it has run on the GPU)
+        const bool stage_all = getenv("SGPU_STAGE_ALL") && atoi(getenv("SGPU_STAGE_ALL")) != 0 && !getenv("SGPU_SCATTER2");
+        const bool stage = ((roll && use_ids) || stage_all) && use_stage() && G <= kMaxPieces;
         DArr<uint64_t> pbase;
         Pieces pcs;
         {
