@@ -1959,8 +1959,15 @@ static void dist_begin_nw(DistState *d) {
     SG_CUDA(cudaMemsetAsync(d->blk_counts.p, 0, d->blk_counts.bytes(), st));
     Timer tm(st);
     tm.start();
+    // SGPU_DIST_ROLL=1 (opt-in until it has run on 2 GPUs): the rolling kernels in their id-less form (canonical mode only)
+    const bool dist_roll = getenv("SGPU_DIST_ROLL") && atoi(getenv("SGPU_DIST_ROLL")) != 0 && !d->src.both;
     if (d->src.n) {
-        levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
+        if (dist_roll) {
+            SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
+            levelA_count_roll_k<NW><<<d->G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
+        } else {
+            levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
+        }
         ctx->launches++;
     }
     levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(d->blk_counts.p, PA_all, d->G, d->part_total_local.p);
@@ -1989,8 +1996,14 @@ static void dist_scatter_nw(DistState *d, int p) {
     tm.start();
     size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
     SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool dist_roll = getenv("SGPU_DIST_ROLL") && atoi(getenv("SGPU_DIST_ROLL")) != 0 && !d->src.both;
     if (d->src.n) {
-        levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u);
+        if (dist_roll) {
+            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            levelA_scatter_roll_k<NW, false, false><<<d->G, kRollThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u, PA, 0u);
+        } else {
+            levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u);
+        }
         ctx->launches++;
     }
     SG_CUDA(cudaGetLastError());
