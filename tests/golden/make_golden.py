@@ -141,3 +141,5 @@ if __name__ == "__main__":
     save("dense_k7_B4_tcgraph", "tcgraph", synthetic_reads(800, 60, 400, 0.03, seed=14), 7, 4, early_tc=10)
     for nm, (rd, _) in GTEST_CASES.items():
         save("gtest_" + nm + "_k5", "graph", rd, 5, 2)
+    # construction_test.cpp:97-105 (SimpleTestEarlyPairedInfo, k=3): its coverage table is the known answer in tests/test_oracle_golden.py
+    save("gtest_EarlyPairedInfo_k3", "graph", ["CCCAC", "CCACG", "ACCAC", "CCACA"], 3, 2)

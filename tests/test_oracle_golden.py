@@ -61,6 +61,24 @@ GTEST = {  # construction_test.cpp:30-64
 }
 
 
+def test_oracle_reference_gtest_coverage_table():
+    """construction_test.cpp:97-105 (SimpleTestEarlyPairedInfo, k = 3): edges and their coverage (every edge holds one 4-mer, so the
+    average coverage AssertCoverage checks, test_utils.cpp:144-151, is the raw count KC)."""
+    reads = ["CCCAC", "CCACG", "ACCAC", "CCACA"]       # both reads of both pairs; the strand of the mates does not matter
+    want = {"CCCA": 1, "ACCA": 1, "CCAC": 4, "CACG": 1, "CACA": 1}
+    r = O.full_graph(reads, 3, 2)
+    got = {}
+    for line in r["gfa"].splitlines():
+        f = line.split("\t")
+        if f[0] == "S":
+            kc = int([x for x in f if x.startswith("KC:i:")][0][5:])
+            got[f[2]] = kc
+    assert len(got) == len(want)
+    for seq, kc in got.items():
+        key = seq if seq in want else revcomp(seq)
+        assert want[key] == kc
+
+
 @pytest.mark.parametrize("name", sorted(GTEST))
 def test_oracle_reference_gtest_known_answers(name):
     reads, etalon = GTEST[name]
