@@ -102,6 +102,24 @@ def test_ragged_empty_and_short_reads():
     assert _compare(art, _oracle_art(reads, 21, 6), 6) == []
 
 
+@pytest.mark.skipif(__import__("os").environ.get("SGPU_RUN_NEW") is None, reason="first GPU run pending (set SGPU_RUN_NEW=1; scripts/gpu_round2_sweep.sh)")
+def test_long_reads_take_the_unstaged_path():
+    """reads of 400..6000 bp: a tile's packed reads no longer fit the shared-memory staging area (kStageWords), so the level-A
+    kernels read the words from global memory; mixed with short reads so that staged and unstaged tiles alternate"""
+    from gpu_util import gpu_graph_artifacts
+    rng = np.random.default_rng(8)
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, 9000))
+    reads = []
+    for _ in range(700):
+        L = int(rng.choice([150, 400, 1000, 2500, 6000]))
+        st = int(rng.integers(0, len(genome) - L + 1))
+        r = genome[st:st + L]
+        reads.append(r if rng.random() < 0.5 else revcomp(r))
+    for k, B in ((21, 5), (55, 3), (77, 2)):
+        art, _ = gpu_graph_artifacts(reads, k, B)
+        assert _compare(art, _oracle_art(reads, k, B), B) == []
+
+
 def test_no_kmers_at_all():
     from gpu_util import gpu_graph_artifacts
     reads = ["ACGT", "AC", "GGGTTT"]
