@@ -14,7 +14,7 @@ ph() { grep -o '"value": [0-9.]*' $1 | head -2 | tr '\n' ' '; grep -o '"phases_m
 step "gpu suite, defaults"
 timeout 200 python -m pytest tests -q -m gpu --timeout 150 > $O/s1_tests.log 2>&1; echo "exit=$?" >> $O/s1_tests.log; tail -3 $O/s1_tests.log
 step "first GPU run of the gbuilder-style adapter tool"
-SGPU_RUN_NEW=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k long_reads --timeout 180 > $O/s1_tests_long.log 2>&1; echo "exit=$?" >> $O/s1_tests_long.log; tail -3 $O/s1_tests_long.log
+SGPU_RUN_NEW=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "long_reads or EarlyPairedInfo" --timeout 180 > $O/s1_tests_long.log 2>&1; echo "exit=$?" >> $O/s1_tests_long.log; tail -3 $O/s1_tests_long.log
 SGPU_RUN_NEW=1 timeout 300 python -m pytest tests/test_integration_tool.py -q -m gpu --timeout 280 > $O/s1_tests_gbuilder.log 2>&1; echo "exit=$?" >> $O/s1_tests_gbuilder.log; tail -5 $O/s1_tests_gbuilder.log
 step "parity, sector pairing"
 SGPU_PAIR=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair.log; tail -3 $O/s1_tests_pair.log

@@ -39,8 +39,14 @@ def test_device_arithmetic():
     check_roll(ctx().h, 1)
 
 
+# fixtures added after the last GPU session of round 1 run for the first time in round 2 (scripts/gpu_round2_sweep.sh sets SGPU_RUN_NEW)
+_PENDING = {"gtest_EarlyPairedInfo_k3"}
+
+
 @pytest.mark.parametrize("name", G.names("graph"))
 def test_graph_matches_reference_golden(name):
+    if name in _PENDING and __import__("os").environ.get("SGPU_RUN_NEW") is None:
+        pytest.skip("first GPU run pending (set SGPU_RUN_NEW=1)")
     from gpu_util import gpu_graph_artifacts
     g = G.load(name)
     art, _ = gpu_graph_artifacts(g["reads"], g["k"], g["B"])
