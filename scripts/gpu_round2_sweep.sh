@@ -29,6 +29,8 @@ step "parity, staging for every source (k-mers from (k+1)-mers, all-windows mode
 SGPU_STAGE_ALL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_stage_all.log 2>&1; echo "exit=$?" >> $O/s1_tests_stage_all.log; tail -3 $O/s1_tests_stage_all.log
 step "parity, 1024 local-sort bins"
 SGPU_BINBITS=10 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_bins10.log 2>&1; echo "exit=$?" >> $O/s1_tests_bins10.log; tail -3 $O/s1_tests_bins10.log
+step "parity, 1024-record local-sort segments, 1024 bins"
+SGPU_SORT_CAP=1024 SGPU_BINBITS=10 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_cap1024.log 2>&1; echo "exit=$?" >> $O/s1_tests_cap1024.log; tail -3 $O/s1_tests_cap1024.log
 step "sanitizer smoke, pairing"
 SGPU_PAIR=1 timeout 100 compute-sanitizer --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/s1_sanitizer_pair.log 2>&1; echo "exit=$?" >> $O/s1_sanitizer_pair.log; tail -2 $O/s1_sanitizer_pair.log
 
@@ -43,6 +45,8 @@ for cfg in "0 4 11 4096" "1 4 11 4096" "1 2 11 4096" "1 3 11 4096" "0 4 9 4096" 
 done
 [ $(left) -gt 40 ] && { step "bench 20M binbits=10"; SGPU_BINBITS=10 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10.json 2> $O/s1_bench20_bins10.err; ph $O/s1_bench20_bins10.json; }
 [ $(left) -gt 40 ] && { step "bench 20M binbits=10 target=7/8"; SGPU_BINBITS=10 SGPU_TARGET_8THS=7 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10_t7.json 2> $O/s1_bench20_bins10_t7.err; ph $O/s1_bench20_bins10_t7.json; }
+[ $(left) -gt 40 ] && { step "bench 20M sort cap=1024 binbits=10"; SGPU_SORT_CAP=1024 SGPU_BINBITS=10 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_cap1024_bins10.json 2> $O/s1_bench20_cap1024_bins10.err; ph $O/s1_bench20_cap1024_bins10.json; }
+[ $(left) -gt 40 ] && { step "bench 20M sort cap=1024 binbits=11"; SGPU_SORT_CAP=1024 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_cap1024.json 2> $O/s1_bench20_cap1024.err; ph $O/s1_bench20_cap1024.json; }
 # 100 M reads
 for cfg in "0 11 4096" "1 11 4096" "2 11 4096" "0 7 1280" "1 7 1280" "0 9 4096" "0 8 2560"; do
   set -- $cfg          # pair: 0 = off, 1 = level A, 2 = level A + refinement

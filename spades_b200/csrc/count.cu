@@ -1042,14 +1042,14 @@ static const int kBinBitsDefault = 11;       // SGPU_BINBITS = 9 | 10 | 11: fewe
 // uses the segment's region in the partner buffer as scratch.
 static const int kResCap = 512;
 
-template <int NW, int kBinBits>
+template <int NW, int kBinBits, int CAP>
 __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict__ segs, uint64_t nsegs, int K, uint64_t *__restrict__ buf0,
                                                           uint64_t *__restrict__ buf1, uint32_t *__restrict__ ndist,
                                                           unsigned long long *__restrict__ work_counter, unsigned long long *__restrict__ stats) {
-    constexpr int CAP = SortCfg<NW>::CAP;
     constexpr int kBins = 1 << kBinBits;
     constexpr int BPT = kBins / kSThreads;
-    static_assert(3 * kBins >= SortCfg<NW>::CAP + 1 && 3 * kBins >= kSWarps * 256, "rep/repcnt/rhist double as scratch of the LSD fallback");
+    static_assert(3 * kBins >= CAP + 1 && 3 * kBins >= kSWarps * 256, "rep/repcnt/rhist double as scratch of the LSD fallback");
+    static_assert(CAP % kSThreads == 0 && CAP <= SortCfg<NW>::CAP, "segment capacity: a multiple of the CTA size, at most the default");
     constexpr int IPT = CAP / kSThreads;                  // records per thread
     extern __shared__ uint64_t sm64[];
     uint64_t *A = sm64;                                   // CAP*NW   the segment
@@ -1344,11 +1344,19 @@ struct Trace {
 
 static int ilog2_floor(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
 
+// local-sort segment capacity (records): SGPU_SORT_CAP=1024 halves the segments (one more refinement bit) for ~40 KB instead of
+// ~69 KB of shared memory per CTA -- more CTAs per SM to hide the per-segment load / barrier latency. Opt-in until measured.
+template <int NW>
+static int sort_cap() {
+    const char *e = getenv("SGPU_SORT_CAP");
+    return (e && atoi(e) == 1024 && SortCfg<NW>::CAP >= 1024) ? 1024 : SortCfg<NW>::CAP;
+}
+
 template <int NW>
 static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, const uint64_t *part_start_p, const uint64_t *part_total_p, uint32_t PA,
                       int rA_, uint32_t b_lo, int b_hi, int64_t first, bool want_counts, bool double_selfrc, unsigned long long *d_bsz_p, Chunk &ch_out,
                       Timer &tm, Trace &tr, const Pieces *pieces = nullptr) {
-    constexpr int CAP = SortCfg<NW>::CAP;
+    const int CAP = sort_cap<NW>();
     const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     cudaStream_t st = ctx->stream;
@@ -1424,8 +1432,14 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
                 kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
             };
             const int binbits = getenv("SGPU_BINBITS") ? atoi(getenv("SGPU_BINBITS")) : kBinBitsDefault;
-            if (binbits == 10) launch_sort(local_sort3_k<NW, 10>, 1 << 10);
-            else launch_sort(local_sort3_k<NW, 11>, 1 << 11);
+            constexpr int CAPD = SortCfg<NW>::CAP, CAPH = SortCfg<NW>::CAP >= 2048 ? 1024 : SortCfg<NW>::CAP;
+            if (CAP == CAPD) {
+                if (binbits == 10) launch_sort(local_sort3_k<NW, 10, CAPD>, 1 << 10);
+                else launch_sort(local_sort3_k<NW, 11, CAPD>, 1 << 11);
+            } else {
+                if (binbits == 10) launch_sort(local_sort3_k<NW, 10, CAPH>, 1 << 10);
+                else launch_sort(local_sort3_k<NW, 11, CAPH>, 1 << 11);
+            }
             ctx->launches++;
             SG_CUDA(cudaGetLastError());
         }
@@ -1473,7 +1487,7 @@ static bool use_stage() {
 template <int NW, class Src>
 static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
                              KSet *out, const std::vector<cudaEvent_t> *ready = nullptr, const std::vector<uint64_t> *src_records = nullptr) {
-    constexpr int CAP = SortCfg<NW>::CAP;
+    const int CAP = sort_cap<NW>();
     const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
     const int total_bits = 2 * K;
     // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
