@@ -1702,6 +1702,8 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
                     int nsub_auto = (int)(4.0 * (double)I / (double)std::max<uint64_t>(1, total_records) + 0.5);
                     nsub_auto = std::min(4, std::max(1, nsub_auto));
                     uint32_t nsub = use_ids ? (uint32_t)std::max(1, getenv("SGPU_A_SUB") ? atoi(getenv("SGPU_A_SUB")) : nsub_auto) : 1u;
+                    if (NW == 2 && use_ids && getenv("SGPU_PAIR") && atoi(getenv("SGPU_PAIR")) != 0 && !getenv("SGPU_A_SUB"))
+                        nsub = std::max(nsub, (PA + 1023u) / 1024u);          // the pairing variant holds mailboxes for <= 1024 partitions
                     if (nsub > PA) nsub = PA;
                     for (uint32_t sb = 0; sb < nsub; ++sb) {
                         const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
