@@ -21,8 +21,8 @@ SGPU_RUN_NEW=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -
 SGPU_RUN_NEW=1 timeout 300 python -m pytest tests/test_integration_tool.py -q -m gpu --timeout 280 > $O/s1_tests_gbuilder.log 2>&1; echo "exit=$?" >> $O/s1_tests_gbuilder.log; tail -5 $O/s1_tests_gbuilder.log
 step "parity, sector pairing"
 SGPU_PAIR=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair.log; tail -3 $O/s1_tests_pair.log
-step "parity, sector pairing in the refinement too"
-SGPU_PAIR=1 SGPU_PAIR_REFINE=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair_refine.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair_refine.log; tail -3 $O/s1_tests_pair_refine.log
+step "parity, sector pairing in the refinement too (+ prefetch)"
+SGPU_PAIR=1 SGPU_PAIR_REFINE=1 SGPU_PREFETCH=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_pair_refine.log 2>&1; echo "exit=$?" >> $O/s1_tests_pair_refine.log; tail -3 $O/s1_tests_pair_refine.log
 step "parity, three-level split (RMAX=7, PA_MAX=1280)"
 SGPU_RMAX=7 SGPU_PA_MAX=1280 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 150 > $O/s1_tests_rmax7.log 2>&1; echo "exit=$?" >> $O/s1_tests_rmax7.log; tail -3 $O/s1_tests_rmax7.log
 step "parity, staging for every source (k-mers from (k+1)-mers, all-windows mode)"
@@ -43,6 +43,7 @@ for cfg in "0 4 11 4096" "1 4 11 4096" "1 2 11 4096" "1 3 11 4096" "0 4 9 4096" 
   SGPU_PAIR=$1 SGPU_A_SUB=$2 SGPU_RMAX=$3 SGPU_PA_MAX=$4 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $f 2> ${f%.json}.err
   ph $f
 done
+[ $(left) -gt 40 ] && { step "bench 20M pair + L2 prefetch of the next id row"; SGPU_PAIR=1 SGPU_PREFETCH=1 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_pair_prefetch.json 2> $O/s1_bench20_pair_prefetch.err; ph $O/s1_bench20_pair_prefetch.json; }
 [ $(left) -gt 40 ] && { step "bench 20M binbits=10"; SGPU_BINBITS=10 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10.json 2> $O/s1_bench20_bins10.err; ph $O/s1_bench20_bins10.json; }
 [ $(left) -gt 40 ] && { step "bench 20M binbits=10 target=7/8"; SGPU_BINBITS=10 SGPU_TARGET_8THS=7 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_bins10_t7.json 2> $O/s1_bench20_bins10_t7.err; ph $O/s1_bench20_bins10_t7.json; }
 [ $(left) -gt 40 ] && { step "bench 20M sort cap=1024 binbits=10"; SGPU_SORT_CAP=1024 SGPU_BINBITS=10 timeout 100 python bench.py --reads 20000000 --steps 2 --warmup 1 --no-cpu-baseline > $O/s1_bench20_cap1024_bins10.json 2> $O/s1_bench20_cap1024_bins10.err; ph $O/s1_bench20_cap1024_bins10.json; }

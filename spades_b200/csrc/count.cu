@@ -511,7 +511,7 @@ __device__ __forceinline__ void emit_rec(uint64_t *out, const uint64_t *cur_base
 template <int NW, bool HAS_IDS, bool PAIR>
 __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
                                                                         const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
-                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo) {
+                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo, uint32_t flags) {
     extern __shared__ uint32_t sm_dyn[];
     uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
     PmBox *boxes = reinterpret_cast<PmBox *>(cur_base + p.PA);          // PAIR: PA * kPmDepth mailboxes (24 bytes each)
@@ -535,6 +535,12 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
         const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
         const bool staged = tile_stage(src, item0, nitems, ts);
         const ulonglong2 *row = HAS_IDS ? reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]) : nullptr;
+        if (PAIR && HAS_IDS && (flags & 1u) && t + 1 < t1) {
+            // experimental (pairing variant only, SGPU_PREFETCH=1): pull the next tile's id row into L2 while this tile is walked --
+            // ncu put half of this kernel's stall samples on the consumers of the id words
+            const char *a = reinterpret_cast<const char *>(ids + tile_off[t + 1]), *e = reinterpret_cast<const char *>(ids + tile_off[t + 2]);
+            for (const char *q = a + 128 * (size_t)threadIdx.x; q < e; q += 128 * (size_t)blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
         for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
             uint64_t idw[kRollC / 4];
             if (HAS_IDS) {
@@ -1714,9 +1720,10 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
                             const Src &src = srcs[si];
                             if (src.n == 0) continue;
                             if (use_ids && want_pair && pa_sub.PA <= 1024u)
-                                levelA_scatter_roll_k<NW, true, true><<<G, kRollThreads, pa_sub.PA * pair_bytes, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo);
-                            else if (use_ids) levelA_scatter_roll_k<NW, true, false><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo);
-                            else levelA_scatter_roll_k<NW, false, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u, PA, 0u);
+                                levelA_scatter_roll_k<NW, true, true><<<G, kRollThreads, pa_sub.PA * pair_bytes, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo,
+                                                                                                       (getenv("SGPU_PREFETCH") && atoi(getenv("SGPU_PREFETCH"))) ? 1u : 0u);
+                            else if (use_ids) levelA_scatter_roll_k<NW, true, false><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo, 0u);
+                            else levelA_scatter_roll_k<NW, false, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u, PA, 0u, 0u);
                             ctx->launches++;
                         }
                     }
@@ -2016,7 +2023,7 @@ static void dist_scatter_nw(DistState *d, int p) {
     if (d->src.n) {
         if (dist_roll) {
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            levelA_scatter_roll_k<NW, false, false><<<d->G, kRollThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u, PA, 0u);
+            levelA_scatter_roll_k<NW, false, false><<<d->G, kRollThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u, PA, 0u, 0u);
         } else {
             levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u);
         }
