@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Compare the SASS of the kernels in spades_b200/csrc/build/count.o with a build of another commit (default: the last commit whose
+r"""Compare the SASS of the kernels in spades_b200/csrc/build/count.o with a build of another commit (default: the last commit whose
 kernels ran on the GPU). Used when refactoring without GPU access: identical SASS of the default kernels == nothing to re-verify.
     python scripts/sass_diff.py <commit> ['regex=>replacement' ...]      (renames applied to the old mangled names, e.g. new template arguments)
     python scripts/sass_diff.py 8f22764 'local_sort3_kILi([12])EEE=>local_sort3_kILi\1ELi11ELi2048EEE' 'local_sort3_kILi([34])EEE=>local_sort3_kILi\1ELi11ELi1024EEE' \
         'levelA_scatter_roll_kILi(\d)ELb(\d)EEE(.*)PKtjjj=>levelA_scatter_roll_kILi\1ELb\2ELb0EEE\3PKtjjjj' 'refine_kILi(\d)ELb(\d)EEE=>refine_kILi\1ELb\2ELb0EEE'
+"""
 import re
 import subprocess
 import sys
