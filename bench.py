@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=int(os.environ.get("SGPU_BENCH_READS", 100_000_000)), help="reads per GPU")
     ap.add_argument("--buckets", type=int, default=0, help="0 = 10 x host threads, as the reference's graph path (construction.cpp:242)")
-    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads per reference-arm step; 0 = as many as fit the time budget (calibrated on a 1 M-read run)")
+    ap.add_argument("--check-reads", type=int, default=2_000_000, help="N>1: reads per rank of the distributed-vs-single-GPU checksum check (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -125,26 +126,94 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the UNMODIFIED reference (oracle/_ref/ref_probe "bench": KMerDiskCounter::Count + KMerIndexBuilder::BuildIndex on
+# in-memory read streams, all host threads, B = 10 x threads as construction.cpp:242) on a bounded prefix of the workload
+# ---------------------------------------------------------------------------------------------------------------------
+PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+FULL_READS = 100_000_000
+
+
+def _fs_of(path):
+    """file-system type the reference's bucket files land on (BASELINE.md 3.3 asks for tmpfs vs disk)"""
+    best, fstype = "", "unknown"
+    try:
+        for line in open("/proc/mounts"):
+            f = line.split()
+            if len(f) >= 3 and os.path.abspath(path).startswith(f[1]) and len(f[1]) > len(best):
+                best, fstype = f[1], f[2]
+    except Exception:
+        pass
+    return fstype
+
+
+def _host_facts(workdir):
+    ram = None
+    try:
+        import psutil
+        ram = round(psutil.virtual_memory().total / 2**30)
+    except Exception:
+        pass
+    return {"nproc": host_threads(), "ram_gib": ram, "workdir_fs": _fs_of(workdir)}
+
+
+def _probe_bench(n, B, T, reps, d):
+    """reps runs of the reference on the first n reads of the CPU sample generator; returns the per-run records"""
+    rf = os.path.join(d, "reads_%d.txt" % n)
+    if not os.path.exists(rf):
+        _cpu_sample(n).tofile(rf)
+    out = subprocess.run([PROBE, "bench", rf, str(K_GRAPH), str(B), str(T), os.path.join(d, "out_%d" % n), str(reps)], capture_output=True, text=True).stdout
+    os.remove(rf)
+    return [json.loads(l[6:]) for l in out.splitlines() if l.startswith("BENCH ")]
+
+
+def _cpu_sample(n):
+    """n reads of the workload's shape (150x coverage: genome of n bases, 1 % substitutions, random strand), as a text matrix"""
+    import numpy as np
+    from spades_b200.packing import synthetic_reads
+    out = np.empty((n, READ_LEN + 1), dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    step = 1_000_000
+    codes = synthetic_reads(n, READ_LEN, max(READ_LEN + 1, n), 0.01, seed=42, as_codes=True) if n <= 4 * step else None
+    if codes is not None:
+        out[:, :READ_LEN] = lut[codes]
+    else:                                      # large samples: piecewise (same genome, bounded temporaries)
+        rng = np.random.default_rng(42)
+        genome = rng.integers(0, 4, size=n, dtype=np.uint8)
+        for s0 in range(0, n, step):
+            c = min(step, n - s0)
+            starts = rng.integers(0, n - READ_LEN + 1, size=c)
+            r = genome[starts[:, None] + np.arange(READ_LEN)[None, :]]
+            st = rng.random(c) < 0.5
+            r[st] = (3 - r[st])[:, ::-1]
+            e = rng.random(r.shape) < 0.01
+            r[e] = (r[e] + rng.integers(1, 4, size=int(e.sum()), dtype=np.uint8)) & 3
+            out[s0:s0 + c, :READ_LEN] = lut[r]
+    out[:, READ_LEN] = 10
+    return out
+
+
 def run_reference(args, rank, world):
-    """UNMODIFIED reference (ref_probe 'bench') on the host cores. Rank 0 only."""
     if rank != 0:
         return
-    import numpy as np
-    probe = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
     T = host_threads()
     B = args.buckets or 10 * T
-    n = args.cpu_sample_reads
-    if not os.path.exists(probe):
+    if not os.path.exists(PROBE):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_probe was not built (needs /root/reference at build time)"}))
         return
-    reads = _cpu_sample(n)
+    reps = args.warmup + args.steps
     with tempfile.TemporaryDirectory() as d:
-        rf = os.path.join(d, "reads.txt")
-        reads.tofile(rf)
-        reps = args.warmup + args.steps
-        out = subprocess.run([probe, "bench", rf, str(K_GRAPH), str(B), str(T), os.path.join(d, "out"), str(reps)],
-                             capture_output=True, text=True).stdout
-    recs = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("BENCH ")]
+        facts = _host_facts(d)
+        # calibration on 1 M reads (also the first point of the size scaling), then the largest prefix whose `reps` runs fit ~4 minutes
+        cal = _probe_bench(1_000_000, B, T, 2, d)[-1]
+        cal_rate = cal["windows"] / cal["total_s"]
+        n = args.cpu_sample_reads
+        if n <= 0:
+            per_rep_s = max(2.0, min(30.0, 240.0 / reps))
+            n = int(cal_rate * per_rep_s / (READ_LEN - K + 1))
+            ram_cap = int((facts["ram_gib"] or 64) * 2**30 * 0.25 / (READ_LEN + 1 + 2 * (READ_LEN - K + 1) * 16 * 0.6))    # text + spilled runs
+            n = max(1_000_000, min(n, ram_cap, FULL_READS))
+            n -= n % 100_000
+        recs = _probe_bench(n, B, T, reps, d)
     timed = recs[args.warmup:]
     tot = sum(r["total_s"] for r in timed)
     windows = timed[0]["windows"]
@@ -152,48 +221,40 @@ def run_reference(args, rank, world):
     line = {"metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": val, "unit": "Mk-mers/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(timed), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "synthetic %d x 150 bp reads (bounded sample of the bench workload), k=55 (K=56 canonical (k+1)-mers), %d buckets" % (n, B),
-                       "k": K_GRAPH, "reads": n, "buckets": B},
+            "config": {"workload": "synthetic %d x 150 bp reads = the first %.1f %% of the 100 M-read bench workload's shape (150x coverage, 1%% substitutions), k=55 "
+                                   "(K=56 canonical (k+1)-mers), %d buckets; the largest prefix whose %d runs fit the few-minute budget" % (n, 100.0 * n / FULL_READS, B, reps),
+                       "k": K_GRAPH, "reads": n, "buckets": B, "sample_fraction": n / FULL_READS, "host": facts,
+                       "size_scaling": [{"reads": 1_000_000, "Mk-mers/s": cal_rate / 1e6}, {"reads": n, "Mk-mers/s": val}]},
             "cpu_baseline": {"value": val, "unit": "Mk-mers/s", "cores": T, "kind": "reference",
-                             "sample": "%d reads x 150 bp, in-memory read streams, count+index region of ref_probe (unmodified SPAdes KMerDiskCounter + KMerIndexBuilder)" % n},
+                             "sample": "%d reads x 150 bp, in-memory read streams, count+index region of ref_probe (unmodified SPAdes KMerDiskCounter + KMerIndexBuilder), "
+                                       "bucket files on %s" % (n, facts["workdir_fs"])},
             "e2e": {"value": val, "unit": "Mk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def _cpu_sample(n):
-    """first n reads of the bench generator (seed 42, rank 0), as a text matrix; generated on the CPU with the same
-    torch generator semantics is not needed -- the sample only has to have the workload's shape (same genome size ratio)."""
-    import numpy as np
-    from spades_b200.packing import synthetic_reads
-    codes = synthetic_reads(n, READ_LEN, max(READ_LEN + 1, n), 0.01, seed=42, as_codes=True)
-    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    out = np.empty((n, READ_LEN + 1), dtype=np.uint8)
-    out[:, :READ_LEN] = lut[codes]
-    out[:, READ_LEN] = 10
-    return out
-
-
 def cpu_baseline(args):
-    probe = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
     T = host_threads()
     B = args.buckets or 10 * T
-    n = args.cpu_sample_reads
-    if os.path.exists(probe):
-        reads = _cpu_sample(n)
+    if os.path.exists(PROBE):
         with tempfile.TemporaryDirectory() as d:
-            rf = os.path.join(d, "reads.txt")
-            reads.tofile(rf)
-            out = subprocess.run([probe, "bench", rf, str(K_GRAPH), str(B), str(T), os.path.join(d, "out"), "2"], capture_output=True, text=True).stdout
-        recs = [json.loads(l[6:]) for l in out.splitlines() if l.startswith("BENCH ")]
-        r = recs[-1]
-        return {"value": r["windows"] / r["total_s"] / 1e6, "unit": "Mk-mers/s", "cores": T, "kind": "reference",
-                "sample": "%d reads x 150 bp (2nd of 2 runs), unmodified SPAdes KMerDiskCounter::Count + KMerIndexBuilder::BuildIndex via oracle/_ref/ref_probe, %d buckets, in-memory streams" % (n, B)}
+            facts = _host_facts(d)
+            r1 = _probe_bench(1_000_000, B, T, 2, d)[-1]
+            rate1 = r1["windows"] / r1["total_s"]
+            # second, larger point (~10 s of CPU work) so that the size dependence of the CPU path is visible
+            n2 = int(min(10_000_000, max(2_000_000, rate1 * 10.0 / (READ_LEN - K + 1))))
+            n2 -= n2 % 100_000
+            r2 = _probe_bench(n2, B, T, 1, d)[-1]
+            rate2 = r2["windows"] / r2["total_s"]
+        return {"value": rate2 / 1e6, "unit": "Mk-mers/s", "cores": T, "kind": "reference",
+                "sample": "%d reads x 150 bp (%.0f %% of the workload), unmodified SPAdes KMerDiskCounter::Count + KMerIndexBuilder::BuildIndex via oracle/_ref/ref_probe, "
+                          "%d buckets, in-memory streams, bucket files on %s" % (n2, 100.0 * n2 / FULL_READS, B, facts["workdir_fs"]),
+                "sample_fraction": n2 / FULL_READS, "host": facts,
+                "size_scaling": [{"reads": 1_000_000, "Mk-mers/s": rate1 / 1e6}, {"reads": n2, "Mk-mers/s": rate2 / 1e6}]}
     # the plain-C oracle port (single thread)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
     import oracle as O
     from spades_b200.packing import pack_fixed, synthetic_reads
-    n = min(n, 100_000)
+    n = 100_000
     codes = synthetic_reads(n, READ_LEN, max(READ_LEN + 1, n), 0.01, seed=42, as_codes=True)
     words, offs, lens = pack_fixed(codes)
     t0 = time.time()
@@ -204,6 +265,52 @@ def cpu_baseline(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def multi_gpu_check(torch, dist, ctx, dcounter, B, n_check, rank, world, dev):
+    """N>1, before anything is timed: the distributed count of `world` shards against ONE GPU counting their union -- bucket sizes
+    equal, and the order-independent device checksums of (records, multiplicities) add / xor up. Raises on a mismatch."""
+    import numpy as np
+    from spades_b200.kmer_index import DeBruijnReadKMerSplitter, KMerDiskCounter
+    glen = max(READ_LEN + 1, n_check)
+    w, o, l, nwr = gen_reads_device(torch, n_check, glen, 1000 + rank, dev)
+    ctx.adopt_device_reads(w.data_ptr(), n_check * nwr, o.data_ptr(), l.data_ptr(), n_check)
+    st = dcounter.Count(B)
+    mine = st.checksum()
+    bsz = torch.from_numpy(st.bucket_sizes().copy()).to(dev)
+    st.free()
+    dist.all_reduce(bsz, op=dist.ReduceOp.SUM)
+    t = torch.tensor([mine[0], mine[1] - (1 << 64) if mine[1] >= (1 << 63) else mine[1], mine[3]], dtype=torch.int64, device=dev)   # sums wrap mod 2^64
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    xs = [None] * world
+    dist.all_gather_object(xs, mine[2])
+    ok, detail = True, None
+    if rank == 0:
+        x = 0
+        for v in xs:
+            x ^= v
+        got = [int(t[0].item()), int(t[1].item()) & ((1 << 64) - 1), x, int(t[2].item()) & ((1 << 64) - 1)]
+        parts = [gen_reads_device(torch, n_check, glen, 1000 + r, dev) for r in range(world)]
+        uw = torch.cat([p_[0][: n_check * nwr] for p_ in parts] + [torch.zeros(8, dtype=torch.int64, device=dev)])
+        uo = torch.cat([p_[1] + r * n_check * nwr for r, p_ in enumerate(parts)])
+        ul = torch.cat([p_[2] for p_ in parts])
+        del parts
+        ctx.adopt_device_reads(uw.data_ptr(), world * n_check * nwr, uo.data_ptr(), ul.data_ptr(), world * n_check)
+        ref = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(K)).Count(B)
+        want = ref.checksum()
+        want_bsz = ref.bucket_sizes()
+        ref.free()
+        torch.cuda.synchronize()
+        ok = got == want and np.array_equal(want_bsz, bsz.cpu().numpy())
+        detail = {"reads_per_rank": n_check, "distinct": want[0], "checksums_distributed": got, "checksums_single_gpu": want, "ok": ok}
+        del uw, uo, ul
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    del w, o, l
+    torch.cuda.empty_cache()
+    if int(flag.item()) != 1:
+        raise RuntimeError("multi-GPU self check FAILED: distributed count != single-GPU count of the union: %s" % (detail,))
+    return detail
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -229,14 +336,18 @@ def main():
     genome_len = max(READ_LEN + 1, n_reads)          # 150x coverage like config 3 (100 M reads over 100 Mbp)
     words, offs, lens, nwr = gen_reads_device(torch, n_reads, genome_len, 42 + rank, dev)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()                         # the generator's temporaries go back to the driver before the library reserves its arena
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
     nwords = n_reads * nwr
 
     dcounter = None
+    check = None
     if world > 1:
         from spades_b200.distributed import DistributedKMerCounter
         dcounter = DistributedKMerCounter(ctx, K)
+        if args.check_reads > 0:
+            check = multi_gpu_check(torch, dist, ctx, dcounter, B, min(args.check_reads, n_reads), rank, world, dev)
 
     def count(ctx_):
         # N>1: buckets are owned by ranks; one pull kernel per rank does the exchange + merge over NVLink peer memory
@@ -328,10 +439,11 @@ def main():
             pass
         peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         per_step = {k2: v / steps for k2, v in phases.items()}
-        # algorithmic bytes per step of each kernel family: I = instances, D = distinct
+        # algorithmic bytes per step of each kernel family: I = instances, D = distinct; SURVEY 8(d) counts the packed reads
+        # ONCE for the partition kernel however many bucket-group passes re-read them
         I, D = instances, distinct
         alg = {
-            "extract_scatter_ms": max(1, passes) * n_reads * nwr * 8 + I * W,   # packed reads in (once per bucket-group pass), records out
+            "extract_scatter_ms": n_reads * nwr * 8 + I * W,                  # packed reads in, records out
             "extract_count_ms": n_reads * nwr * 8,                           # packed reads in
             "refine_ms": 2 * I * W,                                          # one read + one write of every record
             "local_sort_ms": I * W + D * (W + 4),                            # records in, distinct records + counts out
@@ -342,6 +454,9 @@ def main():
         achieved = alg[dom] / (per_step[dom] / 1e3) / 1e9 if per_step[dom] > 0 else 0.0
         kernel_names = {"extract_scatter_ms": "levelA_scatter_roll_k (radix partition)", "extract_count_ms": "levelA_count_roll_k", "refine_ms": "refine_k (gather + MSD split)",
                         "local_sort_ms": "local_sort3_k", "compact_ms": "compact_k", "exchange_ms": "dist_pull_k (NVLink exchange+merge)"}
+        launches_per_step = {"extract_scatter_ms": int(max(1, passes)), "refine_ms": None, "local_sort_ms": int(max(1, passes)), "compact_ms": int(max(1, passes)),
+                             "extract_count_ms": 1, "exchange_ms": int(max(1, passes))}
+        whole_alg = n_reads * nwr * 8 + 2 * I * W + 2 * D * W + D * (4 + 5.8 / 8)      # extract + count + index
         line = {
             "metric": "Mk-mers/s (extract+count+index) k=55, 150 bp reads", "value": value, "unit": "Mk-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -350,33 +465,44 @@ def main():
                                    "%d XXH3 buckets, sort/unique/count + boomphf MPHF (extract+count+index)" % (n_reads, genome_len, B),
                        "k": K_GRAPH, "reads_per_gpu": n_reads, "buckets": B, "distinct_kpomers": int(distinct), "instances": int(instances), "passes": int(passes),
                        "parallelism": ("1 GPU" if world == 1 else "%d GPUs: reads sharded, buckets owned by ranks, one pull kernel per rank exchanges + merges the partitions over NVLink peer memory" % world),
-                       "l2": "inputs (%.1f GB) and intermediates larger than L2; no flush needed" % (nwords * 8 / 1e9), "peak_hbm_gb": peak / 1e9},
+                       "l2": "inputs (%.1f GB) and intermediates larger than L2; no flush needed" % (nwords * 8 / 1e9), "peak_hbm_gb": peak / 1e9,
+                       "multi_gpu_check": check},
             "clocks": sampler.result(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "Mk-mers/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "pinned host reads -> sgpu_reads_upload -> sgpu_count -> sgpu_mphf_build -> sgpu_mphf_serialize + bucket sizes to host; sorted (k+1)-mers stay in HBM for the graph phases"},
             "phases_ms_per_step": per_step,
             "roofline": {"bound": "hbm", "kernel": kernel_names[dom], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "peak_source": peak_src,
-                         # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r01_ncu_full_top_kernels_20M.csv,
-                         # 20 M-read workload, one launch): only quoted when the bench runs that workload
-                         # no ncu --set full capture of the current dominant kernel exists yet (the capture of the rolling partition kernel failed,
-                         # profiles/README): null rather than a number from an older kernel
-                         # per-launch DRAM bytes are only quoted for the workload ncu captured (4 M reads: profiles/r01c_ncu_full_staged_*.csv);
-                         # for other sizes the capture is reported next to it instead of being extrapolated
-                         "traffic": ({"extract_scatter_ms": 14.46e9, "refine_ms": 18.53e9}.get(dom) if (n_reads == 4_000_000 and world == 1) else None),
-                         "traffic_ncu": {"workload": "4 M reads (380 M records, 6.08 GB), one launch", "levelA_scatter_roll_k": {"dram_bytes": 14.46e9, "algorithmic_bytes": 6.24e9},
-                                         "refine_k<2,true>": {"dram_bytes": 18.53e9, "algorithmic_bytes": 12.16e9, "note": "the kernel reads its input twice (histogram, scatter): 18.2 GB expected"},
-                                         "source": "profiles/r01c_ncu_full_staged_scatter_and_gather_refine_4M.csv"},
-                         "launches_per_step": int(max(1, passes)) if dom == "extract_scatter_ms" else None,
+                         # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) come from the committed ncu --set full capture of the
+                         # SAME workload (profiles/, see NCU_TRAFFIC below); null when no capture of this kernel at this size exists
+                         "traffic": NCU_TRAFFIC.get((n_reads, dom)) if world == 1 else None,
+                         "launches_per_step": launches_per_step.get(dom),
                          "algorithmic_bytes_per_step": int(alg[dom]),
+                         "whole_step": {"algorithmic_bytes": int(whole_alg), "achieved": whole_alg / (ms / steps / 1e3) / 1e9, "frac": whole_alg / (ms / steps / 1e3) / 1e9 / peak_gbs},
                          "all": {kernel_names[k2]: (alg[k2] / (per_step[k2] / 1e3) / 1e9 if per_step[k2] > 0 else None) for k2 in alg}},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+# DRAM bytes per launch of a kernel family from `ncu --set full` captures committed under profiles/ : (reads per GPU, phase) -> bytes
+NCU_TRAFFIC = {}
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as e:      # the failing rank's reason must be the LAST thing it prints (torchrun's summary hides earlier output)
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        msg = "bench.py rank %s FAILED: %s: %s" % (os.environ.get("RANK", "0"), type(e).__name__, e)
+        sys.stdout.flush()
+        print(msg, file=sys.stderr, flush=True)
+        print(json.dumps({"error": msg}), flush=True)
+        os._exit(1)

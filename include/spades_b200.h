@@ -75,6 +75,8 @@ typedef struct sgpu_times {
 } sgpu_times;
 
 int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out);
+/* k-mer sets, indexes, graphs and distributed counts created from a context keep device memory of that context. Destroying the
+ * context while some are alive is safe in any order: the context is torn down when the last of them has been freed. */
 void sgpu_destroy(sgpu_ctx *ctx);
 const char *sgpu_last_error(const sgpu_ctx *ctx);
 int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out);
@@ -83,7 +85,9 @@ int sgpu_get_times(const sgpu_ctx *ctx, sgpu_times *out);
  * (N-free: apply LongestValid first, io/reads/longest_valid_wrapper.hpp:16-53). offs are relative to `words`. */
 int sgpu_reads_clear(sgpu_ctx *ctx);
 int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
-/* replace the read set with these HOST buffers, copied straight to the device (pinned buffers copy at full PCIe rate) */
+/* replace the read set with these HOST buffers, copied straight to the device (pinned buffers copy at full PCIe rate). The copies
+ * are enqueued on the context's stream and the call returns: the buffers must stay valid and unmodified until the next
+ * sgpu_count / sgpu_dist_begin on this context has returned (both synchronise the stream). */
 int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
 /* use a read set that already lives in device memory (not copied, must stay valid while the context uses it) */
 int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads);
@@ -122,6 +126,10 @@ int sgpu_kset_num_buckets(const sgpu_kset *s);
 int sgpu_kset_record_bytes(const sgpu_kset *s);                       /* KMerCounter::kmer_size(): 8*ceil(K/32) */
 int sgpu_kset_bucket_sizes(const sgpu_kset *s, int64_t *out);         /* num_buckets entries */
 /* records [first, first+n) of final_kmers order (KMerDiskStorage::merge, kmer_index_builder.hpp:190-203) to host memory */
+/* order-independent checksums computed on the device: out4 = { number of records, weighted sum of all record words, xor of
+ * the rotated record words, sum of the multiplicities } (mod 2^64). Disjoint bucket sets add / xor up, so the per-rank sets of a
+ * multi-GPU count can be checked against a single-GPU count of the union without moving records. */
+int sgpu_kset_checksum(const sgpu_kset *s, uint64_t *out4);
 int sgpu_kset_download_keys(const sgpu_kset *s, int64_t first, int64_t n, uint64_t *out);
 int sgpu_kset_download_counts(const sgpu_kset *s, int64_t first, int64_t n, uint32_t *out);   /* SGPU_CANONICAL sets only */
 /* writes <prefix>.<b> for every bucket in the reference's bucket file format (raw W-byte records) */
@@ -160,23 +168,23 @@ void sgpu_graph_free(sgpu_graph *g);
 
 /* ---- multi-GPU count (one process per GPU). Replaces hpcspades' shared-filesystem + MPI pattern
  * (projects/hpcspades/mpi/stages/construction_mpi.cpp:222-300, mpi/kmer_index/kmer_extension_index_builder_mpi.hpp:87,190):
- * buckets are owned by ranks; every rank partitions its own reads into a staging buffer, then sgpu_dist_exchange is ONE
- * kernel on the owner that pulls its pieces from all peers' staging buffers over NVLink peer memory (cudaIpc mappings)
- * and merges them partition by partition. The host language only moves the small tables between ranks
- * (torch.distributed / MPI all_gather) and provides the barriers:
- *   begin -> local_counts -> [all_gather counts] -> plan -> ipc_handle -> [all_gather handles] -> open_peers ->
+ * buckets are owned by ranks; every rank partitions its own reads into a staging buffer (same kernels as sgpu_count), then
+ * sgpu_dist_exchange is ONE kernel on the owner that pulls its pieces from all peers' staging buffers over NVLink peer memory
+ * (cudaIpc mappings of the peers' memory arenas, opened once per process) and merges them partition by partition. The host
+ * language only moves small tables between ranks (torch.distributed / MPI all_gather) and provides the barriers:
+ *   begin -> local_counts -> [all_gather counts] -> plan -> ipc_handle -> [all_gather descriptors] -> open_peers ->
  *   for each pass: scatter [barrier] exchange [barrier] sort   -> end (k-mer set holding this rank's buckets) */
 typedef struct sgpu_dist sgpu_dist;
 int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, int rank, sgpu_dist **out);
 int64_t sgpu_dist_num_partitions(const sgpu_dist *d);
 int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out);                 /* num_partitions host entries */
+/* budget_bytes: device bytes every rank can still allocate (the minimum over ranks); identical inputs give identical plans */
 int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_partitions, rank-major, host */, uint64_t budget_bytes,
                    int *npass, uint64_t *exchange_records);
-/* after plan: take over the buffers and peer mappings of a finished count (returns 1; then skip ipc_handle/open_peers), or 0 */
-int sgpu_dist_adopt(sgpu_dist *d, sgpu_dist *previous);
-#define SGPU_IPC_BYTES 72
-int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out /* SGPU_IPC_BYTES: cudaIpcMemHandle_t + offset of the staging buffer */);
-int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles /* world x SGPU_IPC_BYTES */);
+#define SGPU_IPC_BYTES 96
+/* this rank's descriptor: cudaIpcMemHandle_t of its memory arena + the offsets of its staging buffer and piece tables inside it */
+int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out /* SGPU_IPC_BYTES */);
+int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *descriptors /* world x SGPU_IPC_BYTES, rank-major */);
 int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* partition this rank's shard into its staging buffer */
 int sgpu_dist_exchange(sgpu_dist *d, int pass);                         /* fused NVLink exchange + merge: pulls the owned pieces from every peer */
 int sgpu_dist_sort(sgpu_dist *d, int pass);                             /* refinement + local sort + compaction of what arrived */

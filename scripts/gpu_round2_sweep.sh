@@ -11,9 +11,9 @@ step() { echo "== $1 (t=$(( $(date +%s) - T0 ))s)"; }
 export PYTHONUNBUFFERED=1
 ph() { grep -o '"value": [0-9.]*' $1 | head -2 | tr '\n' ' '; grep -o '"phases_ms_per_step": {[^}]*}' $1; }
 
-step "microbenchmark: streams per CTA x store width x layout"
-[ -x scripts/microbench/_build/scatter_bench ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/microbench/_build/scatter_bench scripts/microbench/scatter_bench.cu
-timeout 90 scripts/microbench/_build/scatter_bench -g 8 > $O/s1_microbench.txt 2>&1; tail -12 $O/s1_microbench.txt
+#step "microbenchmark: streams per CTA x store width x layout"
+#[ -x scripts/microbench/_build/scatter_bench ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/microbench/_build/scatter_bench scripts/microbench/scatter_bench.cu
+#timeout 90 scripts/microbench/_build/scatter_bench -g 8 > $O/s1_microbench.txt 2>&1; tail -12 $O/s1_microbench.txt
 step "gpu suite, defaults"
 timeout 200 python -m pytest tests -q -m gpu --timeout 150 > $O/s1_tests.log 2>&1; echo "exit=$?" >> $O/s1_tests.log; tail -3 $O/s1_tests.log
 step "first GPU run of the gbuilder-style adapter tool"

@@ -17,11 +17,11 @@ SYMBOLS = [
     "sgpu_reads_append_batch",
     "sgpu_count", "sgpu_kmers_from_kpomers",
     "sgpu_kset_size", "sgpu_kset_k", "sgpu_kset_num_buckets", "sgpu_kset_record_bytes", "sgpu_kset_bucket_sizes",
-    "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
+    "sgpu_kset_checksum", "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
     "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
     "sgpu_graph_build", "sgpu_graph_build_ex", "sgpu_graph_tip_clipper_stats", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
-    "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_adopt", "sgpu_dist_ipc_handle",
+    "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_ipc_handle",
     "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_exchange", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
     "sgpu_selftest",
 ]
@@ -78,6 +78,7 @@ def load():
     L.sgpu_kset_num_buckets.restype = i32; L.sgpu_kset_num_buckets.argtypes = [vp]
     L.sgpu_kset_record_bytes.restype = i32; L.sgpu_kset_record_bytes.argtypes = [vp]
     L.sgpu_kset_bucket_sizes.restype = i32; L.sgpu_kset_bucket_sizes.argtypes = [vp, vp]
+    L.sgpu_kset_checksum.restype = i32; L.sgpu_kset_checksum.argtypes = [vp, vp]
     L.sgpu_kset_download_keys.restype = i32; L.sgpu_kset_download_keys.argtypes = [vp, i64, i64, vp]
     L.sgpu_kset_download_counts.restype = i32; L.sgpu_kset_download_counts.argtypes = [vp, i64, i64, vp]
     L.sgpu_kset_write_buckets.restype = i32; L.sgpu_kset_write_buckets.argtypes = [vp, C.c_char_p]
@@ -104,7 +105,6 @@ def load():
     L.sgpu_dist_num_partitions.restype = i64; L.sgpu_dist_num_partitions.argtypes = [vp]
     L.sgpu_dist_local_counts.restype = i32; L.sgpu_dist_local_counts.argtypes = [vp, vp]
     L.sgpu_dist_plan.restype = i32; L.sgpu_dist_plan.argtypes = [vp, vp, u64, C.POINTER(i32), C.POINTER(u64)]
-    L.sgpu_dist_adopt.restype = i32; L.sgpu_dist_adopt.argtypes = [vp, vp]
     L.sgpu_dist_ipc_handle.restype = i32; L.sgpu_dist_ipc_handle.argtypes = [vp, vp]
     L.sgpu_dist_open_peers.restype = i32; L.sgpu_dist_open_peers.argtypes = [vp, vp]
     L.sgpu_dist_scatter.restype = i32; L.sgpu_dist_scatter.argtypes = [vp, i32]

@@ -10,6 +10,21 @@
 using namespace sg;
 
 struct sgpu_ctx { Ctx c; bool own_stream = true; };
+
+// Lifetime: k-mer sets, indexes, graphs and distributed counts keep blocks of their context's arena. sgpu_destroy() while any of
+// them is alive only marks the context; the last child to be freed then tears it down (no use-after-free whatever the order,
+// e.g. Python finalisers at interpreter exit).
+static void ctx_teardown(sgpu_ctx *ctx) {
+    cudaSetDevice(ctx->c.device);
+    ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
+    ctx->c.pool_trim();
+    if (ctx->c.stream && ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+static void child_add(Ctx *c) { c->live_children++; }
+static void child_release(Ctx *c) {
+    if (--c->live_children == 0 && c->destroy_pending) ctx_teardown(static_cast<sgpu_ctx *>(c->owner));
+}
 struct sgpu_kset { KSet *s; };
 struct sgpu_mphf { Mphf *m; };
 struct sgpu_graph { Graph *g; };
@@ -35,6 +50,7 @@ int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out) {
     if (dev < 0 || dev >= ndev) return SGPU_EINVAL;
     if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return SGPU_ENODEV; }
     sgpu_ctx *h = new sgpu_ctx();
+    h->c.owner = h;
     h->c.device = dev;
     h->c.hbm_budget = cfg ? (size_t)cfg->hbm_budget_bytes : 0;
     h->c.verbose = cfg ? cfg->verbose : 0;
@@ -48,14 +64,9 @@ int sgpu_create(const sgpu_config *cfg, sgpu_ctx **out) {
 }
 
 void sgpu_destroy(sgpu_ctx *ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->c.device);
-    ctx->c.r_words.release(); ctx->c.r_offs.release(); ctx->c.r_lens.release();
-    for (UploadChunk &u : ctx->c.up_chunks) if (u.ev) cudaEventDestroy(u.ev);
-    if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
-    ctx->c.pool_trim();
-    if (ctx->c.stream && ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
-    delete ctx;
+    if (!ctx || ctx->c.destroy_pending) return;
+    if (ctx->c.live_children > 0) { ctx->c.destroy_pending = true; return; }      // deferred until the last child is freed
+    ctx_teardown(ctx);
 }
 
 const char *sgpu_last_error(const sgpu_ctx *ctx) { return ctx ? ctx->c.err.c_str() : "no context"; }
@@ -77,8 +88,6 @@ int sgpu_reads_clear(sgpu_ctx *ctx) {
         c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear();
         c->r_words.release(); c->r_offs.release(); c->r_lens.release();
         c->d_words = nullptr; c->d_offs = nullptr; c->d_lens = nullptr; c->n_reads = 0; c->n_words = 0; c->staged_dirty = false;
-        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
-        c->up_chunks.clear();
     })
 }
 
@@ -95,8 +104,6 @@ int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwor
         }
         c->h_words.insert(c->h_words.end(), words, words + nwords);
         c->staged_dirty = true;
-        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
-        c->up_chunks.clear();
     })
 }
 
@@ -115,45 +122,14 @@ int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, con
         if (c->r_words.n < nwords + 4) c->r_words.alloc(c, nwords + 4, true);
         if (c->r_offs.n < (size_t)nreads + 1) c->r_offs.alloc(c, (size_t)nreads + 1, true);
         if (c->r_lens.n < (size_t)nreads + 1) c->r_lens.alloc(c, (size_t)nreads + 1, true);
-        // chunked copy on a second stream; every chunk carries an event so that the first pass over the reads (per-chunk
-        // histogram kernels) overlaps the rest of the transfer. The window statistics the planner needs are taken on the
-        // host while the DMA engine works.
-        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
-        c->up_chunks.clear();
-        if (!c->copy_stream) SG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        // Opt-in (SGPU_UPLOAD_CHUNKS=n): measured on the B200 box the per-read host statistics and the extra per-chunk launches cost
-        // more than the overlap won (e2e 7965 vs 8637 Mk-mers/s at 20 M reads), so the default is one copy on the main stream.
-        const int nchunk = (getenv("SGPU_UPLOAD_CHUNKS") && nreads >= (1 << 20)) ? std::max(1, atoi(getenv("SGPU_UPLOAD_CHUNKS"))) : 1;
-        if (nchunk <= 1) {
-            if (nwords) SG_CUDA(cudaMemcpyAsync(c->r_words.p, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
-            if (nreads) {
-                SG_CUDA(cudaMemcpyAsync(c->r_offs.p, offs, (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));
-                SG_CUDA(cudaMemcpyAsync(c->r_lens.p, lens, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
-            }
-        } else {
-        cudaEvent_t start_ev;
-        SG_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
-        SG_CUDA(cudaEventRecord(start_ev, c->stream));                      // earlier work on the main stream may still read the old set
-        SG_CUDA(cudaStreamWaitEvent(c->copy_stream, start_ev, 0));
-        cudaEventDestroy(start_ev);
-        for (int q = 0; q < nchunk && nreads; ++q) {
-            UploadChunk u;
-            u.r0 = nreads * q / nchunk; u.r1 = nreads * (q + 1) / nchunk;
-            if (u.r1 == u.r0) continue;
-            const uint64_t w0 = offs[u.r0];
-            const uint64_t w1 = (u.r1 < nreads) ? offs[u.r1] : nwords;      // reads are consecutive in `words`
-            SG_CHECK(w1 >= w0 && w1 <= nwords, SGPU_EINVAL, "sgpu_reads_upload needs reads stored consecutively (ascending offsets)");
-            SG_CUDA(cudaMemcpyAsync(c->r_words.p + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, c->copy_stream));
-            SG_CUDA(cudaMemcpyAsync(c->r_offs.p + u.r0, offs + u.r0, (size_t)(u.r1 - u.r0) * 8, cudaMemcpyHostToDevice, c->copy_stream));
-            SG_CUDA(cudaMemcpyAsync(c->r_lens.p + u.r0, lens + u.r0, (size_t)(u.r1 - u.r0) * 4, cudaMemcpyHostToDevice, c->copy_stream));
-            SG_CUDA(cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
-            SG_CUDA(cudaEventRecord(u.ev, c->copy_stream));
-            for (int64_t r = u.r0; r < u.r1; ++r) {
-                const uint32_t l = lens[r];
-                if (l < 256) u.hist[l]++; else { u.sum_long += l; u.n_long++; }
-            }
-            c->up_chunks.push_back(u);
-        }
+        // one asynchronous copy per array on the context's stream (a chunked copy overlapped with the first pass over the reads was
+        // measured slower on the B200: the per-chunk launches cost more than the overlap won). The caller's buffers must stay
+        // valid and unmodified until the next call that synchronises (sgpu_count / sgpu_dist_begin), see spades_b200.h.
+        if (nwords) SG_CUDA(cudaMemcpyAsync(c->r_words.p, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
+        SG_CUDA(cudaMemsetAsync(c->r_words.p + nwords, 0, 4 * 8, c->stream));       // the padding words the window loads may touch
+        if (nreads) {
+            SG_CUDA(cudaMemcpyAsync(c->r_offs.p, offs, (size_t)nreads * 8, cudaMemcpyHostToDevice, c->stream));
+            SG_CUDA(cudaMemcpyAsync(c->r_lens.p, lens, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
         }
         c->d_words = c->r_words.p; c->d_offs = c->r_offs.p; c->d_lens = c->r_lens.p; c->n_reads = nreads; c->n_words = nwords;
     })
@@ -165,8 +141,6 @@ int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwo
     API_TRY(c, {
         c->h_words.clear(); c->h_offs.clear(); c->h_lens.clear(); c->staged_dirty = false;
         c->r_words.release(); c->r_offs.release(); c->r_lens.release();
-        for (UploadChunk &u : c->up_chunks) if (u.ev) cudaEventDestroy(u.ev);
-        c->up_chunks.clear();
         c->d_words = d_words; c->d_offs = d_offs; c->d_lens = d_lens; c->n_reads = nreads; c->n_words = nwords;
     })
 }
@@ -180,6 +154,7 @@ int sgpu_count(sgpu_ctx *ctx, int K, int num_buckets, int mode, sgpu_kset **out)
         SG_CUDA(cudaSetDevice(c->device));
         KSet *s = count_from_reads(c, K, num_buckets, mode);
         *out = new sgpu_kset{s};
+        child_add(c);
     })
 }
 
@@ -191,6 +166,7 @@ int sgpu_kmers_from_kpomers(sgpu_ctx *ctx, const sgpu_kset *kpomers, int num_buc
         SG_CUDA(cudaSetDevice(c->device));
         KSet *s = kmers_from_kpomers(c, kpomers->s, num_buckets);
         *out = new sgpu_kset{s};
+        child_add(c);
     })
 }
 
@@ -237,6 +213,11 @@ static void write_range(const KSet *ks, int64_t first, int64_t n, FILE *f) {
 
 extern "C" {
 
+int sgpu_kset_checksum(const sgpu_kset *s, uint64_t *out4) {
+    if (!s || !out4) return SGPU_EINVAL;
+    Ctx *c = s->s->ctx;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); kset_checksum(s->s, out4); })
+}
 int sgpu_kset_download_keys(const sgpu_kset *s, int64_t first, int64_t n, uint64_t *out) {
     if (!s || (n && !out)) return SGPU_EINVAL;
     Ctx *c = s->s->ctx;
@@ -276,7 +257,7 @@ int sgpu_kset_write_final(const sgpu_kset *s, const char *path) {
 }
 void sgpu_kset_free(sgpu_kset *s) {
     if (!s) return;
-    if (s->s) { cudaSetDevice(s->s->ctx->device); delete s->s; }
+    if (s->s) { Ctx *c = s->s->ctx; cudaSetDevice(c->device); delete s->s; child_release(c); }
     delete s;
 }
 
@@ -288,6 +269,7 @@ int sgpu_mphf_build(sgpu_ctx *ctx, const sgpu_kset *s, sgpu_mphf **out) {
         SG_CUDA(cudaSetDevice(c->device));
         Mphf *m = mphf_build(c, s->s);
         *out = new sgpu_mphf{m};
+        child_add(c);
     })
 }
 int64_t sgpu_mphf_serialized_size(const sgpu_mphf *m) { return m ? (int64_t)mphf_serialized_size(m->m) : -1; }
@@ -306,7 +288,7 @@ int sgpu_mphf_lookup(const sgpu_mphf *m, const uint64_t *keys, int64_t n, uint64
 }
 void sgpu_mphf_free(sgpu_mphf *m) {
     if (!m) return;
-    if (m->m) { cudaSetDevice(m->m->ctx->device); delete m->m; }
+    if (m->m) { Ctx *c = m->m->ctx; cudaSetDevice(c->device); delete m->m; child_release(c); }
     delete m;
 }
 
@@ -319,6 +301,7 @@ int sgpu_graph_build(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *k
         SG_CUDA(cudaSetDevice(c->device));
         Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0);
         *out = new sgpu_graph{g};
+        child_add(c);
     })
 }
 int sgpu_graph_build_ex(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *kmers, const sgpu_mphf *kmer_index, const sgpu_mphf *kpomer_index,
@@ -331,6 +314,7 @@ int sgpu_graph_build_ex(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset
         Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0,
                                early_tip_length_bound);
         *out = new sgpu_graph{g};
+        child_add(c);
     })
 }
 int sgpu_graph_tip_clipper_stats(const sgpu_graph *g, uint64_t *out3) {
@@ -397,7 +381,7 @@ int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *p
 }
 void sgpu_graph_free(sgpu_graph *g) {
     if (!g) return;
-    if (g->g) { cudaSetDevice(g->g->ctx->device); delete g->g; }
+    if (g->g) { Ctx *c = g->g->ctx; cudaSetDevice(c->device); delete g->g; child_release(c); }
     delete g;
 }
 
@@ -413,6 +397,7 @@ int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, 
         SG_CUDA(cudaSetDevice(c->device));
         DistState *d = dist_begin(c, K, num_buckets, mode, world, rank);
         *out = new sgpu_dist{d, c};
+        child_add(c);
     })
 }
 int64_t sgpu_dist_num_partitions(const sgpu_dist *d) { return d ? (int64_t)dist_num_partitions(d->d) : -1; }
@@ -424,13 +409,9 @@ int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts, uint64_t budget_byt
     if (!d || !all_counts || !npass || !exchange_records) return SGPU_EINVAL;
     API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_plan(d->d, all_counts, budget_bytes, npass, exchange_records); })
 }
-int sgpu_dist_adopt(sgpu_dist *d, sgpu_dist *previous) {
-    if (!d) return 0;
-    try { return dist_adopt(d->d, previous ? previous->d : nullptr); } catch (...) { return 0; }
-}
-int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out64) {
-    if (!d || !out64) return SGPU_EINVAL;
-    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_ipc_handle(d->d, out64); })
+int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out) {
+    if (!d || !out) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_ipc_handle(d->d, out); })
 }
 int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *handles) {
     if (!d || !handles) return SGPU_EINVAL;
@@ -451,13 +432,15 @@ int sgpu_dist_sort(sgpu_dist *d, int pass) {
 int sgpu_dist_end(sgpu_dist *d, sgpu_kset **out) {
     if (!d || !out) return SGPU_EINVAL;
     *out = nullptr;
-    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); KSet *s = dist_end(d->d); *out = new sgpu_kset{s}; })
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); KSet *s = dist_end(d->d); *out = new sgpu_kset{s}; child_add(d->c); })
 }
 void sgpu_dist_free(sgpu_dist *d) {
     if (!d) return;
-    cudaSetDevice(d->c->device);
+    Ctx *c = d->c;
+    cudaSetDevice(c->device);
     dist_free(d->d);
     delete d;
+    child_release(c);
 }
 int sgpu_dist_plan_host(int world, int num_buckets, int key_bits_in_partition, const uint64_t *all_counts, uint64_t budget_bytes, int record_bytes,
                         int *pass_bounds, uint64_t *max_recv) {
@@ -538,6 +521,7 @@ extern "C" int sg_selftest_pair_mailbox(uint64_t arg, int64_t per_thread, uint64
 extern "C" int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
     if (K < 1 || K > 128 || n < 0 || (n && (!keys || !out))) return SGPU_EINVAL;
     Ctx *c = ctx ? &ctx->c : nullptr;
+    if (on_device && !c) return SGPU_EINVAL;
     if (op == 11) {
         if (on_device || n < 3) return SGPU_EINVAL;
         return sg_selftest_pair_mailbox(arg, (int64_t)keys[0], out);

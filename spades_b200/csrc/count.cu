@@ -487,41 +487,20 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc 
 // base rows are `row_stride` cursors long; this launch handles the partitions [q_lo, q_lo + p.PA) of a row (p.PA = the
 // sub-range's size, id_lo = id of its first partition): a bucket-group pass may be split into partition sub-ranges so that
 // the lines and pages a CTA has open at any time stay few (TLB reach).
-// stores of the pairing variant (pair_mailbox.cuh): one full 32-byte sector for two records of a stream, 16 bytes for a lone record
-struct PairSink {
-    uint64_t *out;
-    __device__ __forceinline__ void pair(uint64_t pos, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1) {
-        asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + pos * 2), "l"(a0), "l"(a1), "l"(b0), "l"(b1) : "memory");
-    }
-    __device__ __forceinline__ void single(uint64_t pos, uint64_t w0, uint64_t w1) {
-        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(out + pos * 2), "l"(w0), "l"(w1) : "memory");
-    }
-};
-template <int NW, bool PAIR>
-__device__ __forceinline__ void emit_rec(uint64_t *out, const uint64_t *cur_base, uint32_t *cnt, PmBox *boxes, uint32_t part, const Kmer<NW> &k) {
-    const uint32_t slot = atomicAdd(&cnt[part], 1u);
-    if constexpr (PAIR && NW == 2) {
-        PairSink sink{out};
-        pm_put<kPmDepth>(boxes + (size_t)part * kPmDepth, cur_base[part], slot, k.w[0], k.w[1], sink);
-    } else {
-        store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
-    }
-}
-
-template <int NW, bool HAS_IDS, bool PAIR>
+// (A sector-pairing variant of this kernel -- two records of a stream leave as one 32-byte store through shared-memory
+// mailboxes -- was measured on the B200 in round 2: parity clean but 1.8x SLOWER, 185 -> 336 ms at 100 M reads; the CAS
+// traffic on the mailboxes costs more than the full sectors win. profiles/r02a_sweep_variants.log. Removed.)
+template <int NW, bool HAS_IDS>
 __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
                                                                         const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
-                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo, uint32_t flags) {
+                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo) {
     extern __shared__ uint32_t sm_dyn[];
     uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
-    PmBox *boxes = reinterpret_cast<PmBox *>(cur_base + p.PA);          // PAIR: PA * kPmDepth mailboxes (24 bytes each)
-    uint32_t *cnt = PAIR ? reinterpret_cast<uint32_t *>(boxes + (size_t)p.PA * kPmDepth) : reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
     __shared__ RollTile rt;
     __shared__ TileStage ts;
     uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
-    if (PAIR)
-        for (uint32_t i = threadIdx.x; i < p.PA * kPmDepth; i += blockDim.x) boxes[i].state = 0u;
     __syncthreads();
     const int K = p.K;
     const uint32_t PA = p.PA;
@@ -535,12 +514,6 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
         const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
         const bool staged = tile_stage(src, item0, nitems, ts);
         const ulonglong2 *row = HAS_IDS ? reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]) : nullptr;
-        if (PAIR && HAS_IDS && (flags & 1u) && t + 1 < t1) {
-            // experimental (pairing variant only, SGPU_PREFETCH=1): pull the next tile's id row into L2 while this tile is walked --
-            // ncu put half of this kernel's stall samples on the consumers of the id words
-            const char *a = reinterpret_cast<const char *>(ids + tile_off[t + 1]), *e = reinterpret_cast<const char *>(ids + tile_off[t + 2]);
-            for (const char *q = a + 128 * (size_t)threadIdx.x; q < e; q += 128 * (size_t)blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        }
         for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
             uint64_t idw[kRollC / 4];
             if (HAS_IDS) {
@@ -559,173 +532,24 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
             for (int s = 0; s < kRollC; ++s) {
                 if (s < q.cnt) {
                     if (s > 0) roll_next<NW>(st, seq, K);
+                    uint32_t part;
+                    bool mine;
                     if (HAS_IDS) {
-                        const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;     // 0xffff - id_lo stays >= PA
-                        if (part < PA) {
-                            const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
-                            emit_rec<NW, PAIR>(out, cur_base, cnt, boxes, part, k);
-                        }
-                    } else {
-                        const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
-                        uint32_t part;
-                        if (part_of<NW>(p, k, &part)) emit_rec<NW, PAIR>(out, cur_base, cnt, boxes, part, k);
+                        part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;     // 0xffff - id_lo stays >= PA
+                        mine = part < PA;
+                    }
+                    const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                    if (!HAS_IDS) mine = part_of<NW>(p, k, &part);
+                    if (mine) {
+                        const uint32_t slot = atomicAdd(&cnt[part], 1u);
+                        store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
                     }
                 }
             }
         }
         __syncthreads();
-    }
-    if constexpr (PAIR && NW == 2) {
-        // every producer is past the barrier that ends the last tile: what is still deposited goes out as single records
-        PairSink sink{out};
-        for (uint32_t i = threadIdx.x; i < PA * kPmDepth; i += blockDim.x) pm_flush_box(&boxes[i], cur_base[i / kPmDepth], sink);
     }
     for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
-}
-
-// ---- radix-partition kernel, second generation: gather -> sort in shared memory -> coalesced flush -------------------
-// ncu on levelA_scatter_k: 49 GB written + 23 GB read back for 30 GB of records; every 16-byte store opened its own 32-byte
-// sector and partially written lines were evicted before their neighbours arrived (DRAM-random-access bound at ~0.5 TB/s).
-// Here a CTA only looks at the 2-byte partition ids the count pass left behind, extracts the records of the current
-// partition sub-range, collects them in shared memory, counting-sorts a batch by partition and writes every partition's
-// run with consecutive threads -> consecutive addresses, so sectors/lines leave the SM full. The sub-range is kept small
-// (<= kA2MaxParts partitions) so that a batch holds ~10 records per partition; the caller loops over sub-ranges, which is
-// cheap because records outside the sub-range cost one 2-byte load and a compare.
-static const int kA2Threads = 1024;
-static const int kA2Cap = 4096;          // pending records per batch (4096 x 16 B = 64 KB for NW = 2)
-static const int kA2MaxParts = 1024;     // one histogram bin per thread
-
-template <int NW, class Src>
-__global__ void __launch_bounds__(kA2Threads, 2) levelA_scatter2_k(Src src, int K, uint64_t *__restrict__ base /*[G][PA]*/, uint64_t *__restrict__ out,
-                                                                const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
-                                                                uint32_t id_lo, uint32_t PA) {
-    extern __shared__ uint64_t sm64[];
-    uint64_t *pend = sm64;                                                 // kA2Cap * NW
-    uint64_t *cur_base = pend + (size_t)kA2Cap * NW;                       // PA   running global cursor of this CTA
-    uint32_t *hist = reinterpret_cast<uint32_t *>(cur_base + kA2MaxParts); // kA2MaxParts  (-> exclusive offsets -> cursors)
-    uint32_t *off = hist + kA2MaxParts;                                    // kA2MaxParts+1
-    uint16_t *ppart = reinterpret_cast<uint16_t *>(off + kA2MaxParts + 1); // kA2Cap   partition of pending record
-    uint16_t *sidx = ppart + kA2Cap;                                       // kA2Cap   pending index in sorted order
-    __shared__ uint32_t pref[kATile + 1];
-    __shared__ uint32_t npend;
-    __shared__ uint32_t wtot[kA2Threads / 32];
-    uint64_t *mybase = base + (size_t)blockIdx.x * PA;
-    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) cur_base[i] = mybase[i];
-    if (threadIdx.x == 0) npend = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    auto flush = [&]() {
-        // all threads arrive with npend final
-        const uint32_t n = npend;
-        if (threadIdx.x < kA2MaxParts) hist[threadIdx.x] = 0;
-        __syncthreads();
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) atomicAdd(&hist[ppart[j]], 1u);
-        __syncthreads();
-        // exclusive scan over PA <= 1024 bins, one per thread
-        uint32_t v = threadIdx.x < PA ? hist[threadIdx.x] : 0, inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) wtot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = wtot[lane], winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            wtot[lane] = winc - w;
-        }
-        __syncthreads();
-        const uint32_t ex = wtot[warp] + inc - v;
-        if (threadIdx.x < PA) { off[threadIdx.x] = ex; hist[threadIdx.x] = ex; }
-        if (threadIdx.x == 0) off[PA] = n;
-        __syncthreads();
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) sidx[atomicAdd(&hist[ppart[j]], 1u)] = (uint16_t)j;
-        __syncthreads();
-        // flush in sorted order: thread q writes the q-th record; runs of one partition are contiguous in q AND in memory
-        for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
-            const uint32_t j = sidx[q];
-            const uint32_t p = ppart[j];
-            store_rec<NW>(out + (cur_base[p] + (q - off[p])) * NW, load_rec<NW>(pend + (size_t)j * NW));
-        }
-        __syncthreads();
-        if (threadIdx.x < PA) cur_base[threadIdx.x] += off[threadIdx.x + 1] - off[threadIdx.x];
-        if (threadIdx.x == 0) npend = 0;
-        __syncthreads();
-    };
-
-    uint32_t np = 0;      // every thread's copy of the pending count
-    __shared__ uint32_t rsum[3];     // records entering the batch per round, triple buffered (one barrier per round)
-    if (threadIdx.x < 3) rsum[threadIdx.x] = 0;
-    __syncthreads();
-    uint32_t round_no = 0;
-    constexpr int V = 4;             // consecutive records per thread and round
-    const int64_t ntiles = (src.n + kATile - 1) / kATile;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t item0 = t * kATile;
-        const int nitems = (int)min((int64_t)kATile, src.n - item0);
-        const uint32_t total = tile_prefix(src, item0, nitems, pref);
-        const uint16_t *tid_ids = ids + tile_off[t];                        // 16-byte aligned row (tile totals are padded to 8)
-        for (uint32_t i0 = 0; i0 < total; i0 += V * blockDim.x, ++round_no) {
-            const uint32_t ib = i0 + V * threadIdx.x;
-            uint32_t part[V];
-            uint32_t c = 0;
-            {
-                ushort4 raw = make_ushort4(0xffff, 0xffff, 0xffff, 0xffff);
-                if (ib < total) raw = *reinterpret_cast<const ushort4 *>(tid_ids + ib);   // may cover row padding: masked below
-                const uint32_t r4[V] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    part[v] = (ib + v < total) ? r4[v] - id_lo : 0xffffffffu;
-                    c += part[v] < PA ? 1u : 0u;
-                }
-            }
-            // warp-inclusive scan of c -> slots of this warp are contiguous; the warp total also feeds the round total
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += x;
-            }
-            const uint32_t wtotal = __shfl_sync(0xffffffffu, inc, 31);
-            const uint32_t buf = round_no % 3u;
-            if (lane == 0 && wtotal) atomicAdd(&rsum[buf], wtotal);
-            __syncthreads();                                               // the only barrier of the round
-            const uint32_t round_in = rsum[buf];
-            if (threadIdx.x == 0) rsum[(round_no + 2u) % 3u] = 0;           // last read two rounds ago, next written two rounds ahead
-            if (np + round_in > (uint32_t)kA2Cap) { flush(); np = 0; }
-            np += round_in;
-            if (wtotal) {
-                uint32_t wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&npend, wtotal);
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                uint32_t slot = wbase + inc - c;
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    if (part[v] < PA) {
-                        const uint32_t i = ib + v;
-                        const int it = find_item(pref, nitems, i);
-                        const Kmer<NW> k = src.template get<NW>(item0 + it, i - pref[it]);
-                        store_rec<NW>(pend + (size_t)slot * NW, k);
-                        ppart[slot] = (uint16_t)part[v];
-                        ++slot;
-                    }
-                }
-            }
-        }
-        __syncthreads();       // pref is rewritten by the next tile_prefix
-    }
-    __syncthreads();
-    flush();
-    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i];   // chained launches continue here
-    (void)K;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -826,6 +650,17 @@ __global__ void refine_copy_k(const Seg *__restrict__ segs, uint64_t n, const ui
     if (isw[i]) worklist[work_pos[i]] = i;
     else nsegs[child_base[i]] = segs[i];
 }
+
+// stores of the pairing refinement (pair_mailbox.cuh): one full 32-byte sector for two records of a bin, 16 bytes for a lone record
+struct PairSink {
+    uint64_t *out;
+    __device__ __forceinline__ void pair(uint64_t pos, uint64_t a0, uint64_t a1, uint64_t b0, uint64_t b1) {
+        asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + pos * 2), "l"(a0), "l"(a1), "l"(b0), "l"(b1) : "memory");
+    }
+    __device__ __forceinline__ void single(uint64_t pos, uint64_t w0, uint64_t w1) {
+        asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(out + pos * 2), "l"(w0), "l"(w1) : "memory");
+    }
+};
 
 static const int kRThreads = 1024;
 static const int kRMaxBins = 2048;
@@ -1036,8 +871,8 @@ __device__ __forceinline__ uint64_t *lsd_sort_range(uint64_t *A, uint64_t *Bf, u
 // copies of a few keys (a genomic (k+1)-mer is seen ~coverage times) plus error singletons. Two earlier generations (a full LSD
 // radix sort per segment; one counting pass into 2^11 bins with one thread collapsing each bin) were replaced by the kernel
 // below; the LSD passes above survive as its exact fallback.
-static const int kBinBitsDefault = 11;       // SGPU_BINBITS = 9 | 10 | 11: fewer bins = less per-segment bookkeeping (init + two scans over the
-                                            // bins), more keys sharing a bin (more residual work, earlier fallback)
+static const int kSortBinBits = 11;   // bins per segment = 2^11: fewer bins = less per-segment bookkeeping (init + two scans over the bins) but more
+                                      // keys sharing a bin (B200, 20 M reads: 2^10 bins 51.0 ms vs 2^11 bins 50.2 ms -- no gain, profiles/r02a_sweep_variants.log)
 
 // ncu on the one-thread-per-bin generation showed 8.5 active lanes per instruction and barrier stalls on top: one thread chewing
 // through the ~coverage copies of a genomic k-mer held up its whole CTA. Here every bin elects a representative (the
@@ -1335,10 +1170,33 @@ struct Timer {
     float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 
+// Environment, read ONCE per process and clamped to what the kernels support. User options: SGPU_ARENA_GB (sgpu_internal.h) and
+// SGPU_TRACE (per-phase wall clock on stderr). Tuning knobs kept for A/B runs on the GPU box:
+//   SGPU_PA_MAX   level-A partitions for the whole job (default 4096; every (CTA, partition) pair is an open write stream)
+//   SGPU_RMAX     key bits per refinement round (default 11 = 2048 bins per CTA)
+//   SGPU_A_SUB    partition sub-ranges per level-A scatter pass (default 0 = automatic)
+struct Tuning {
+    uint32_t pa_max = 4096;
+    uint32_t rmax = 11;
+    int a_sub = 0;
+    bool trace = false;
+};
+static const Tuning &tuning() {
+    static const Tuning t = [] {
+        Tuning x;
+        if (const char *e = getenv("SGPU_PA_MAX")) x.pa_max = (uint32_t)std::min(8192, std::max(1, atoi(e)));
+        if (const char *e = getenv("SGPU_RMAX")) x.rmax = (uint32_t)std::min(11, std::max(1, atoi(e)));
+        if (const char *e = getenv("SGPU_A_SUB")) x.a_sub = std::min(64, std::max(0, atoi(e)));
+        x.trace = getenv("SGPU_TRACE") != nullptr;
+        return x;
+    }();
+    return t;
+}
+
 struct Trace {
     bool on; cudaStream_t st; double t0;
     static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
-    Trace(cudaStream_t s) : on(getenv("SGPU_TRACE") != nullptr), st(s), t0(now()) {}
+    Trace(cudaStream_t s) : on(tuning().trace), st(s), t0(now()) {}
     void mark(const char *what) {
         if (!on) return;
         cudaStreamSynchronize(st);
@@ -1350,163 +1208,302 @@ struct Trace {
 
 static int ilog2_floor(uint64_t v) { int r = 0; while (v >>= 1) ++r; return r; }
 
-// local-sort segment capacity (records): SGPU_SORT_CAP=1024 halves the segments (one more refinement bit) for ~40 KB instead of
-// ~69 KB of shared memory per CTA -- more CTAs per SM to hide the per-segment load / barrier latency. Opt-in until measured.
-template <int NW>
-static int sort_cap() {
-    const char *e = getenv("SGPU_SORT_CAP");
-    return (e && atoi(e) == 1024 && SortCfg<NW>::CAP >= 1024) ? 1024 : SortCfg<NW>::CAP;
-}
+static const int kLevelAMaxParts = 8192;      // partitions one level-A launch can address (shared-memory histogram / cursor tables)
 
+// mean segment length the refinement aims for: 3/4 of the local-sort capacity
+template <int NW> static uint32_t sort_target() { return (uint32_t)SortCfg<NW>::CAP * 6 / 8; }
+
+// refinement + local sort + compaction of one pass: X holds the level-A output (CTA-major pieces when `pieces` is given, else
+// partition-major with the given starts/totals), Y is the ping-pong partner of the same size.
 template <int NW>
 static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, const uint64_t *part_start_p, const uint64_t *part_total_p, uint32_t PA,
                       int rA_, uint32_t b_lo, int b_hi, int64_t first, bool want_counts, bool double_selfrc, unsigned long long *d_bsz_p, Chunk &ch_out,
                       Timer &tm, Trace &tr, const Pieces *pieces = nullptr) {
-    const int CAP = sort_cap<NW>();
-    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
+    constexpr int CAP = SortCfg<NW>::CAP;
     const int total_bits = 2 * K;
     cudaStream_t st = ctx->stream;
-        // ---- segments + refinement rounds
-        uint64_t nsegs = PA;
-        DArr<Seg> segs(ctx, nsegs);
-        seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start_p, part_total_p, PA, rA_, b_lo, segs.p);
+    // ---- segments + refinement rounds
+    uint64_t nsegs = PA;
+    DArr<Seg> segs(ctx, nsegs);
+    seg_init_k<<<div_up(PA, 256), 256, 0, st>>>(part_start_p, part_total_p, PA, rA_, b_lo, segs.p);
+    ctx->launches++;
+    RefinePlan rp; rp.cap = CAP; rp.target = sort_target<NW>(); rp.total_bits = total_bits;
+    rp.rmax = tuning().rmax;
+    DArr<unsigned long long> wcounter(ctx, 4);
+    tm.start();
+    for (int round = 0; round < 300; ++round) {
+        DArr<uint32_t> nchild(ctx, nsegs + 1), isw(ctx, nsegs + 1);
+        DArr<uint64_t> cbase(ctx, nsegs + 1), wpos(ctx, nsegs + 1);
+        SG_CUDA(cudaMemsetAsync(nchild.p + nsegs, 0, 4, st));
+        SG_CUDA(cudaMemsetAsync(isw.p + nsegs, 0, 4, st));
+        const bool pieced = pieces && round == 0;       // X holds the CTA-major staging buffer: round 0 gathers every partition
+        refine_plan_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, rp, nchild.p, isw.p, pieced ? 1 : 0);
         ctx->launches++;
-        RefinePlan rp; rp.cap = CAP; rp.target = TARGET; rp.total_bits = total_bits;
-        // bins per refinement round = open 128-byte lines per CTA. ncu: at <= 512 bins the kernel's DRAM traffic equals its algorithmic
-        // traffic, at 2048 bins (100 M reads) it is twice as slow per record. SGPU_RMAX trades an extra round for fewer bins.
-        rp.rmax = getenv("SGPU_RMAX") ? (uint32_t)std::min(11, std::max(1, atoi(getenv("SGPU_RMAX")))) : 11u;
-        DArr<unsigned long long> wcounter(ctx, 4);
-        tm.start();
-        for (int round = 0; round < 300; ++round) {
-            DArr<uint32_t> nchild(ctx, nsegs + 1), isw(ctx, nsegs + 1);
-            DArr<uint64_t> cbase(ctx, nsegs + 1), wpos(ctx, nsegs + 1);
-            SG_CUDA(cudaMemsetAsync(nchild.p + nsegs, 0, 4, st));
-            SG_CUDA(cudaMemsetAsync(isw.p + nsegs, 0, 4, st));
-            const bool pieced = pieces && round == 0;       // X holds the CTA-major staging buffer: round 0 gathers every partition
-            refine_plan_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, rp, nchild.p, isw.p, pieced ? 1 : 0);
-            ctx->launches++;
-            exclusive_scan_u32_to_u64(ctx, nchild.p, cbase.p, nsegs + 1);
-            exclusive_scan_u32_to_u64(ctx, isw.p, wpos.p, nsegs + 1);
-            uint64_t tot[2];
-            SG_CUDA(cudaMemcpyAsync(&tot[0], cbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
-            SG_CUDA(cudaMemcpyAsync(&tot[1], wpos.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
-            SG_CUDA(cudaStreamSynchronize(st));
-            tr.mark("refine plan+scans");
-            if (tot[1] == 0) break;
-            DArr<Seg> nsegs_arr(ctx, tot[0]);
-            DArr<uint64_t> worklist(ctx, tot[1]);
-            tr.mark("refine allocs");
-            refine_copy_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, isw.p, cbase.p, wpos.p, nsegs_arr.p, worklist.p);
-            ctx->launches++;
-            SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
-            int grid = (int)std::min<uint64_t>(tot[1], (uint64_t)ctx->num_sms * 2);
-            const bool pair_refine = NW == 2 && getenv("SGPU_PAIR_REFINE") && atoi(getenv("SGPU_PAIR_REFINE")) != 0;     // opt-in until measured
-            if (pair_refine) {
-                const size_t sm = (size_t)kRMaxBins * sizeof(PmBox);
-                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                if (pieced) refine_k<NW, true, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
-                else refine_k<NW, false, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
-            } else if (pieced) refine_k<NW, true, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
-            else refine_k<NW, false, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
-            ctx->launches++;
-            SG_CUDA(cudaGetLastError());
-            SG_CUDA(cudaStreamSynchronize(st));
-            tr.mark("refine kernel");
-            segs = std::move(nsegs_arr);
-            nsegs = tot[0];
-        }
-        ctx->times.refine += tm.stop();
-        tr.mark("refine end");
-        // ---- local sort
-        DArr<uint32_t> ndist(ctx, nsegs + 1);
-        DArr<unsigned long long> stats(ctx, 4);
-        SG_CUDA(cudaMemsetAsync(ndist.p, 0, ndist.bytes(), st));
-        SG_CUDA(cudaMemsetAsync(stats.p, 0, 32, st));
-        SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
-        tm.start();
-        {
-            auto launch_sort = [&](auto kernel, int bins) {
-                size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * bins * sizeof(uint32_t) +
-                              ((size_t)2 * bins + 2 + kResCap) * sizeof(uint16_t) + 16;
-                SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int occ = 1;
-                SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSThreads, smem));
-                if (occ < 1) occ = 1;
-                int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
-                if (grid < 1) grid = 1;
-                kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
-            };
-            const int binbits = getenv("SGPU_BINBITS") ? atoi(getenv("SGPU_BINBITS")) : kBinBitsDefault;
-            constexpr int CAPD = SortCfg<NW>::CAP, CAPH = SortCfg<NW>::CAP >= 2048 ? 1024 : SortCfg<NW>::CAP;
-            if (CAP == CAPD) {
-                if (binbits == 10) launch_sort(local_sort3_k<NW, 10, CAPD>, 1 << 10);
-                else launch_sort(local_sort3_k<NW, 11, CAPD>, 1 << 11);
-            } else {
-                if (binbits == 10) launch_sort(local_sort3_k<NW, 10, CAPH>, 1 << 10);
-                else launch_sort(local_sort3_k<NW, 11, CAPH>, 1 << 11);
-            }
-            ctx->launches++;
-            SG_CUDA(cudaGetLastError());
-        }
-        DArr<uint64_t> dbase(ctx, nsegs + 1);
-        exclusive_scan_u32_to_u64(ctx, ndist.p, dbase.p, nsegs + 1);
-        uint64_t D = 0;
-        unsigned long long h_stats[4];
-        SG_CUDA(cudaMemcpyAsync(&D, dbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(h_stats, stats.p, 32, cudaMemcpyDeviceToHost, st));
+        exclusive_scan_u32_to_u64(ctx, nchild.p, cbase.p, nsegs + 1);
+        exclusive_scan_u32_to_u64(ctx, isw.p, wpos.p, nsegs + 1);
+        uint64_t tot[2];
+        SG_CUDA(cudaMemcpyAsync(&tot[0], cbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(&tot[1], wpos.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaStreamSynchronize(st));
-        ctx->times.local_sort += tm.stop();
-        tr.mark("local sort");
-        SG_CHECK(h_stats[0] == 0, 6, "internal: oversize segment with unfixed key bits reached the local sort");
-        // ---- compaction into the dense chunk
-        Chunk ch;
-        ch.n = (int64_t)D; ch.b_lo = (int)b_lo; ch.b_hi = b_hi; ch.first = first;
-        ch.keys.alloc(ctx, (size_t)D * NW + 2, true);
-        if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1, true);
-        tm.start();
-        if (nsegs) {
-            compact_k<NW><<<div_up((int64_t)nsegs * 32, 256), 256, 0, st>>>(segs.p, nsegs, ndist.p, dbase.p, X.p, Y.p, K, want_counts ? 1 : 0,
-                                                                         double_selfrc ? 1 : 0, ch.keys.p, ch.counts.p, d_bsz_p);
-            ctx->launches++;
-            SG_CUDA(cudaGetLastError());
+        if (tot[1] == 0) break;
+        DArr<Seg> nsegs_arr(ctx, tot[0]);
+        DArr<uint64_t> worklist(ctx, tot[1]);
+        refine_copy_k<<<div_up(nsegs, 256), 256, 0, st>>>(segs.p, nsegs, isw.p, cbase.p, wpos.p, nsegs_arr.p, worklist.p);
+        ctx->launches++;
+        SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
+        const int grid = (int)std::min<uint64_t>(tot[1], (uint64_t)ctx->num_sms * 2);
+        // 16-byte records: the scatter phase pairs the two records of a 32-byte sector (B200, 100 M reads: 285 -> 185 ms)
+        if (NW == 2) {
+            const size_t sm = (size_t)kRMaxBins * sizeof(PmBox);
+            if (pieced) {
+                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                refine_k<NW, true, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
+            } else {
+                SG_CUDA(cudaFuncSetAttribute(refine_k<NW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                refine_k<NW, false, true><<<grid, kRThreads, sm, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
+            }
+        } else if (pieced) {
+            refine_k<NW, true, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, *pieces);
+        } else {
+            refine_k<NW, false, false><<<grid, kRThreads, 0, st>>>(segs.p, worklist.p, tot[1], cbase.p, rp, K, X.p, Y.p, nsegs_arr.p, wcounter.p, Pieces());
         }
-        ctx->times.compact += tm.stop();
-        tr.mark("compact");
-        ch_out = std::move(ch);
+        ctx->launches++;
+        SG_CUDA(cudaGetLastError());
+        tr.mark("refine round");
+        segs = std::move(nsegs_arr);
+        nsegs = tot[0];
+    }
+    ctx->times.refine += tm.stop();
+    // ---- local sort
+    DArr<uint32_t> ndist(ctx, nsegs + 1);
+    DArr<unsigned long long> stats(ctx, 4);
+    SG_CUDA(cudaMemsetAsync(ndist.p, 0, ndist.bytes(), st));
+    SG_CUDA(cudaMemsetAsync(stats.p, 0, 32, st));
+    SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
+    tm.start();
+    {
+        constexpr int bins = 1 << kSortBinBits;
+        auto kernel = local_sort3_k<NW, kSortBinBits, CAP>;
+        const size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * bins * sizeof(uint32_t) +
+                            ((size_t)2 * bins + 2 + kResCap) * sizeof(uint16_t) + 16;
+        SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSThreads, smem));
+        if (occ < 1) occ = 1;
+        int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
+        if (grid < 1) grid = 1;
+        kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+        ctx->launches++;
+        SG_CUDA(cudaGetLastError());
+    }
+    DArr<uint64_t> dbase(ctx, nsegs + 1);
+    exclusive_scan_u32_to_u64(ctx, ndist.p, dbase.p, nsegs + 1);
+    uint64_t D = 0;
+    unsigned long long h_stats[4];
+    SG_CUDA(cudaMemcpyAsync(&D, dbase.p + nsegs, 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_stats, stats.p, 32, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    ctx->times.local_sort += tm.stop();
+    tr.mark("local sort");
+    SG_CHECK(h_stats[0] == 0, 6, "internal: oversize segment with unfixed key bits reached the local sort");
+    // ---- compaction into the dense chunk
+    Chunk ch;
+    ch.n = (int64_t)D; ch.b_lo = (int)b_lo; ch.b_hi = b_hi; ch.first = first;
+    ch.keys.alloc(ctx, (size_t)D * NW + 2, true);
+    if (want_counts) ch.counts.alloc(ctx, (size_t)D + 1, true);
+    tm.start();
+    if (nsegs) {
+        compact_k<NW><<<div_up((int64_t)nsegs * 32, 256), 256, 0, st>>>(segs.p, nsegs, ndist.p, dbase.p, X.p, Y.p, K, want_counts ? 1 : 0,
+                                                                     double_selfrc ? 1 : 0, ch.keys.p, ch.counts.p, d_bsz_p);
+        ctx->launches++;
+        SG_CUDA(cudaGetLastError());
+    }
+    ctx->times.compact += tm.stop();
+    tr.mark("compact");
+    ch_out = std::move(ch);
 }
 
-// rolling level-A kernels (reads, canonical mode): SGPU_ROLL=0/1 overrides the default
-static const bool kRollDefault = true;    // verified on the B200: parity suite, no-ids variant and compute-sanitizer clean with SGPU_ROLL=1
-static bool use_roll() {
-    const char *e = getenv("SGPU_ROLL");
-    return e ? atoi(e) != 0 : kRollDefault;
-}
+// ---- level A as a job: one histogram (+ partition id) pass over the source, then one scatter per bucket-group pass -----------
+// Shared by the single-GPU count and the multi-GPU count (where a "pass" scatters this rank's shard for the pass's buckets).
+template <int NW, class Src>
+struct LevelAJob {
+    Ctx *ctx = nullptr;
+    std::vector<Src> srcs;
+    int K = 0, B = 0, rA = 0, G = 0;
+    int s_lo = 0, s_hi = 0;               // buckets covered by this job (one histogram super-range)
+    uint32_t PA_all = 0;                  // (s_hi - s_lo) << rA
+    bool roll = false, use_ids = false;
+    DArr<uint32_t> blk_counts;            // [G][PA_all] records of (CTA, partition)
+    DArr<uint64_t> part_total_all;        // [PA_all]
+    std::vector<DArr<uint64_t>> tile_off; // per source: first id of every tile
+    std::vector<DArr<uint16_t>> ids;      // per source: 2-byte partition id per record slot
+    std::vector<uint64_t> h_part;         // host copy of part_total_all
+    uint64_t bucket_records(int b) const {
+        uint64_t s = 0;
+        for (uint32_t q = 0; q < (1u << rA); ++q) s += h_part[((size_t)(b - s_lo) << rA) + q];
+        return s;
+    }
+};
 
-// CTA-major staging of the level-A output + gathering first refinement round: SGPU_STAGE=0/1 overrides the default
-static const bool kStageDefault = true;    // B200, parity suite + compute-sanitizer clean with SGPU_STAGE=1; 20 M reads: scatter 56.8 -> 31.5 ms (4 sub-ranges), 100 M: 259 -> 184 ms
-static bool use_stage() {
-    const char *e = getenv("SGPU_STAGE");
-    return e ? atoi(e) != 0 : kStageDefault;
+// total fan-out bits wanted for est_records, minus what the bucket function provides, clamped to the tables
+static int levelA_key_bits(uint64_t est_records, int B, int total_bits, uint32_t target, uint32_t pa_max) {
+    const int want = ilog2_floor(est_records / target + 1) + 1;
+    const int bbits = ilog2_floor((uint64_t)B) + (((1u << ilog2_floor((uint64_t)B)) < (uint32_t)B) ? 1 : 0);
+    int rA = want - bbits;
+    if (rA < 0) rA = 0;
+    while (rA > 0 && ((uint64_t)B << rA) > pa_max) --rA;
+    if (rA > total_bits) rA = total_bits;
+    if (rA > 13) rA = 13;                 // a histogram super-range holds at least one bucket: (1 << rA) <= kLevelAMaxParts
+    return rA;
 }
 
 template <int NW, class Src>
-static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records,
-                             KSet *out, const std::vector<cudaEvent_t> *ready = nullptr, const std::vector<uint64_t> *src_records = nullptr) {
-    const int CAP = sort_cap<NW>();
-    const uint32_t TARGET = CAP * (getenv("SGPU_TARGET_8THS") ? atoi(getenv("SGPU_TARGET_8THS")) : 6) / 8;   // mean segment length aimed for
+static void levelA_count(LevelAJob<NW, Src> &job, uint64_t est_records, Timer &tm, Trace &tr) {
+    Ctx *ctx = job.ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t PA_all = job.PA_all;
+    const int G = job.G;
+    SG_CHECK(PA_all >= 1 && PA_all <= (uint32_t)kLevelAMaxParts, 6, "internal: level-A partition table too large");
+    LevelA pa_all;
+    pa_all.K = job.K; pa_all.B = (uint32_t)job.B; pa_all.b_lo = (uint32_t)job.s_lo; pa_all.b_hi = (uint32_t)job.s_hi; pa_all.rA = job.rA; pa_all.PA = PA_all;
+    job.blk_counts.alloc(ctx, (size_t)G * PA_all);
+    job.part_total_all.alloc(ctx, (size_t)PA_all + 1);
+    job.h_part.assign(PA_all, 0);
+    SG_CUDA(cudaMemsetAsync(job.blk_counts.p, 0, job.blk_counts.bytes(), st));
+    job.tile_off.clear(); job.ids.clear();
+    job.tile_off.resize(job.srcs.size()); job.ids.resize(job.srcs.size());
+    // per-record partition ids (2 bytes per record slot): only when they fit comfortably next to the sort buffers
+    job.use_ids = PA_all < 0xffffu && (double)est_records * 2.0 < (double)ctx->free_bytes() * 0.15;
+    if (job.use_ids) {
+        for (size_t si = 0; si < job.srcs.size(); ++si) {
+            const Src &src = job.srcs[si];
+            if (src.n == 0) continue;
+            const int64_t ntiles = (src.n + kATile - 1) / kATile;
+            DArr<uint32_t> ttot(ctx, (size_t)ntiles + 1);
+            job.tile_off[si].alloc(ctx, (size_t)ntiles + 1);
+            SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
+            if (job.roll) {
+                if constexpr (std::is_same<Src, ReadsSrc>::value) roll_tile_ids_k<<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
+            } else {
+                tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p, 8u);
+            }
+            ctx->launches++;
+            exclusive_scan_u32_to_u64(ctx, ttot.p, job.tile_off[si].p, (size_t)ntiles + 1);
+            uint64_t nrec_src = 0;
+            SG_CUDA(cudaMemcpyAsync(&nrec_src, job.tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaStreamSynchronize(st));
+            job.ids[si].alloc(ctx, (size_t)nrec_src + 8);
+        }
+    }
+    tm.start();
+    for (size_t si = 0; si < job.srcs.size(); ++si) {
+        const Src &src = job.srcs[si];
+        if (src.n == 0) continue;
+        if (job.roll) {
+            if constexpr (std::is_same<Src, ReadsSrc>::value) {
+                SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
+                levelA_count_roll_k<NW><<<G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, job.blk_counts.p, job.tile_off[si].p, job.ids[si].p);
+            }
+        } else {
+            SG_CUDA(cudaFuncSetAttribute(levelA_count_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
+            levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, job.blk_counts.p, job.tile_off[si].p, job.ids[si].p);
+        }
+        ctx->launches++;
+    }
+    SG_CUDA(cudaGetLastError());
+    levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(job.blk_counts.p, PA_all, G, job.part_total_all.p);
+    ctx->launches++;
+    SG_CUDA(cudaMemcpyAsync(job.h_part.data(), job.part_total_all.p, (size_t)PA_all * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    ctx->times.extract_count += tm.stop();
+    tr.mark("A1 count+totals");
+}
+
+// Scatter the records of buckets [b_lo, b_hi) into X, CTA-major (see `Pieces`): CTA g of the level-A grid owns one contiguous
+// region, partitioned inside. pbase_buf ([G][PA], caller-owned) receives the first record of every (CTA, partition) piece.
+// I_pass / total_records only steer the number of partition sub-ranges.
+template <int NW, class Src>
+static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t I_pass, uint64_t total_records, uint64_t *X, uint64_t *pbase_buf,
+                           Pieces &pcs, Timer &tm, Trace &tr) {
+    Ctx *ctx = job.ctx;
+    cudaStream_t st = ctx->stream;
+    const int G = job.G;
+    const uint32_t PA_all = job.PA_all;
+    const uint32_t p_lo = (uint32_t)(b_lo - job.s_lo) << job.rA;
+    LevelA pa;
+    pa.K = job.K; pa.B = (uint32_t)job.B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = job.rA; pa.PA = (uint32_t)(b_hi - b_lo) << job.rA;
+    const uint32_t PA = pa.PA;
+    SG_CHECK(PA >= 1 && PA <= (uint32_t)kLevelAMaxParts && G <= kMaxPieces, 6, "internal: level-A pass geometry");
+    DArr<uint64_t> base(ctx, (size_t)G * PA);
+    {
+        DArr<uint64_t> row_total(ctx, (size_t)G + 1), row_start(ctx, (size_t)G + 1);
+        SG_CUDA(cudaMemsetAsync(row_total.p + G, 0, 8, st));
+        stage_rows_k<<<G, 256, 0, st>>>(job.blk_counts.p + p_lo, PA_all, PA, base.p, row_total.p);
+        exclusive_scan_u64(ctx, row_total.p, row_start.p, (size_t)G + 1);
+        stage_add_k<<<div_up((int64_t)G * PA, 256), 256, 0, st>>>(base.p, row_start.p, PA, G);
+        ctx->launches += 2;
+        SG_CUDA(cudaMemcpyAsync(pbase_buf, base.p, (size_t)G * PA * 8, cudaMemcpyDeviceToDevice, st));   // the scatter advances `base`
+    }
+    pcs.pbase = pbase_buf; pcs.cnt = job.blk_counts.p + p_lo; pcs.cnt_stride = PA_all; pcs.PA = PA; pcs.G = G;
+    tm.start();
+    if (job.roll) {
+        if constexpr (std::is_same<Src, ReadsSrc>::value) {
+            const size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // partition sub-ranges (only with the id array, where a foreign window costs just the roll): fewer lines and pages open
+            // per CTA. A sub-range costs one more roll over ALL windows of the source: worth it when the pass holds most of the job's
+            // records (measured: 20 M reads / 1 pass: 46.5 / 36.7 / 31.5 ms with 1 / 2 / 4 sub-ranges; 100 M reads / 5 passes: 184 ms
+            // with 1, 353 ms with 2)
+            int nsub_auto = (int)(4.0 * (double)I_pass / (double)std::max<uint64_t>(1, total_records) + 0.5);
+            nsub_auto = std::min(4, std::max(1, nsub_auto));
+            uint32_t nsub = job.use_ids ? (uint32_t)(tuning().a_sub ? tuning().a_sub : nsub_auto) : 1u;
+            if (nsub > PA) nsub = PA;
+            for (uint32_t sb = 0; sb < nsub; ++sb) {
+                const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
+                if (q_hi == q_lo) continue;
+                LevelA pa_sub = pa;
+                pa_sub.PA = q_hi - q_lo;
+                const size_t smem_sub = (size_t)pa_sub.PA * (sizeof(uint64_t) + sizeof(uint32_t));
+                for (size_t si = 0; si < job.srcs.size(); ++si) {
+                    const Src &src = job.srcs[si];
+                    if (src.n == 0) continue;
+                    if (job.use_ids)
+                        levelA_scatter_roll_k<NW, true><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X, job.tile_off[si].p, job.ids[si].p, p_lo + q_lo, PA, q_lo);
+                    else
+                        levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X, nullptr, nullptr, 0u, PA, 0u);
+                    ctx->launches++;
+                }
+            }
+        }
+    } else {
+        const size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+        SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (size_t si = 0; si < job.srcs.size(); ++si) {
+            const Src &src = job.srcs[si];
+            if (src.n == 0) continue;
+            levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X, job.use_ids ? job.tile_off[si].p : nullptr,
+                                                                 job.use_ids ? job.ids[si].p : nullptr, p_lo);
+            ctx->launches++;
+        }
+    }
+    SG_CUDA(cudaGetLastError());
+    ctx->times.extract_scatter += tm.stop();       // synchronises: `base` may go out of scope
+    tr.mark("A2 scatter");
+}
+
+// what one pass needs next to what is already resident: X + Y + its own output (distinct/instances <= 0.6 assumed, checked
+// against the arena when the output is allocated)
+static double pass_bytes_needed(uint64_t recs, size_t W) { return (double)recs * W * 2.0 + (double)recs * (W + 4) * 0.6 + (64 << 20); }
+
+template <int NW, class Src>
+static void run_count(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool want_counts, bool double_selfrc, uint64_t est_records, KSet *out) {
     const int total_bits = 2 * K;
-    // one CTA per SM and a modest fan-out: every (CTA, partition) pair is an open write stream whose current
-    // 128-byte line must survive in L2 until it is full (148 x 2048 x 128 B = 39 MB of the 126 MB L2)
-    const int G = getenv("SGPU_A_CTAS_PER_SM") ? ctx->num_sms * atoi(getenv("SGPU_A_CTAS_PER_SM")) : ctx->num_sms * 2;
-    const uint32_t PA_MAX = getenv("SGPU_PA_MAX") ? (uint32_t)atoi(getenv("SGPU_PA_MAX")) : 4096;
     const size_t W = 8 * NW;
     cudaStream_t st = ctx->stream;
     Timer tm(st);
     Trace tr(st);
     constexpr bool kIsReads = std::is_same<Src, ReadsSrc>::value;
-    bool roll = false;
-    if constexpr (kIsReads) roll = use_roll() && !srcs.empty() && !srcs[0].both;
 
     out->bsz.assign(B, 0);
     DArr<unsigned long long> d_bsz(ctx, B);
@@ -1514,242 +1511,69 @@ static void run_count_chunks(Ctx *ctx, const std::vector<Src> &srcs, int K, int 
 
     // ---- level-A geometry for the whole job. Partition id = (bucket, top rA key bits). ONE histogram pass over the
     // source serves every bucket-group pass (the groups are contiguous partition ranges), so a multi-pass job hashes
-    // the source npass+1 times instead of 2*npass times, and passes are planned from exact per-bucket record counts.
-    int rA = 0;
-    {
-        int want = ilog2_floor(est_records / TARGET + 1) + 1;               // total fan-out bits wanted
-        int bbits = ilog2_floor((uint64_t)B) + (((1u << ilog2_floor((uint64_t)B)) < (uint32_t)B) ? 1 : 0);
-        rA = want - bbits;
-        if (rA < 0) rA = 0;
-        while (rA > 0 && ((uint64_t)B << rA) > PA_MAX) --rA;
-        if (rA > total_bits) rA = total_bits;
-        if (rA > 24) rA = 24;
-    }
-    const int SR = 8192 >> rA;                 // buckets per histogram super-range (shared-memory histogram <= 8192 bins)
+    // the source once, and passes are planned from exact per-bucket record counts.
+    const int rA = levelA_key_bits(est_records, B, total_bits, sort_target<NW>(), tuning().pa_max);
+    const int SR = std::max(1, kLevelAMaxParts >> rA);      // buckets per histogram super-range
     int64_t first = 0;
     for (int s_lo = 0; s_lo < B; s_lo += SR) {
-    const int s_hi = std::min(B, s_lo + SR);
-    LevelA pa_all;
-    pa_all.K = K; pa_all.B = (uint32_t)B; pa_all.b_lo = (uint32_t)s_lo; pa_all.b_hi = (uint32_t)s_hi; pa_all.rA = rA;
-    pa_all.PA = (uint32_t)(s_hi - s_lo) << rA;
-    const uint32_t PA_all = pa_all.PA;
-    DArr<uint32_t> blk_counts(ctx, (size_t)G * PA_all);
-    DArr<uint64_t> part_total_all(ctx, (size_t)PA_all + 1);
-    std::vector<uint64_t> h_part(PA_all);
-    SG_CUDA(cudaMemsetAsync(blk_counts.p, 0, blk_counts.bytes(), st));
-    // per-record partition ids (2 bytes per record), only worth it when it fits comfortably
-    std::vector<DArr<uint64_t>> tile_off(srcs.size());
-    std::vector<DArr<uint16_t>> ids(srcs.size());
-    const bool use_ids = PA_all < 0xffffu && !getenv("SGPU_NO_IDS") && (double)est_records * 2.0 < (double)ctx->free_bytes() * 0.15;
-    if (use_ids) {
-        for (size_t si = 0; si < srcs.size(); ++si) {
-            const Src &src = srcs[si];
-            if (src.n == 0) continue;
-            const int64_t ntiles = (src.n + kATile - 1) / kATile;
-            DArr<uint32_t> ttot(ctx, (size_t)ntiles + 1);
-            tile_off[si].alloc(ctx, (size_t)ntiles + 1);
-            if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));      // this source is still being uploaded
-            SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
-            if (roll) {
-                if constexpr (kIsReads) roll_tile_ids_k<<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p);
-            } else {
-                tile_totals_k<Src><<<div_up(ntiles, 8), 256, 0, st>>>(src, ntiles, ttot.p, 8u);
-            }
-            ctx->launches++;
-            exclusive_scan_u32_to_u64(ctx, ttot.p, tile_off[si].p, (size_t)ntiles + 1);
-            uint64_t nrec_src = 0;
-            if (src_records && !roll) nrec_src = (*src_records)[si] + 8ull * (uint64_t)ntiles;   // known on the host (+ row padding): no sync, the upload keeps overlapping
-            else {
-                SG_CUDA(cudaMemcpyAsync(&nrec_src, tile_off[si].p + ntiles, 8, cudaMemcpyDeviceToHost, st));
-                SG_CUDA(cudaStreamSynchronize(st));
-            }
-            ids[si].alloc(ctx, (size_t)nrec_src + 2);
-        }
-    }
-    tm.start();
-    for (size_t si = 0; si < srcs.size(); ++si) {
-        const Src &src = srcs[si];
-        if (src.n == 0) continue;
-        if (ready) SG_CUDA(cudaStreamWaitEvent(st, (*ready)[si], 0));
-        if (roll) {
-            if constexpr (kIsReads) {
-                SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
-                levelA_count_roll_k<NW><<<G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
-            }
-        } else {
-            levelA_count_k<NW, Src><<<G, kAThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, blk_counts.p, tile_off[si].p, ids[si].p);
-        }
-        ctx->launches++;
-    }
-    SG_CUDA(cudaGetLastError());
-    levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(blk_counts.p, PA_all, G, part_total_all.p);
-    ctx->launches++;
-    SG_CUDA(cudaMemcpyAsync(h_part.data(), part_total_all.p, (size_t)PA_all * 8, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
-    ctx->times.extract_count += tm.stop();
-    tr.mark("A1 count+totals");
-    // bucket-group passes: simulate the greedy "as many whole buckets as fit" plan to learn how many passes are needed, then
-    // aim for equally sized passes (a tiny last pass still costs a full scan of the source, and equal sizes let the caching
-    // allocator reuse the X / Y blocks)
-    auto bucket_records = [&](int b) {
-        uint64_t ib = 0;
-        for (uint32_t q = 0; q < (1u << rA); ++q) ib += h_part[((size_t)(b - s_lo) << rA) + q];
-        return ib;
-    };
-    auto bytes_needed = [&](uint64_t recs) { return (double)recs * W * 2.0 + (double)recs * (W + 4) * 0.6 + (64 << 20); };
-    auto current_limit = [&]() {
-        return ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(ctx->free_bytes() * 0.90);
-    };
-    uint64_t total_records = 0;
-    for (int b = s_lo; b < s_hi; ++b) total_records += bucket_records(b);
-    uint64_t pass_target = total_records;
-    {
-        double lim_sim = (double)current_limit();
-        int npass_sim = 0, b = s_lo;
-        while (b < s_hi) {
-            uint64_t I = 0; int b0 = b;
-            while (b < s_hi) {
-                uint64_t ib = bucket_records(b);
-                if (b > b0 && bytes_needed(I + ib) > lim_sim) break;
-                I += ib; ++b;
-                if ((uint32_t)(b - b0) << rA >= 8192u) break;
-            }
-            lim_sim -= (double)I * (W + 4) * 0.5;            // this pass's output stays resident
-            ++npass_sim;
-        }
-        pass_target = total_records / (uint64_t)npass_sim + total_records / 64 + 1;
-    }
-    int b_lo = s_lo;
-    while (b_lo < s_hi) {
-        // ---- plan this pass: whole buckets that fit next to what is already resident (X + Y + its own output)
-        size_t lim = current_limit();
-        int b_hi = b_lo;
-        uint64_t I = 0;
-        while (b_hi < s_hi) {
-            uint64_t ib = bucket_records(b_hi);
-            if (b_hi > b_lo && (bytes_needed(I + ib) > (double)lim || I + ib > pass_target)) break;
-            I += ib; ++b_hi;
-            if ((uint32_t)(b_hi - b_lo) << rA >= 8192u) break;
-        }
-        const uint32_t nb = (uint32_t)(b_hi - b_lo);
-        const uint32_t p_lo = (uint32_t)(b_lo - s_lo) << rA;
-        LevelA pa;
-        pa.K = K; pa.B = (uint32_t)B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = rA; pa.PA = nb << rA;
-        const uint32_t PA = pa.PA;
-        const uint64_t *part_total_p = part_total_all.p + p_lo;
-        DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1);
-        SG_CUDA(cudaMemcpyAsync(part_total.p, part_total_p, (size_t)PA * 8, cudaMemcpyDeviceToDevice, st));
-        SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
-        exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
-        ctx->times.passes++;
-        ctx->times.instances += I;
-        // ---- A2: scatter
-        DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
-        tr.mark("alloc X,Y");
-        // CTA-major staging (see `Pieces`): level A writes every CTA's records into the CTA's own region of X, the first
-        // refinement round gathers the partitions into Y
-        // (the first-generation kernels write wherever `base` points, so staging also works for the (k+1)-mer source and the
-        // all-windows mode: SGPU_STAGE_ALL=1, opt-in until it has run on the GPU)
-        const bool stage_all = getenv("SGPU_STAGE_ALL") && atoi(getenv("SGPU_STAGE_ALL")) != 0 && !getenv("SGPU_SCATTER2");
-        const bool stage = ((roll && use_ids) || stage_all) && use_stage() && G <= kMaxPieces;
-        DArr<uint64_t> pbase;
-        Pieces pcs;
+        LevelAJob<NW, Src> job;
+        job.ctx = ctx; job.srcs = srcs; job.K = K; job.B = B; job.rA = rA; job.G = ctx->num_sms * 2;
+        job.s_lo = s_lo; job.s_hi = std::min(B, s_lo + SR);
+        job.PA_all = (uint32_t)(job.s_hi - job.s_lo) << rA;
+        if constexpr (kIsReads) job.roll = !srcs.empty() && !srcs[0].both;
+        levelA_count(job, est_records, tm, tr);
+        // bucket-group passes: simulate the greedy "as many whole buckets as fit" plan to learn how many passes are needed, then
+        // aim for equally sized passes (a tiny last pass still costs a full scan of the source)
+        auto current_limit = [&]() {
+            return ctx->hbm_budget ? (ctx->hbm_budget > ctx->allocated ? ctx->hbm_budget - ctx->allocated : 0) : (size_t)(ctx->free_bytes() * 0.90);
+        };
+        uint64_t total_records = 0;
+        for (int b = job.s_lo; b < job.s_hi; ++b) total_records += job.bucket_records(b);
+        uint64_t pass_target = total_records;
         {
-            DArr<uint64_t> base(ctx, (size_t)G * PA);
-            if (stage) {
-                DArr<uint64_t> row_total(ctx, (size_t)G + 1), row_start(ctx, (size_t)G + 1);
-                SG_CUDA(cudaMemsetAsync(row_total.p + G, 0, 8, st));
-                stage_rows_k<<<G, 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, base.p, row_total.p);
-                exclusive_scan_u64(ctx, row_total.p, row_start.p, (size_t)G + 1);
-                stage_add_k<<<div_up((int64_t)G * PA, 256), 256, 0, st>>>(base.p, row_start.p, PA, G);
-                ctx->launches += 2;
-                pbase.alloc(ctx, (size_t)G * PA);
-                SG_CUDA(cudaMemcpyAsync(pbase.p, base.p, (size_t)G * PA * 8, cudaMemcpyDeviceToDevice, st));   // the scatter advances `base`
-                pcs.pbase = pbase.p; pcs.cnt = blk_counts.p + p_lo; pcs.cnt_stride = PA_all; pcs.PA = PA; pcs.G = G;
-            } else {
-                levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(blk_counts.p + p_lo, PA_all, PA, G, part_start.p, base.p);
-                ctx->launches++;
-            }
-            tm.start();
-            if (use_ids && !roll && getenv("SGPU_SCATTER2")) {   // coalesced-flush kernel: opt-in. Correct, full-sector stores, but measured slower than the direct scatter
-                // sub-ranges of <= kA2MaxParts partitions; each is one launch per source over the 2-byte ids
-                const size_t smem2 = (size_t)kA2Cap * NW * 8 + (size_t)kA2MaxParts * 8 + ((size_t)2 * kA2MaxParts + 1) * 4 + (size_t)2 * kA2Cap * 2 + 16;
-                SG_CUDA(cudaFuncSetAttribute(levelA_scatter2_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                const uint32_t sub_max = getenv("SGPU_A2_PARTS") ? (uint32_t)atoi(getenv("SGPU_A2_PARTS")) : 1024u;
-                const uint32_t nsub = (PA + sub_max - 1) / sub_max;
-                for (uint32_t sb = 0; sb < nsub; ++sb) {
-                    const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
-                    if (q_hi == q_lo) continue;
-                    // base rows are [G][PA]: the kernel addresses row g at base + g*PA_sub, so give it a compacted copy
-                    DArr<uint64_t> sub_base(ctx, (size_t)G * (q_hi - q_lo));
-                    SG_CUDA(cudaMemcpy2DAsync(sub_base.p, (size_t)(q_hi - q_lo) * 8, base.p + q_lo, (size_t)PA * 8, (size_t)(q_hi - q_lo) * 8, (size_t)G,
-                                              cudaMemcpyDeviceToDevice, st));
-                    for (size_t si = 0; si < srcs.size(); ++si) {
-                        const Src &src = srcs[si];
-                        if (src.n == 0) continue;
-                        levelA_scatter2_k<NW, Src><<<G, kA2Threads, smem2, st>>>(src, K, sub_base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, q_hi - q_lo);
-                        ctx->launches++;
-                    }
+            double lim_sim = (double)current_limit();
+            int npass_sim = 0, b = job.s_lo;
+            while (b < job.s_hi) {
+                uint64_t I = 0; const int b0 = b;
+                while (b < job.s_hi) {
+                    const uint64_t ib = job.bucket_records(b);
+                    if (b > b0 && pass_bytes_needed(I + ib, W) > lim_sim) break;
+                    I += ib; ++b;
                 }
-            } else if (roll) {
-                if constexpr (kIsReads) {
-                    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
-                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    // sector pairing (pair_mailbox.cuh): opt-in until measured on the GPU; 16-byte records only, and only while the
-                    // mailboxes of a sub-range fit next to two resident CTAs
-                    const bool want_pair = NW == 2 && use_ids && getenv("SGPU_PAIR") && atoi(getenv("SGPU_PAIR")) != 0;
-                    const size_t pair_bytes = sizeof(uint64_t) + sizeof(uint32_t) + (size_t)kPmDepth * sizeof(PmBox);
-                    if (want_pair) SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 * pair_bytes)));
-                    // partition sub-ranges (only with the id array, where a foreign window costs just the roll): fewer lines and pages open per CTA
-                    // a sub-range costs one more roll over ALL windows of the source and pays per record written: worth it when the pass
-                    // holds most of the job's records (measured: 20 M reads / 1 pass: 46.5 / 36.7 / 31.5 ms with 1 / 2 / 4 sub-ranges;
-                    // 100 M reads / 5 passes: 184 ms with 1, 353 ms with 2)
-                    int nsub_auto = (int)(4.0 * (double)I / (double)std::max<uint64_t>(1, total_records) + 0.5);
-                    nsub_auto = std::min(4, std::max(1, nsub_auto));
-                    uint32_t nsub = use_ids ? (uint32_t)std::max(1, getenv("SGPU_A_SUB") ? atoi(getenv("SGPU_A_SUB")) : nsub_auto) : 1u;
-                    if (NW == 2 && use_ids && getenv("SGPU_PAIR") && atoi(getenv("SGPU_PAIR")) != 0 && !getenv("SGPU_A_SUB"))
-                        nsub = std::max(nsub, (PA + 1023u) / 1024u);          // the pairing variant holds mailboxes for <= 1024 partitions
-                    if (nsub > PA) nsub = PA;
-                    for (uint32_t sb = 0; sb < nsub; ++sb) {
-                        const uint32_t q_lo = (uint32_t)((uint64_t)PA * sb / nsub), q_hi = (uint32_t)((uint64_t)PA * (sb + 1) / nsub);
-                        LevelA pa_sub = pa;
-                        pa_sub.PA = q_hi - q_lo;
-                        const size_t smem_sub = (size_t)pa_sub.PA * (sizeof(uint64_t) + sizeof(uint32_t));
-                        for (size_t si = 0; si < srcs.size(); ++si) {
-                            const Src &src = srcs[si];
-                            if (src.n == 0) continue;
-                            if (use_ids && want_pair && pa_sub.PA <= 1024u)
-                                levelA_scatter_roll_k<NW, true, true><<<G, kRollThreads, pa_sub.PA * pair_bytes, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo,
-                                                                                                       (getenv("SGPU_PREFETCH") && atoi(getenv("SGPU_PREFETCH"))) ? 1u : 0u);
-                            else if (use_ids) levelA_scatter_roll_k<NW, true, false><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X.p, tile_off[si].p, ids[si].p, p_lo + q_lo, PA, q_lo, 0u);
-                            else levelA_scatter_roll_k<NW, false, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X.p, nullptr, nullptr, 0u, PA, 0u, 0u);
-                            ctx->launches++;
-                        }
-                    }
-                }
-            } else {
-            size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
-            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            for (size_t si = 0; si < srcs.size(); ++si) {
-                const Src &src = srcs[si];
-                if (src.n == 0) continue;
-                levelA_scatter_k<NW, Src><<<G, kAThreads, smem, st>>>(src, pa, base.p, X.p, tile_off[si].p, ids[si].p, p_lo);
-                ctx->launches++;
+                lim_sim -= (double)I * (W + 4) * 0.5;            // this pass's output stays resident
+                ++npass_sim;
             }
-            }
-            SG_CUDA(cudaGetLastError());
-            ctx->times.extract_scatter += tm.stop();
-            tr.mark("A2 scatter");
+            pass_target = total_records / (uint64_t)npass_sim + total_records / 64 + 1;
         }
-        Chunk ch;
-        sort_pass<NW>(ctx, K, X, Y, part_start.p, part_total.p, PA, rA, (uint32_t)b_lo, b_hi, first, want_counts, double_selfrc, d_bsz.p, ch, tm, tr,
-                      stage ? &pcs : nullptr);
-        first += ch.n;
-        out->chunks.push_back(std::move(ch));
-        b_lo = b_hi;
-        tr.mark("pass end (before frees)");
-    }
+        int b_lo = job.s_lo;
+        while (b_lo < job.s_hi) {
+            // ---- plan this pass: whole buckets that fit next to what is already resident (X + Y + its own output)
+            const size_t lim = current_limit();
+            int b_hi = b_lo;
+            uint64_t I = 0;
+            while (b_hi < job.s_hi) {
+                const uint64_t ib = job.bucket_records(b_hi);
+                if (b_hi > b_lo && (pass_bytes_needed(I + ib, W) > (double)lim || I + ib > pass_target)) break;
+                I += ib; ++b_hi;
+            }
+            const uint32_t p_lo = (uint32_t)(b_lo - job.s_lo) << rA;
+            const uint32_t PA = (uint32_t)(b_hi - b_lo) << rA;
+            DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1);
+            SG_CUDA(cudaMemcpyAsync(part_total.p, job.part_total_all.p + p_lo, (size_t)PA * 8, cudaMemcpyDeviceToDevice, st));
+            SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
+            exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
+            ctx->times.passes++;
+            ctx->times.instances += I;
+            DArr<uint64_t> X(ctx, (size_t)I * NW + 2), Y(ctx, (size_t)I * NW + 2);
+            DArr<uint64_t> pbase(ctx, (size_t)job.G * PA);
+            Pieces pcs;
+            levelA_scatter(job, b_lo, b_hi, I, total_records, X.p, pbase.p, pcs, tm, tr);
+            Chunk ch;
+            sort_pass<NW>(ctx, K, X, Y, part_start.p, part_total.p, PA, rA, (uint32_t)b_lo, b_hi, first, want_counts, double_selfrc, d_bsz.p, ch, tm, tr, &pcs);
+            first += ch.n;
+            out->chunks.push_back(std::move(ch));
+            b_lo = b_hi;
+        }
     }
     std::vector<unsigned long long> hb(B);
     SG_CUDA(cudaMemcpyAsync(hb.data(), d_bsz.p, B * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1770,6 +1594,26 @@ __global__ void count_windows_k(const uint32_t *__restrict__ lens, int64_t n, in
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+// windows of the context's read set (exact), for the level-A geometry
+static uint64_t count_windows(Ctx *ctx, int K) {
+    DArr<unsigned long long> d_w(ctx, 1);
+    SG_CUDA(cudaMemsetAsync(d_w.p, 0, 8, ctx->stream));
+    if (ctx->n_reads) {
+        count_windows_k<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_lens, ctx->n_reads, K, d_w.p);
+        ctx->launches++;
+    }
+    unsigned long long wn = 0;
+    SG_CUDA(cudaMemcpyAsync(&wn, d_w.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (uint64_t)wn;
+}
+
+static ReadsSrc reads_source(Ctx *ctx, int K, bool both) {
+    ReadsSrc src;
+    src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = both;
+    return src;
+}
+
 template <int NW>
 static KSet *count_reads_nw(Ctx *ctx, int K, int B, int mode) {
     ensure_reads_on_device(ctx);
@@ -1777,37 +1621,9 @@ static KSet *count_reads_nw(Ctx *ctx, int K, int B, int mode) {
     ks->ctx = ctx; ks->K = K; ks->nw = NW; ks->B = B; ks->has_counts = (mode == kCanonical);
     try {
         const bool both = (mode == kAllWindows);
-        if (!ctx->up_chunks.empty()) {
-            // reads are arriving from the host in chunks (sgpu_reads_upload): one source per chunk; each chunk's histogram pass
-            // starts as soon as its copy has landed, so the H2D transfer overlaps the first pass over the reads
-            std::vector<ReadsSrc> srcs;
-            std::vector<cudaEvent_t> ready;
-            std::vector<uint64_t> recs;
-            uint64_t total = 0;
-            for (const UploadChunk &c : ctx->up_chunks) {
-                ReadsSrc src;
-                src.words = ctx->d_words; src.offs = ctx->d_offs + c.r0; src.lens = ctx->d_lens + c.r0; src.n = c.r1 - c.r0; src.K = K; src.both = both;
-                uint64_t w = c.sum_long >= c.n_long * (uint64_t)(K - 1) ? c.sum_long - c.n_long * (uint64_t)(K - 1) : 0;
-                for (int l = K; l < 256; ++l) w += (uint64_t)c.hist[l] * (uint64_t)(l - K + 1);
-                w *= both ? 2 : 1;
-                srcs.push_back(src); ready.push_back(c.ev); recs.push_back(w); total += w;
-            }
-            run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), total, ks, &ready, &recs);
-        } else {
-        DArr<unsigned long long> d_w(ctx, 1);
-        SG_CUDA(cudaMemsetAsync(d_w.p, 0, 8, ctx->stream));
-        if (ctx->n_reads) {
-            count_windows_k<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_lens, ctx->n_reads, K, d_w.p);
-            ctx->launches++;
-        }
-        unsigned long long wn = 0;
-        SG_CUDA(cudaMemcpyAsync(&wn, d_w.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        SG_CUDA(cudaStreamSynchronize(ctx->stream));
-        ReadsSrc src;
-        src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = both;
-        std::vector<ReadsSrc> srcs{src};
-        run_count_chunks<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), (uint64_t)wn * (both ? 2 : 1), ks);
-        }
+        const uint64_t wn = count_windows(ctx, K);
+        std::vector<ReadsSrc> srcs{reads_source(ctx, K, both)};
+        run_count<NW, ReadsSrc>(ctx, srcs, K, B, mode == kCanonical, mode == kCanonical && (K % 2 == 0), wn * (both ? 2 : 1), ks);
     } catch (...) { delete ks; throw; }
     return ks;
 }
@@ -1835,13 +1651,14 @@ static KSet *kmers_from_kpomers_nw(Ctx *ctx, const KSet *kp, int B) {
             KpomerSrc<NWS> s; s.keys = c.keys.p; s.n = c.n; s.K = K;
             srcs.push_back(s);
         }
-        run_count_chunks<NW, KpomerSrc<NWS>>(ctx, srcs, K, B, false, false, (uint64_t)kp->n * 2, ks);
+        run_count<NW, KpomerSrc<NWS>>(ctx, srcs, K, B, false, false, (uint64_t)kp->n * 2, ks);
     } catch (...) { delete ks; throw; }
     return ks;
 }
 
 KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B) {
     SG_CHECK(kp->K >= 2, 2, "source k-mers too short");
+    SG_CHECK(B >= 1 && B <= (1 << 20), 2, "num_buckets must be in [1, 2^20]");
     const int K = kp->K - 1;
     const int nw = nwords_of(K), nws = kp->nw;
     ctx->times = PhaseTimes();
@@ -1855,16 +1672,53 @@ KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B) {
     throw Error(2, "unsupported k-mer word combination");
 }
 
+// checksums of a counted set (bench / multi-GPU self check): out = { n, sum of all key words, xor of all key words rotated by
+// their word index, sum of multiplicities } -- order independent, so per-rank values of disjoint bucket sets add / xor up
+__global__ void kset_checksum_k(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t n, int nw,
+                                unsigned long long *__restrict__ out) {
+    unsigned long long s = 0, x = 0, c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        for (int q = 0; q < nw; ++q) {
+            const unsigned long long w = keys[i * nw + q];
+            s += w * (unsigned long long)(2 * q + 1);
+            x ^= (w << (7 * q + 1)) | (w >> (64 - (7 * q + 1)));
+        }
+        if (counts) c += counts[i];
+    }
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        x ^= __shfl_down_sync(0xffffffffu, x, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[1], s); atomicXor(&out[2], x); atomicAdd(&out[3], c); }
+}
+void kset_checksum(const KSet *ks, uint64_t *out4) {
+    Ctx *ctx = ks->ctx;
+    DArr<unsigned long long> d(ctx, 4);
+    SG_CUDA(cudaMemsetAsync(d.p, 0, 32, ctx->stream));
+    for (const Chunk &c : ks->chunks) {
+        if (c.n == 0) continue;
+        kset_checksum_k<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(c.keys.p, ks->has_counts ? c.counts.p : nullptr, (uint64_t)c.n, ks->nw, d.p);
+        ctx->launches++;
+    }
+    SG_CUDA(cudaGetLastError());
+    unsigned long long h[4];
+    SG_CUDA(cudaMemcpyAsync(h, d.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(cudaStreamSynchronize(ctx->stream));
+    out4[0] = (uint64_t)ks->n; out4[1] = h[1]; out4[2] = h[2]; out4[3] = h[3];
+}
 
 // ------------------------------------------------------------------------------------------------------------
-// multi-GPU count. Buckets are the unit of independence (KMerSegmentPolicy is a pure function of the k-mer),
-// so every bucket has one owner GPU. Each rank histograms its own read shard once; the per-partition totals are
-// all-gathered (host plumbing, torch.distributed). Per pass every rank partitions its shard into a local staging buffer
-// (partition-major), and then ONE kernel on the owner does the exchange AND the merge: it pulls every (source rank,
-// partition) piece out of the sources' staging buffers through NVLink peer mappings (cudaIpc) with coalesced 16-byte
-// loads and lays the pieces of a partition next to each other, ready for the ordinary refinement / local sort /
-// compaction. (A first version pushed each 16-byte record to its owner from inside the partition kernel; remote
-// scattered stores are not write-combined and ran at ~1 GB/s.)
+// multi-GPU count (replaces projects/hpcspades/mpi/stages/construction_mpi.cpp:222-300). Buckets are the unit of
+// independence (KMerSegmentPolicy is a pure function of the k-mer), so every bucket has one owner GPU. Each rank histograms its
+// own read shard once with the same rolling kernel as the single-GPU count (2-byte partition ids included); the per-partition
+// totals are all-gathered (host plumbing, torch.distributed). Per pass every rank scatters its shard's records of the pass's
+// buckets into a local staging buffer (CTA-major pieces, like the single-GPU count), and then ONE kernel on the owner does the
+// exchange AND the merge: it pulls every (source rank, level-A CTA, partition) piece out of the sources' staging buffers through
+// NVLink peer mappings (cudaIpc: every rank maps the peers' memory ARENAS once per process; buffers are offsets inside them) with
+// coalesced 16-byte loads and lays the pieces of a partition next to each other, ready for the ordinary refinement / local sort
+// / compaction. (A first version pushed each 16-byte record to its owner from inside the partition kernel; remote scattered
+// stores are not write-combined and ran at ~1 GB/s.)
 // ------------------------------------------------------------------------------------------------------------
 struct DistPlan {
     int world = 1, rank = 0, B = 0, rA = 0, npass = 1;
@@ -1881,39 +1735,26 @@ struct DistPlan {
     }
 };
 
+static const double kDistHeadroom = 1.05;      // staging / merged buffers are sized 5 % above the planned maximum
+
+// device bytes a plan with these maxima needs: staging buffer (doubles as ping-pong partner, so >= recv), merged buffer, the
+// outputs of all passes (distinct/instances <= 0.6 assumed) and the per-pass tables
+static double dist_plan_bytes(uint64_t mx, uint64_t ms, int np, size_t W, uint64_t fixed_bytes) {
+    return ((double)std::max(mx, ms) + (double)mx) * W * (kDistHeadroom + 0.05) + (double)mx * (W + 4) * 0.6 * np + (double)fixed_bytes;
+}
+
 // pure host function (also exported for the CPU/gloo tests): identical on every rank given the same inputs
-void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, size_t W) {
+void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, size_t W, uint64_t fixed_bytes) {
     pl.world = world; pl.rank = rank; pl.B = B; pl.rA = rA; pl.PA_all = (uint32_t)B << rA;
     pl.tot.assign(pl.PA_all, 0);
     for (int s = 0; s < world; ++s)
         for (uint32_t q = 0; q < pl.PA_all; ++q) pl.tot[q] += cnt_all[(size_t)s * pl.PA_all + q];
-    for (int np = 1;; ++np) {
+    auto evaluate = [&](int np) {
         pl.npass = np;
         pl.pass_b.assign(np + 1, 0);
         for (int p = 0; p <= np; ++p) pl.pass_b[p] = (int)((int64_t)B * p / np);
-        uint64_t mx = 0;
-        for (int p = 0; p < np; ++p)
-            for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
-        pl.max_recv = mx;
-        uint64_t ms = 0;
-        for (int p = 0; p < np; ++p)
-            for (int s = 0; s < world; ++s) {
-                uint64_t t = 0;
-                for (size_t q = (size_t)pl.pass_b[p] << rA; q < ((size_t)pl.pass_b[p + 1] << rA); ++q) t += cnt_all[(size_t)s * pl.PA_all + q];
-                ms = std::max(ms, t);
-            }
-        pl.max_send = ms;
-        // staging buffer (doubles as ping-pong partner) + merged buffer + output estimate must fit the budget
-        double need = (double)std::max(mx, ms) * W * 2.0 + (double)mx * (W + 4) * 0.6 * np + (256 << 20);
-        if (need <= (double)budget_bytes || np >= B || (uint32_t)(((B + np - 1) / np) << rA) <= 1u) break;
-    }
-    // a pass's partitions must also fit the scatter kernel's shared-memory tables
-    while ((((size_t)(B + pl.npass - 1) / pl.npass) << rA) > 8192 && pl.npass < B) {
-        ++pl.npass;
-        pl.pass_b.assign(pl.npass + 1, 0);
-        for (int p = 0; p <= pl.npass; ++p) pl.pass_b[p] = (int)((int64_t)B * p / pl.npass);
         uint64_t mx = 0, ms = 0;
-        for (int p = 0; p < pl.npass; ++p) {
+        for (int p = 0; p < np; ++p) {
             for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
             for (int s = 0; s < world; ++s) {
                 uint64_t t = 0;
@@ -1922,300 +1763,318 @@ void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint
             }
         }
         pl.max_recv = mx; pl.max_send = ms;
+    };
+    for (int np = 1;; ++np) {
+        evaluate(np);
+        // every pass must hold at least one bucket, and its partitions must fit the scatter kernel's shared-memory tables
+        const bool tables_fit = (((size_t)(B + np - 1) / np) << rA) <= (size_t)kLevelAMaxParts;
+        if (np >= B) break;
+        if (tables_fit && dist_plan_bytes(pl.max_recv, pl.max_send, np, W, fixed_bytes) <= (double)budget_bytes) break;
     }
 }
+
+struct PullSrc { const uint64_t *sbuf; const uint64_t *pbase; const uint32_t *blk; };     // one source rank, as seen from this GPU
 
 struct DistState {
     Ctx *ctx = nullptr;
     int K = 0, B = 0, mode = 0, nw = 0, G = 0;
     DistPlan plan;
-    DArr<uint32_t> blk_counts;               // G x PA_all (local)
-    DArr<uint64_t> part_total_local;         // PA_all
-    DArr<uint64_t> d_cnt_all;                // world x PA_all
-    DArr<uint64_t> sbuf, xbuf;               // staging buffer (peers read it; later the ping-pong partner) and the merged buffer
-    std::vector<uint64_t *> peer;            // world mapped staging buffers (own entry = sbuf.p)
-    std::vector<void *> peer_base;           // what cudaIpcOpenMemHandle returned (to close)
     std::vector<uint64_t> h_cnt_all;         // world x PA_all
+    DArr<uint64_t> sbuf, xbuf;               // staging buffer (peers read it; later the ping-pong partner) and the merged buffer
+    DArr<uint64_t> pbase;                    // [G][max partitions of a pass]: piece starts of the current pass (peers read it)
+    std::vector<PullSrc> peers;              // world entries (own entry = local pointers)
     DArr<unsigned long long> d_bsz;
     KSet *out = nullptr;
     int64_t first = 0;
-    ReadsSrc src;
     bool want_counts = false, double_selfrc = false;
+    virtual ~DistState() { delete out; }
+    virtual void begin() = 0;
+    virtual void local_counts(uint64_t *h_out) = 0;
+    virtual const uint32_t *blk_counts_ptr() = 0;
+    virtual void scatter(int p) = 0;
+    virtual void pull(int p) = 0;
+    virtual void sort(int p) = 0;
 };
 
-// exchange + merge in one kernel: the owner PULLS every (source rank, partition) piece out of the sources' staging buffers
-// through NVLink peer mappings with coalesced 16-byte loads and lays the pieces of a partition next to each other.
-struct PullPiece { const uint64_t *src; uint64_t dst; uint64_t n; };
+// exchange + merge in one kernel. Work item = (owned partition q, source rank s): the CTA fetches the source's G piece
+// descriptors (start in its staging buffer, record count) with one parallel remote read, then streams the pieces into the
+// merged buffer back to back with 16-byte loads over NVLink.
+static const int kPullThreads = 512;
 template <int NW>
-__global__ void __launch_bounds__(512) dist_pull_k(const PullPiece *__restrict__ pieces, uint64_t npieces, uint64_t *__restrict__ out,
-                                                   unsigned long long *__restrict__ work_counter) {
+__global__ void __launch_bounds__(kPullThreads) dist_pull_k(const PullSrc *__restrict__ srcs, int world, int G, uint32_t PA_all, uint32_t PAp, uint32_t pq0,
+                                                            uint32_t q0, uint32_t nq, const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ out,
+                                                            unsigned long long *__restrict__ work_counter) {
     __shared__ unsigned long long s_w;
+    __shared__ uint64_t p_start[kMaxPieces];      // source record index of piece g
+    __shared__ uint64_t p_dst[kMaxPieces + 1];    // destination record index of piece g (exclusive prefix of the counts)
+    __shared__ uint32_t wsum[kPullThreads / 32];
+    const uint64_t nwork = (uint64_t)nq * (uint64_t)world;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1ull);
         __syncthreads();
         const uint64_t w = s_w;
         __syncthreads();
-        if (w >= npieces) return;
-        const PullPiece pc = pieces[w];
-        const uint64_t nwords = pc.n * NW;
-        uint64_t *dst = out + pc.dst * NW;
-        if ((((uintptr_t)pc.src | (uintptr_t)dst) & 15) == 0) {
-            const ulonglong2 *s2 = reinterpret_cast<const ulonglong2 *>(pc.src);
-            ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst);
-            for (uint64_t i = threadIdx.x; i < nwords / 2; i += blockDim.x) d2[i] = s2[i];
-            if ((nwords & 1) && threadIdx.x == 0) dst[nwords - 1] = pc.src[nwords - 1];
-        } else {
-            for (uint64_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = pc.src[i];
+        if (w >= nwork) return;
+        const uint32_t q = q0 + (uint32_t)(w / (uint64_t)world);
+        const int s = (int)(w % (uint64_t)world);
+        const PullSrc ps = srcs[s];
+        // piece counts -> exclusive prefix (G <= kMaxPieces = 2 * kPullThreads: two per thread)
+        uint32_t c0 = 0, c1 = 0;
+        const int g0 = 2 * threadIdx.x;
+        if (g0 < G) { c0 = ps.blk[(size_t)g0 * PA_all + q]; p_start[g0] = ps.pbase[(size_t)g0 * PAp + (q - pq0)]; }
+        if (g0 + 1 < G) { c1 = ps.blk[(size_t)(g0 + 1) * PA_all + q]; p_start[g0 + 1] = ps.pbase[(size_t)(g0 + 1) * PAp + (q - pq0)]; }
+        uint32_t v = c0 + c1, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int x = 0; x < warp; ++x) wb += wsum[x];
+        const uint64_t d0 = dst_off[w] + (uint64_t)(wb + inc - v);
+        if (g0 < G) p_dst[g0] = d0;
+        if (g0 + 1 < G) p_dst[g0 + 1] = d0 + c0;
+        if (g0 + 2 >= G && g0 < G) p_dst[G] = d0 + v;      // the thread holding the last piece(s) also writes the end
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            const uint64_t n = p_dst[g + 1] - p_dst[g];
+            if (n == 0) continue;
+            const uint64_t *src = ps.sbuf + p_start[g] * NW;
+            uint64_t *dst = out + p_dst[g] * NW;
+            const uint64_t nwords = n * NW;
+            if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+                const ulonglong2 *s2 = reinterpret_cast<const ulonglong2 *>(src);
+                ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst);
+                const uint64_t n2 = nwords / 2;
+                uint64_t i = threadIdx.x;
+                for (; i + 3ull * kPullThreads < n2; i += 4ull * kPullThreads) {       // four loads in flight per thread
+                    const ulonglong2 a = s2[i], b = s2[i + kPullThreads], c = s2[i + 2 * kPullThreads], e = s2[i + 3 * kPullThreads];
+                    d2[i] = a; d2[i + kPullThreads] = b; d2[i + 2 * kPullThreads] = c; d2[i + 3 * kPullThreads] = e;
+                }
+                for (; i < n2; i += kPullThreads) d2[i] = s2[i];
+                if ((nwords & 1) && threadIdx.x == 0) dst[nwords - 1] = src[nwords - 1];
+            } else {
+                for (uint64_t i = threadIdx.x; i < nwords; i += kPullThreads) dst[i] = src[i];
+            }
+        }
+        __syncthreads();      // p_start / p_dst are rewritten by the next work item
     }
 }
 
 template <int NW>
-static void dist_begin_nw(DistState *d) {
-    Ctx *ctx = d->ctx;
-    cudaStream_t st = ctx->stream;
-    const uint32_t PA_all = d->plan.PA_all;
-    LevelA pa_all;
-    pa_all.K = d->K; pa_all.B = (uint32_t)d->B; pa_all.b_lo = 0; pa_all.b_hi = (uint32_t)d->B; pa_all.rA = d->plan.rA; pa_all.PA = PA_all;
-    d->blk_counts.alloc(ctx, (size_t)d->G * PA_all);
-    d->part_total_local.alloc(ctx, (size_t)PA_all + 1);
-    SG_CUDA(cudaMemsetAsync(d->blk_counts.p, 0, d->blk_counts.bytes(), st));
-    Timer tm(st);
-    tm.start();
-    // SGPU_DIST_ROLL=1 (opt-in until it has run on 2 GPUs): the rolling kernels in their id-less form (canonical mode only)
-    const bool dist_roll = getenv("SGPU_DIST_ROLL") && atoi(getenv("SGPU_DIST_ROLL")) != 0 && !d->src.both;
-    if (d->src.n) {
-        if (dist_roll) {
-            SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
-            levelA_count_roll_k<NW><<<d->G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
-        } else {
-            levelA_count_k<NW, ReadsSrc><<<d->G, kAThreads, PA_all * sizeof(uint32_t), st>>>(d->src, pa_all, d->blk_counts.p, nullptr, nullptr);
-        }
-        ctx->launches++;
+struct DistStateNW : DistState {
+    LevelAJob<NW, ReadsSrc> job;
+
+    void begin() override {
+        Timer tm(ctx->stream);
+        Trace tr(ctx->stream);
+        const uint64_t wn = count_windows(ctx, K);
+        job.ctx = ctx; job.K = K; job.B = B; job.rA = plan.rA; job.G = G;
+        job.srcs.assign(1, reads_source(ctx, K, mode == kAllWindows));
+        job.s_lo = 0; job.s_hi = B; job.PA_all = plan.PA_all;
+        job.roll = (mode == kCanonical);
+        levelA_count(job, wn * (mode == kAllWindows ? 2 : 1), tm, tr);
     }
-    levelA_totals_k<<<div_up(PA_all, 256), 256, 0, st>>>(d->blk_counts.p, PA_all, d->G, d->part_total_local.p);
-    ctx->launches++;
-    SG_CUDA(cudaGetLastError());
-    ctx->times.extract_count += tm.stop();
-}
+    void local_counts(uint64_t *h_out) override { memcpy(h_out, job.h_part.data(), (size_t)plan.PA_all * 8); }
+    const uint32_t *blk_counts_ptr() override { return job.blk_counts.p; }
 
-template <int NW>
-static void dist_scatter_nw(DistState *d, int p) {
-    // local partition of this rank's shard for the pass's buckets into the staging buffer (partition-major)
-    Ctx *ctx = d->ctx;
-    cudaStream_t st = ctx->stream;
-    const DistPlan &pl = d->plan;
-    const int b_lo = pl.pass_b[p], b_hi = pl.pass_b[p + 1];
-    const uint32_t p_lo = (uint32_t)b_lo << pl.rA, PA = (uint32_t)(b_hi - b_lo) << pl.rA;
-    DArr<uint64_t> part_total(ctx, PA + 1), part_start(ctx, PA + 1), base(ctx, (size_t)d->G * PA);
-    SG_CUDA(cudaMemcpyAsync(part_total.p, d->part_total_local.p + p_lo, (size_t)PA * 8, cudaMemcpyDeviceToDevice, st));
-    SG_CUDA(cudaMemsetAsync(part_total.p + PA, 0, 8, st));
-    exclusive_scan_u64(ctx, part_total.p, part_start.p, PA + 1);
-    levelA_bases_k<<<div_up(PA, 256), 256, 0, st>>>(d->blk_counts.p + p_lo, pl.PA_all, PA, d->G, part_start.p, base.p);
-    ctx->launches++;
-    LevelA pa;
-    pa.K = d->K; pa.B = (uint32_t)d->B; pa.b_lo = (uint32_t)b_lo; pa.b_hi = (uint32_t)b_hi; pa.rA = pl.rA; pa.PA = PA;
-    Timer tm(st);
-    tm.start();
-    size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
-    SG_CUDA(cudaFuncSetAttribute(levelA_scatter_k<NW, ReadsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool dist_roll = getenv("SGPU_DIST_ROLL") && atoi(getenv("SGPU_DIST_ROLL")) != 0 && !d->src.both;
-    if (d->src.n) {
-        if (dist_roll) {
-            SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            levelA_scatter_roll_k<NW, false, false><<<d->G, kRollThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u, PA, 0u, 0u);
-        } else {
-            levelA_scatter_k<NW, ReadsSrc><<<d->G, kAThreads, smem, st>>>(d->src, pa, base.p, d->sbuf.p, nullptr, nullptr, 0u);
+    void scatter(int p) override {
+        // local partition of this rank's shard for the pass's buckets into the staging buffer (CTA-major pieces)
+        Timer tm(ctx->stream);
+        Trace tr(ctx->stream);
+        const int b_lo = plan.pass_b[p], b_hi = plan.pass_b[p + 1];
+        uint64_t I = 0, total = 0;
+        for (uint32_t q = 0; q < plan.PA_all; ++q) {
+            const uint64_t c = h_cnt_all[(size_t)plan.rank * plan.PA_all + q];
+            total += c;
+            if (q >= ((uint32_t)b_lo << plan.rA) && q < ((uint32_t)b_hi << plan.rA)) I += c;
         }
-        ctx->launches++;
+        SG_CHECK((I * NW + 2) <= sbuf.n, 6, "internal: staging buffer smaller than the pass");
+        Pieces pcs;
+        levelA_scatter(job, b_lo, b_hi, I, total, sbuf.p, pbase.p, pcs, tm, tr);
+        SG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    SG_CUDA(cudaGetLastError());
-    ctx->times.extract_scatter += tm.stop();
-}
 
-template <int NW>
-static void dist_pull_nw(DistState *d, int p) {
-    Ctx *ctx = d->ctx;
-    cudaStream_t st = ctx->stream;
-    const DistPlan &pl = d->plan;
-    const int world = pl.world;
-    const size_t pass_q0 = (size_t)pl.pass_b[p] << pl.rA;
-    const size_t q0 = (size_t)pl.own_lo(p, pl.rank) << pl.rA, q1 = (size_t)pl.own_lo(p, pl.rank + 1) << pl.rA;
-    // every source's staging layout is partition-major over the whole pass: local_start_s[q] = sum_{q' in pass, q' < q} cnt[s][q']
-    std::vector<uint64_t> src_off(world, 0);
-    for (int s = 0; s < world; ++s)
-        for (size_t q = pass_q0; q < q0; ++q) src_off[s] += d->h_cnt_all[(size_t)s * pl.PA_all + q];
-    std::vector<PullPiece> pieces;
-    uint64_t dst = 0;
-    for (size_t q = q0; q < q1; ++q)
-        for (int s = 0; s < world; ++s) {
-            const uint64_t n = d->h_cnt_all[(size_t)s * pl.PA_all + q];
-            if (n) pieces.push_back(PullPiece{d->peer[s] + src_off[s] * NW, dst, n});
-            src_off[s] += n; dst += n;
-        }
-    if (pieces.empty()) return;
-    DArr<PullPiece> dp(ctx, pieces.size());
-    DArr<unsigned long long> wc(ctx, 1);
-    SG_CUDA(cudaMemcpyAsync(dp.p, pieces.data(), pieces.size() * sizeof(PullPiece), cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemsetAsync(wc.p, 0, 8, st));
-    Timer tm(st);
-    tm.start();
-    int grid = (int)std::min<uint64_t>(pieces.size(), (uint64_t)ctx->num_sms * 4);
-    dist_pull_k<NW><<<grid, 512, 0, st>>>(dp.p, pieces.size(), d->xbuf.p, wc.p);
-    ctx->launches++;
-    SG_CUDA(cudaGetLastError());
-    ctx->times.exchange += tm.stop();
-}
-
-template <int NW>
-static void dist_sort_nw(DistState *d, int p) {
-    Ctx *ctx = d->ctx;
-    cudaStream_t st = ctx->stream;
-    const DistPlan &pl = d->plan;
-    const int my_lo = pl.own_lo(p, pl.rank), my_hi = pl.own_lo(p, pl.rank + 1);
-    const uint32_t PA = (uint32_t)(my_hi - my_lo) << pl.rA;
-    const size_t Q0 = (size_t)my_lo << pl.rA;
-    std::vector<uint64_t> tot(PA + 1, 0), start(PA + 1, 0);
-    for (uint32_t q = 0; q < PA; ++q) { tot[q] = pl.tot[Q0 + q]; start[q + 1] = start[q] + tot[q]; }
-    ctx->times.passes++;
-    ctx->times.instances += start[PA];
-    Chunk ch;
-    if (PA) {
-        DArr<uint64_t> d_tot(ctx, PA + 1), d_start(ctx, PA + 1);
-        SG_CUDA(cudaMemcpyAsync(d_tot.p, tot.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(d_start.p, start.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
+    void pull(int p) override {
+        cudaStream_t st = ctx->stream;
+        const int world = plan.world;
+        const uint32_t pq0 = (uint32_t)plan.pass_b[p] << plan.rA;
+        const uint32_t PAp = (uint32_t)(plan.pass_b[p + 1] - plan.pass_b[p]) << plan.rA;
+        const uint32_t q0 = (uint32_t)plan.own_lo(p, plan.rank) << plan.rA, q1 = (uint32_t)plan.own_lo(p, plan.rank + 1) << plan.rA;
+        const uint32_t nq = q1 - q0;
+        if (nq == 0) return;
+        // destination of (q, s): partitions in order, inside a partition the sources in rank order
+        std::vector<uint64_t> dst_off((size_t)nq * world);
+        uint64_t run = 0;
+        for (uint32_t q = q0; q < q1; ++q)
+            for (int s = 0; s < world; ++s) {
+                dst_off[(size_t)(q - q0) * world + s] = run;
+                run += h_cnt_all[(size_t)s * plan.PA_all + q];
+            }
+        SG_CHECK(run * NW + 2 <= xbuf.n, 6, "internal: merged buffer smaller than the pass");
+        if (run == 0) return;
+        DArr<uint64_t> d_off(ctx, dst_off.size());
+        DArr<PullSrc> d_src(ctx, (size_t)world);
+        DArr<unsigned long long> wc(ctx, 1);
+        SG_CUDA(cudaMemcpyAsync(d_off.p, dst_off.data(), dst_off.size() * 8, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(d_src.p, peers.data(), (size_t)world * sizeof(PullSrc), cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemsetAsync(wc.p, 0, 8, st));
         Timer tm(st);
-        Trace tr(st);
-        sort_pass<NW>(ctx, d->K, d->xbuf, d->sbuf, d_start.p, d_tot.p, PA, pl.rA, (uint32_t)my_lo, my_hi, d->first, d->want_counts, d->double_selfrc,
-                      d->d_bsz.p, ch, tm, tr);
-    } else {
-        ch.n = 0; ch.b_lo = my_lo; ch.b_hi = my_hi; ch.first = d->first;
-        ch.keys.alloc(ctx, 2, true);
-        if (d->want_counts) ch.counts.alloc(ctx, 1, true);
+        tm.start();
+        const uint64_t nwork = (uint64_t)nq * world;
+        const int grid = (int)std::min<uint64_t>(nwork, (uint64_t)ctx->num_sms * 4);
+        dist_pull_k<NW><<<grid, kPullThreads, 0, st>>>(d_src.p, world, G, plan.PA_all, PAp, pq0, q0, nq, d_off.p, xbuf.p, wc.p);
+        ctx->launches++;
+        SG_CUDA(cudaGetLastError());
+        ctx->times.exchange += tm.stop();
     }
-    d->first += ch.n;
-    d->out->chunks.push_back(std::move(ch));
-}
 
-#define DIST_DISPATCH(fn, d, ...)                    \
-    switch ((d)->nw) {                               \
-        case 1: fn<1>(d, ##__VA_ARGS__); break;      \
-        case 2: fn<2>(d, ##__VA_ARGS__); break;      \
-        case 3: fn<3>(d, ##__VA_ARGS__); break;      \
-        default: fn<4>(d, ##__VA_ARGS__); break;     \
+    void sort(int p) override {
+        cudaStream_t st = ctx->stream;
+        const int my_lo = plan.own_lo(p, plan.rank), my_hi = plan.own_lo(p, plan.rank + 1);
+        const uint32_t PA = (uint32_t)(my_hi - my_lo) << plan.rA;
+        const size_t Q0 = (size_t)my_lo << plan.rA;
+        std::vector<uint64_t> tot(PA + 1, 0), start(PA + 1, 0);
+        for (uint32_t q = 0; q < PA; ++q) { tot[q] = plan.tot[Q0 + q]; start[q + 1] = start[q] + tot[q]; }
+        ctx->times.passes++;
+        ctx->times.instances += start[PA];
+        Chunk ch;
+        if (PA && start[PA]) {
+            DArr<uint64_t> d_tot(ctx, PA + 1), d_start(ctx, PA + 1);
+            SG_CUDA(cudaMemcpyAsync(d_tot.p, tot.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
+            SG_CUDA(cudaMemcpyAsync(d_start.p, start.data(), (size_t)(PA + 1) * 8, cudaMemcpyHostToDevice, st));
+            Timer tm(st);
+            Trace tr(st);
+            sort_pass<NW>(ctx, K, xbuf, sbuf, d_start.p, d_tot.p, PA, plan.rA, (uint32_t)my_lo, my_hi, first, want_counts, double_selfrc, d_bsz.p, ch, tm, tr);
+        } else {
+            ch.n = 0; ch.b_lo = my_lo; ch.b_hi = my_hi; ch.first = first;
+            ch.keys.alloc(ctx, 2, true);
+            if (want_counts) ch.counts.alloc(ctx, 1, true);
+        }
+        first += ch.n;
+        out->chunks.push_back(std::move(ch));
     }
+};
 
 DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
     SG_CHECK(K >= 1 && K <= 128, 2, "K must be in [1,128]");
-    SG_CHECK(B >= 1 && B <= 8192, 2, "distributed count: num_buckets must be in [1, 8192]");
+    SG_CHECK(B >= 1 && B <= kLevelAMaxParts, 2, "distributed count: num_buckets must be in [1, 8192]");
     SG_CHECK(world >= 1 && world <= 255 && rank >= 0 && rank < world, 2, "bad world/rank");
+    SG_CHECK(mode == kCanonical || mode == kAllWindows, 2, "bad mode");
     ensure_reads_on_device(ctx);
-    for (const UploadChunk &u : ctx->up_chunks) SG_CUDA(cudaStreamWaitEvent(ctx->stream, u.ev, 0));   // a chunked upload may still be in flight
     ctx->times = PhaseTimes();
-    DistState *d = new DistState();
+    DistState *d = nullptr;
+    switch (nwords_of(K)) {
+        case 1: d = new DistStateNW<1>(); break;
+        case 2: d = new DistStateNW<2>(); break;
+        case 3: d = new DistStateNW<3>(); break;
+        default: d = new DistStateNW<4>(); break;
+    }
     d->ctx = ctx; d->K = K; d->B = B; d->mode = mode; d->nw = nwords_of(K);
     d->G = ctx->num_sms * 2;
     d->want_counts = (mode == kCanonical); d->double_selfrc = (mode == kCanonical) && (K % 2 == 0);
-    d->src.words = ctx->d_words; d->src.offs = ctx->d_offs; d->src.lens = ctx->d_lens; d->src.n = ctx->n_reads; d->src.K = K; d->src.both = (mode == kAllWindows);
-    int rA = 0;
     // every rank must use the same geometry, so it depends on B only. As many level-A partitions as the shared-memory tables allow:
     // an owner's segment is the union of all ranks' records of a partition, so finer partitions keep refinement at one round
-    while (rA < 8 && ((uint64_t)B << (rA + 1)) <= 8192 && rA + 1 <= 2 * K) ++rA;
+    int rA = 0;
+    while (rA < 8 && ((uint64_t)B << (rA + 1)) <= (uint64_t)kLevelAMaxParts && rA + 1 <= 2 * K) ++rA;
     d->plan.world = world; d->plan.rank = rank; d->plan.B = B; d->plan.rA = rA; d->plan.PA_all = (uint32_t)B << rA;
-    try { DIST_DISPATCH(dist_begin_nw, d); } catch (...) { delete d; throw; }
+    try { d->begin(); } catch (...) { delete d; throw; }
     return d;
 }
 uint32_t dist_num_partitions(const DistState *d) { return d->plan.PA_all; }
-void dist_local_counts(DistState *d, uint64_t *h_out) {
-    SG_CUDA(cudaMemcpyAsync(h_out, d->part_total_local.p, (size_t)d->plan.PA_all * 8, cudaMemcpyDeviceToHost, d->ctx->stream));
-    SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
-}
+void dist_local_counts(DistState *d, uint64_t *h_out) { d->local_counts(h_out); }
+
 void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records) {
     Ctx *ctx = d->ctx;
-    dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, (size_t)8 * d->nw);
+    const size_t W = (size_t)8 * d->nw;
+    dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, W, (uint64_t)256 << 20);
     d->h_cnt_all.assign(cnt_all, cnt_all + (size_t)d->plan.world * d->plan.PA_all);
-    // buffers are allocated by dist_alloc_buffers() unless adopted from a previous count
     d->d_bsz.alloc(ctx, (size_t)d->B);
     SG_CUDA(cudaMemsetAsync(d->d_bsz.p, 0, (size_t)d->B * 8, ctx->stream));
     d->out = new KSet();
     d->out->ctx = ctx; d->out->K = d->K; d->out->nw = d->nw; d->out->B = d->B; d->out->has_counts = d->want_counts;
+    // buffers the peers read must live inside the arena (one driver allocation, mapped by the peers as a whole)
+    uint32_t max_pa = 1;
+    for (int p = 0; p < d->plan.npass; ++p) max_pa = std::max(max_pa, (uint32_t)(d->plan.pass_b[p + 1] - d->plan.pass_b[p]) << d->plan.rA);
+    d->sbuf.alloc(ctx, (size_t)((double)std::max(d->plan.max_recv, d->plan.max_send) * kDistHeadroom) * d->nw + 16);
+    d->xbuf.alloc(ctx, (size_t)((double)d->plan.max_recv * kDistHeadroom) * d->nw + 16);
+    d->pbase.alloc(ctx, (size_t)d->G * max_pa);
     SG_CUDA(cudaStreamSynchronize(ctx->stream));
     *npass = d->plan.npass; *xchg_records = d->plan.max_recv;
 }
-void dist_ipc_handle(DistState *d, uint8_t *out64) {
-    // staging buffer: exported through cudaIpc (pool blocks are whole driver allocations, as cudaIpcGetMemHandle requires);
-    // 10% headroom so that the next count of a similar shard can adopt it
-    if (!d->sbuf.p) {
-        d->sbuf.alloc(d->ctx, (size_t)((double)std::max(d->plan.max_recv, d->plan.max_send) * 1.1) * d->nw + 2);
-        d->xbuf.alloc(d->ctx, (size_t)((double)d->plan.max_recv * 1.1) * d->nw + 2);
-    }
-    // the staging buffer is a sub-block of the context's arena (one driver allocation): export the arena's handle and
-    // the offset of the block inside it (72 bytes: cudaIpcMemHandle_t + u64 offset)
+
+// descriptor a rank publishes (all_gather) after dist_plan: arena handle + where its peer-readable buffers are inside the arena
+struct DistDesc {
+    cudaIpcMemHandle_t arena;     // 64 bytes
+    uint64_t arena_size, off_sbuf, off_pbase, off_blk;
+};
+static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(DistDesc) == 96, "descriptor layout (SGPU_IPC_BYTES)");
+
+void dist_ipc_handle(DistState *d, uint8_t *out96) {
     Ctx *ctx = d->ctx;
-    cudaIpcMemHandle_t h;
-    uint64_t off = 0;
-    const char *sp = (const char *)d->sbuf.p;
-    if (ctx->arena && sp >= ctx->arena && sp < ctx->arena + ctx->arena_size) {
-        SG_CUDA(cudaIpcGetMemHandle(&h, ctx->arena));
-        off = (uint64_t)(sp - ctx->arena);
-    } else {
-        SG_CUDA(cudaIpcGetMemHandle(&h, d->sbuf.p));
-    }
-    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    memcpy(out64, &h, 64);
-    memcpy(out64 + 64, &off, 8);
+    auto off_of = [&](const void *p, const char *what) {
+        const char *c = (const char *)p;
+        SG_CHECK(ctx->arena && c >= ctx->arena && c < ctx->arena + ctx->arena_size, 4, what);
+        return (uint64_t)(c - ctx->arena);
+    };
+    DistDesc ds;
+    memset(&ds, 0, sizeof ds);
+    ds.off_sbuf = off_of(d->sbuf.p, "distributed count: the staging buffer did not fit the device memory arena");
+    ds.off_pbase = off_of(d->pbase.p, "distributed count: the piece table did not fit the device memory arena");
+    ds.off_blk = off_of(d->blk_counts_ptr(), "distributed count: the level-A count table did not fit the device memory arena");
+    ds.arena_size = ctx->arena_size;
+    if (d->plan.world > 1) SG_CUDA(cudaIpcGetMemHandle(&ds.arena, ctx->arena));
+    memcpy(out96, &ds, sizeof ds);
 }
-void dist_open_peers(DistState *d, const uint8_t *handles) {
+
+void dist_open_peers(DistState *d, const uint8_t *descs) {
     Ctx *ctx = d->ctx;
     const int world = d->plan.world;
-    d->peer.assign(world, nullptr);
+    d->peers.assign(world, PullSrc{nullptr, nullptr, nullptr});
+    if ((int)ctx->peer_arena.size() != world) { ctx->peer_close(); ctx->peer_arena.assign(world, nullptr); ctx->peer_handle.assign((size_t)world * 64, 0); }
     for (int g = 0; g < world; ++g) {
-        if (g == d->plan.rank) { d->peer[g] = d->sbuf.p; continue; }
-        cudaIpcMemHandle_t h;
-        uint64_t off = 0;
-        memcpy(&h, handles + (size_t)g * 72, 64);
-        memcpy(&off, handles + (size_t)g * 72 + 64, 8);
-        void *p = nullptr;
-        SG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        d->peer_base.resize(world, nullptr);
-        d->peer_base[g] = p;
-        d->peer[g] = (uint64_t *)((char *)p + off);
+        DistDesc ds;
+        memcpy(&ds, descs + (size_t)g * sizeof(DistDesc), sizeof ds);
+        char *base = nullptr;
+        if (g == d->plan.rank) {
+            base = ctx->arena;
+        } else {
+            // a peer's arena is mapped once per process; a different handle under the same rank (its context was re-created) remaps
+            if (ctx->peer_arena[g] && memcmp(&ctx->peer_handle[(size_t)g * 64], &ds.arena, 64) != 0) {
+                cudaIpcCloseMemHandle(ctx->peer_arena[g]);
+                ctx->peer_arena[g] = nullptr;
+            }
+            if (!ctx->peer_arena[g]) {
+                void *p = nullptr;
+                SG_CUDA(cudaIpcOpenMemHandle(&p, ds.arena, cudaIpcMemLazyEnablePeerAccess));
+                ctx->peer_arena[g] = (char *)p;
+                memcpy(&ctx->peer_handle[(size_t)g * 64], &ds.arena, 64);
+            }
+            base = ctx->peer_arena[g];
+        }
+        SG_CHECK(ds.off_sbuf < ds.arena_size && ds.off_pbase < ds.arena_size && ds.off_blk < ds.arena_size, 2, "bad peer descriptor");
+        d->peers[g] = PullSrc{(const uint64_t *)(base + ds.off_sbuf), (const uint64_t *)(base + ds.off_pbase), (const uint32_t *)(base + ds.off_blk)};
     }
-    (void)ctx;
-}
-// reuse the staging / merged buffers and the opened peer mappings of a finished distributed count (cudaIpcOpenMemHandle of a
-// tens-of-GB buffer is expensive). Every rank takes the same decision: the capacities come from identical plans.
-int dist_adopt(DistState *d, DistState *old) {
-    if (!old || old->plan.world != d->plan.world || old->nw != d->nw || old->peer.empty()) return 0;
-    const size_t need_s = (size_t)std::max(d->plan.max_recv, d->plan.max_send) * d->nw + 2, need_x = (size_t)d->plan.max_recv * d->nw + 2;
-    if (old->sbuf.n < need_s || old->xbuf.n < need_x) return 0;
-    d->sbuf = std::move(old->sbuf);
-    d->xbuf = std::move(old->xbuf);
-    d->peer = std::move(old->peer);
-    d->peer_base = std::move(old->peer_base);
-    old->peer.clear(); old->peer_base.clear();
-    return 1;
 }
 
 void dist_scatter(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
-    DIST_DISPATCH(dist_scatter_nw, d, p);
+    d->scatter(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // the staging buffer is complete; peers may read it after the next barrier
 }
 void dist_exchange(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
-    DIST_DISPATCH(dist_pull_nw, d, p);
+    SG_CHECK((int)d->peers.size() == d->plan.world, 2, "sgpu_dist_open_peers has not run");
+    d->pull(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // this rank no longer reads any peer's staging buffer
 }
 void dist_sort(DistState *d, int p) {
     SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
-    DIST_DISPATCH(dist_sort_nw, d, p);
+    d->sort(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
-}
-static void dist_close(DistState *d) {
-    for (int g = 0; g < (int)d->peer_base.size(); ++g)
-        if (g != d->plan.rank && d->peer_base[g]) cudaIpcCloseMemHandle(d->peer_base[g]);
-    d->peer.clear(); d->peer_base.clear();
 }
 KSet *dist_end(DistState *d) {
     Ctx *ctx = d->ctx;
@@ -2231,16 +2090,11 @@ KSet *dist_end(DistState *d) {
     d->out = nullptr;
     return ks;
 }
-void dist_free(DistState *d) {
-    if (!d) return;
-    dist_close(d);
-    delete d->out;
-    delete d;
-}
+void dist_free(DistState *d) { delete d; }
 
 int dist_plan_host(int world, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, int record_bytes, int *pass_b, uint64_t *max_recv) {
     DistPlan pl;
-    dist_make_plan(pl, world, 0, B, rA, cnt_all, budget_bytes, (size_t)record_bytes);
+    dist_make_plan(pl, world, 0, B, rA, cnt_all, budget_bytes, (size_t)record_bytes, 0);
     for (int p = 0; p <= pl.npass; ++p) pass_b[p] = pl.pass_b[p];
     *max_recv = pl.max_recv;
     return pl.npass;

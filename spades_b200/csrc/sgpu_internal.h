@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <iterator>
 #include <map>
 #include <stdexcept>
@@ -70,13 +71,6 @@ struct PhaseTimes {   // device milliseconds measured with CUDA events on ctx->s
     uint64_t passes = 0;
 };
 
-struct UploadChunk {      // one piece of a chunked host->device read upload (sgpu_reads_upload)
-    int64_t r0 = 0, r1 = 0;         // reads [r0, r1)
-    cudaEvent_t ev = nullptr;       // recorded on the copy stream when the piece has landed
-    uint64_t sum_long = 0, n_long = 0;   // reads of length >= 256: total bases and count
-    uint32_t hist[256] = {0};       // reads of length < 256 by length (exact window counts for any K without touching the device)
-};
-
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -99,8 +93,15 @@ struct Ctx {
     std::vector<uint64_t> h_words, h_offs;   // host staging until first use
     std::vector<uint32_t> h_lens;
     bool staged_dirty = false;
-    cudaStream_t copy_stream = nullptr;
-    std::vector<UploadChunk> up_chunks;      // non-empty while the current read set came from a chunked upload
+    // objects created from this context that still hold arena blocks (k-mer sets, indexes, graphs, distributed counts):
+    // sgpu_destroy refuses to run while any is alive (their destructors release blocks into this context's arena)
+    int live_children = 0;
+    bool destroy_pending = false;
+    void *owner = nullptr;                   // the sgpu_ctx this context is embedded in
+    // multi-GPU: the peers' arenas mapped through cudaIpc, once per process (rank-indexed; own entry unused)
+    std::vector<char *> peer_arena;
+    std::vector<uint8_t> peer_handle;        // 64 bytes per rank: the handle a mapping was opened from
+    void peer_close();
     // device memory: one arena reserved from the driver at first use and sub-allocated with a coalescing free list.
     // cudaMalloc/cudaFree of tens of GB cost 100s of ms and a 100 M-read step turns over ~300 GB of buffers; inside the
     // arena an allocation is a map lookup. Short-lived buffers (X/Y ping-pong, scratch) grow from the bottom, long-lived
@@ -122,7 +123,8 @@ inline void Ctx::arena_init() {
     size_t f = 0, t = 0;
     cudaMemGetInfo(&f, &t);
     size_t want = hbm_budget ? hbm_budget : (size_t)((double)f * 0.92);
-    if (getenv("SGPU_ARENA_GB")) want = (size_t)atof(getenv("SGPU_ARENA_GB")) << 30;
+    // SGPU_ARENA_GB: user option, caps the arena (e.g. to leave ncu room for its replay buffers)
+    if (const char *e = getenv("SGPU_ARENA_GB")) { const double gb = atof(e); if (gb >= 0.0625) want = std::min(want, (size_t)(gb * (double)(1ull << 30))); }
     want &= ~(size_t)((2u << 20) - 1);
     while (want >= ((size_t)64 << 20)) {
         void *p = nullptr;
@@ -135,7 +137,12 @@ inline void Ctx::arena_init() {
     arena_free[0] = arena_size;
     pool_cached = arena_size;
 }
+inline void Ctx::peer_close() {
+    for (char *p : peer_arena) if (p) cudaIpcCloseMemHandle(p);
+    peer_arena.clear(); peer_handle.clear();
+}
 inline void Ctx::pool_trim() {
+    peer_close();
     if (arena) cudaFree(arena);
     arena = nullptr; arena_size = 0; arena_free.clear(); pool_cached = 0;
     for (auto &d : direct) cudaFree(d.first);
@@ -265,6 +272,8 @@ enum CountMode { kCanonical = 0, kAllWindows = 1 };
 KSet *count_from_reads(Ctx *ctx, int K, int B, int mode);
 KSet *kmers_from_kpomers(Ctx *ctx, const KSet *kp, int B);
 
+void kset_checksum(const KSet *ks, uint64_t *out4);
+
 // distributed count (count.cu)
 struct DistState;
 struct DistPlan;
@@ -272,9 +281,8 @@ DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank);
 uint32_t dist_num_partitions(const DistState *d);
 void dist_local_counts(DistState *d, uint64_t *h_out);
 void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records);
-void dist_ipc_handle(DistState *d, uint8_t *out64);
-void dist_open_peers(DistState *d, const uint8_t *handles);
-int dist_adopt(DistState *d, DistState *old);
+void dist_ipc_handle(DistState *d, uint8_t *out96);
+void dist_open_peers(DistState *d, const uint8_t *descs);
 void dist_scatter(DistState *d, int p);
 void dist_exchange(DistState *d, int p);
 void dist_sort(DistState *d, int p);

@@ -10,23 +10,18 @@ import numpy as np
 
 from .kmer_index import KMerDiskStorage, SGPU_CANONICAL
 
+SGPU_IPC_BYTES = 96
+
 
 class DistributedKMerCounter:
     """KMerDiskCounter over a read set sharded across the ranks of a torch.distributed process group."""
 
     def __init__(self, ctx, K, mode=SGPU_CANONICAL, group=None):
         self.ctx, self.K, self.mode, self.group = ctx, K, mode, group
-        self._prev = None        # the last finished count: owner of reusable buffers and peer mappings
+        self.npass = 0
 
     def close(self):
-        if self._prev is not None:
-            self.ctx.L.sgpu_dist_free(self._prev); self._prev = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        pass
 
     def Count(self, num_buckets, budget_bytes=None):
         import torch
@@ -46,20 +41,19 @@ class DistributedKMerCounter:
             dist.all_gather(gathered, t_local, group=self.group)
             all_counts = np.ascontiguousarray(torch.stack(gathered).cpu().numpy().view(np.uint64))
             if budget_bytes is None:
-                free = torch.cuda.mem_get_info()[0] + ctx.times()["cached_bytes"]
-                tb = torch.tensor([free], dtype=torch.int64, device=backend_dev)
+                # what every rank can still allocate inside its arena (the level-A tables and partition ids are already resident)
+                tb = torch.tensor([ctx.times()["cached_bytes"]], dtype=torch.int64, device=backend_dev)
                 dist.all_reduce(tb, op=dist.ReduceOp.MIN, group=self.group)
-                budget_bytes = int(int(tb.item()) * 0.85)
+                budget_bytes = int(int(tb.item()) * 0.92)
             npass, xrec = C.c_int(), C.c_uint64()
             ctx.check(L.sgpu_dist_plan(h, all_counts.ctypes.data_as(C.c_void_p), budget_bytes, C.byref(npass), C.byref(xrec)))
-            if not L.sgpu_dist_adopt(h, self._prev):
-                handle = np.zeros(72, np.uint8)      # SGPU_IPC_BYTES
-                ctx.check(L.sgpu_dist_ipc_handle(h, handle.ctypes.data_as(C.c_void_p)))
-                t_h = torch.from_numpy(handle).to(backend_dev)
-                hs = [torch.empty_like(t_h) for _ in range(world)]
-                dist.all_gather(hs, t_h, group=self.group)
-                handles = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
-                ctx.check(L.sgpu_dist_open_peers(h, handles.ctypes.data_as(C.c_void_p)))
+            desc = np.zeros(SGPU_IPC_BYTES, np.uint8)
+            ctx.check(L.sgpu_dist_ipc_handle(h, desc.ctypes.data_as(C.c_void_p)))
+            t_h = torch.from_numpy(desc).to(backend_dev)
+            hs = [torch.empty_like(t_h) for _ in range(world)]
+            dist.all_gather(hs, t_h, group=self.group)
+            descs = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
+            ctx.check(L.sgpu_dist_open_peers(h, descs.ctypes.data_as(C.c_void_p)))     # peers' arenas are mapped once per process
             for p in range(npass.value):
                 ctx.check(L.sgpu_dist_scatter(h, p))    # local partition into the staging buffer
                 dist.barrier(group=self.group)          # every rank's staging buffer is complete
@@ -70,14 +64,9 @@ class DistributedKMerCounter:
             ks = C.c_void_p()
             ctx.check(L.sgpu_dist_end(h, C.byref(ks)))
             self.npass = npass.value
-            if self._prev is not None:
-                L.sgpu_dist_free(self._prev)
-            self._prev = h
-            h = None
             return KMerDiskStorage(ctx, ks)
         finally:
-            if h is not None:
-                L.sgpu_dist_free(h)
+            L.sgpu_dist_free(h)
 
 
 def plan_host(world, num_buckets, key_bits, all_counts, budget_bytes, record_bytes):

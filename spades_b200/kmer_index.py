@@ -109,6 +109,12 @@ class KMerDiskStorage:
         self.ctx.check(self.ctx.L.sgpu_kset_download_counts(self.h, first, n, _p(out)))
         return out[:n]
 
+    def checksum(self):
+        """(n, weighted sum of the record words, xor of the rotated record words, sum of multiplicities), computed on the device."""
+        out = np.zeros(4, np.uint64)
+        self.ctx.check(self.ctx.L.sgpu_kset_checksum(self.h, _p(out)))
+        return [int(x) for x in out]
+
     def write_buckets(self, prefix):
         self.ctx.check(self.ctx.L.sgpu_kset_write_buckets(self.h, str(prefix).encode()))
 

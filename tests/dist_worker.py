@@ -77,7 +77,7 @@ def run_gpu():
     ctx = Context(lrank)
     fails = []
     counters = {}
-    for (K, B, n, budget) in ((56, 40, 6000, None), (22, 7, 4000, None), (78, 64, 3000, 300_000_000), (56, 16, 6000, 280_000_000)):
+    for (K, B, n, budget) in ((56, 40, 6000, None), (22, 7, 4000, None), (78, 64, 3000, (256 << 20) + 2_000_000), (56, 16, 6000, (256 << 20) + 3_000_000)):
         reads = synthetic_reads(n, 150, 4000, 0.01, seed=K + B)
         mine = reads[rank::world]
         ctx.set_reads(*pack_reads(mine))
@@ -88,7 +88,7 @@ def run_gpu():
         ids = idx.seq_idx(keys) if len(keys) else np.zeros(0, np.uint64)
         perfect = len(np.unique(ids)) == len(keys)
         gathered = [None] * world
-        dist.all_gather_object(gathered, (keys, counts, bsz, perfect, cnt.npass))
+        dist.all_gather_object(gathered, (keys, counts, bsz, perfect, cnt.npass, st.checksum()))
         if rank == 0:
             words, offs, lens = pack_reads(reads)
             ks = O.count(words, offs, lens, K, B, 0)
@@ -107,6 +107,15 @@ def run_gpu():
             allk = np.concatenate(parts_k) if parts_k else np.zeros((0, ks.nw), np.uint64)
             allc = np.concatenate(parts_c) if parts_c else np.zeros(0, np.uint32)
             ok &= np.array_equal(allk.ravel(), ks.keys.ravel()) and np.array_equal(allc, ks.counts)
+            if budget is not None:
+                ok &= gathered[0][4] > 1          # the budget must have forced several passes (256 MB are the planner's fixed reserve)
+            # the order-independent device checksums (what bench.py's multi-GPU self check uses) must add / xor up to the union's
+            cs = [g[5] for g in gathered]
+            tot = [sum(c[0] for c in cs), sum(c[1] for c in cs) & ((1 << 64) - 1), 0, sum(c[3] for c in cs) & ((1 << 64) - 1)]
+            for c in cs:
+                tot[2] ^= c[2]
+            words_sum = int((ks.keys.astype(np.uint64) * (2 * np.arange(ks.nw, dtype=np.uint64) + 1)[None, :]).sum(dtype=np.uint64)) if ks.n else 0
+            ok &= tot[0] == ks.n and tot[1] == words_sum and tot[3] == int(ks.counts.astype(np.uint64).sum())
             if not ok:
                 fails.append((K, B, n))
             print("dist case K=%d B=%d reads=%d passes=%d distinct=%d %s" % (K, B, n, gathered[0][4], ks.n, "OK" if ok else "MISMATCH"), flush=True)

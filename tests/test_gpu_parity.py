@@ -39,14 +39,8 @@ def test_device_arithmetic():
     check_roll(ctx().h, 1)
 
 
-# fixtures added after the last GPU session of round 1 run for the first time in round 2 (scripts/gpu_round2_sweep.sh sets SGPU_RUN_NEW)
-_PENDING = {"gtest_EarlyPairedInfo_k3"}
-
-
 @pytest.mark.parametrize("name", G.names("graph"))
 def test_graph_matches_reference_golden(name):
-    if name in _PENDING and __import__("os").environ.get("SGPU_RUN_NEW") is None:
-        pytest.skip("first GPU run pending (set SGPU_RUN_NEW=1)")
     from gpu_util import gpu_graph_artifacts
     g = G.load(name)
     art, _ = gpu_graph_artifacts(g["reads"], g["k"], g["B"])
@@ -108,7 +102,6 @@ def test_ragged_empty_and_short_reads():
     assert _compare(art, _oracle_art(reads, 21, 6), 6) == []
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SGPU_RUN_NEW") is None, reason="first GPU run pending (set SGPU_RUN_NEW=1; scripts/gpu_round2_sweep.sh)")
 def test_long_reads_take_the_unstaged_path():
     """reads of 400..6000 bp: a tile's packed reads no longer fit the shared-memory staging area (kStageWords), so the level-A
     kernels read the words from global memory; mixed with short reads so that staged and unstaged tiles alternate"""
@@ -195,7 +188,118 @@ def test_medium_size_properties_and_oracle():
         off += bsz[b]
     ks = O.count(words, offs, lens, K, B, 0)
     assert np.array_equal(keys.ravel(), ks.keys.ravel()) and np.array_equal(counts, ks.counts) and np.array_equal(bsz, ks.bsz)
+    # device checksums (bench.py's multi-GPU self check): n, weighted word sum, xor of rotated words, multiplicity sum
+    n_, s_, x_, c_ = st.checksum()
+    wsum = int((ks.keys * (2 * np.arange(ks.nw, dtype=np.uint64) + 1)[None, :]).sum(dtype=np.uint64))
+    rot = [7 * q + 1 for q in range(ks.nw)]
+    xr = 0
+    for q in range(ks.nw):
+        col = ks.keys[:, q]
+        xr ^= int(np.bitwise_xor.reduce((col << np.uint64(rot[q])) | (col >> np.uint64(64 - rot[q]))))
+    assert (n_, s_, x_, c_) == (ks.n, wsum, xr, int(ks.counts.astype(np.uint64).sum()))
     idx = KMerIndexBuilder(c).BuildIndex(st)
     ids = idx.seq_idx(keys)
     assert len(np.unique(ids)) == len(keys) and ids.max() == len(keys) - 1       # phm_test.cpp:22-79 properties
     assert G.index_equal(O.Mphf(ks).serialize(), idx.serialize(), B)
+
+
+# ---- parity at scale ("Next round" #2) ----------------------------------------------------------------------------
+def _count_with_budget(words, offs, lens, K, B, budget):
+    from spades_b200.kmer_index import Context, DeBruijnReadKMerSplitter, KMerDiskCounter, KMerIndexBuilder
+    c = Context(0, hbm_budget_bytes=budget)
+    try:
+        c.set_reads(words, offs, lens)
+        st = KMerDiskCounter(c, DeBruijnReadKMerSplitter(K)).Count(B)
+        t = c.times()
+        keys, counts, bsz = st.kmers(), st.counts(), st.bucket_sizes()
+        idx = KMerIndexBuilder(c).BuildIndex(st)
+        ser = idx.serialize()
+        idx.free(); st.free()
+        return keys, counts, bsz, ser, int(t["passes"])
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("budget_mb,min_passes", [(420, 3), (200, 5)])
+def test_forced_bucket_group_passes_match_oracle(budget_mb, min_passes):
+    """200 k reads x 150 bp, k=55 (19 M records = 304 MB per buffer) inside a context whose HBM budget only holds a fraction: the
+    multi-pass loop the 100 M-read bench runs (5 passes there), with the partition-id array (420 MB) and without it (200 MB: the ids
+    no longer fit, every pass re-hashes). Keys, multiplicities, bucket sizes and the serialized KMerIndex must equal the oracle's."""
+    from spades_b200.packing import pack_fixed
+    codes = synthetic_reads(200_000, 150, 200_000, 0.01, seed=91, as_codes=True)
+    words, offs, lens = pack_fixed(codes)
+    K, B = 56, 80
+    keys, counts, bsz, ser, passes = _count_with_budget(words, offs, lens, K, B, budget_mb << 20)
+    assert passes >= min_passes, passes
+    ks = O.count(words, offs, lens, K, B, 0)
+    assert np.array_equal(bsz, ks.bsz)
+    assert np.array_equal(keys.ravel(), ks.keys.ravel()) and np.array_equal(counts, ks.counts)
+    assert G.index_equal(O.Mphf(ks).serialize(), ser, B)
+
+
+def test_histogram_super_ranges_match_oracle():
+    """more buckets than one level-A launch can address (B << rA > 8192): the histogram super-range loop"""
+    from gpu_util import ctx
+    from spades_b200.kmer_index import DeBruijnReadKMerSplitter, KMerDiskCounter
+    from spades_b200.packing import pack_fixed
+    codes = synthetic_reads(20_000, 150, 20_000, 0.01, seed=92, as_codes=True)
+    words, offs, lens = pack_fixed(codes)
+    c = ctx()
+    for K, B in ((56, 20_000), (22, 9_000)):
+        c.set_reads(words, offs, lens)
+        st = KMerDiskCounter(c, DeBruijnReadKMerSplitter(K)).Count(B)
+        keys, counts, bsz = st.kmers(), st.counts(), st.bucket_sizes()
+        st.free()
+        ks = O.count(words, offs, lens, K, B, 0)
+        assert np.array_equal(bsz, ks.bsz) and np.array_equal(keys.ravel(), ks.keys.ravel()) and np.array_equal(counts, ks.counts)
+
+
+def _uleb(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+@pytest.mark.parametrize("case", ["k21", "k55"])
+def test_million_reads_sha256(case):
+    """byte identity with the UNMODIFIED reference on a >= 1 M-read synthetic set. tests/golden/syn1M_sha256.json holds
+    the SHA-256 of every artefact `ref_probe graph` wrote for these reads (tests/golden/make_golden_1m.py); the same bytes are
+    rebuilt here from the GPU path's outputs."""
+    import hashlib
+    import json
+    import os
+    from gpu_util import ctx
+    from spades_b200.graph import DeBruijnGraphConstructor
+    from spades_b200.packing import pack_fixed
+    fx = json.load(open(os.path.join(G.GOLDEN_DIR, "syn1M_sha256.json")))
+    r, cs = fx["reads"], fx["cases"][case]
+    codes = synthetic_reads(r["n"], r["len"], r["genome_len"], r["err"], seed=r["seed"], as_codes=True)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    txt = np.empty((r["n"], r["len"] + 1), np.uint8)
+    txt[:, :r["len"]] = lut[codes]; txt[:, r["len"]] = 10
+    assert hashlib.sha256(txt.tobytes()).hexdigest() == r["sha256_text"], "the generator no longer reproduces the fixture's reads"
+    del txt
+    k, B = cs["k"], cs["B"]
+    c = ctx()
+    c.set_reads(*pack_fixed(codes))
+    g = DeBruijnGraphConstructor(c, k, B).ConstructGraph(keep_perfect_loops=True, with_coverage=True)
+    mine = {
+        "kpomers": g.kpomers.kmers().tobytes(),
+        "kpomer_bucket_sizes.txt": "".join("%d\n" % x for x in g.kpomers.bucket_sizes()).encode(),
+        "kmers": g.kmers.kmers().tobytes(),
+        "kmer_index.bin": _uleb(k) + g.kmer_index.serialize(),
+        "kpomer_index.bin": _uleb(k + 1) + g.kpomer_index.serialize(),
+        "masks.bin": g.masks().tobytes(),
+        "coverage.bin": g.coverage().tobytes(),
+        "histogram.txt": "".join("%d\n" % x for x in g.histogram()).encode(),
+        "unitigs.txt": "".join(u + "\n" for u in g.unitigs()).encode(),
+        "graph.gfa": g.gfa().encode(),
+    }
+    bad = [f for f, h in cs["sha256"].items() if hashlib.sha256(mine[f]).hexdigest() != h]
+    sizes = {f: (len(mine[f]), cs["bytes"][f]) for f in bad}
+    g.free()
+    assert bad == [], sizes

@@ -55,7 +55,6 @@ def test_reference_host_code_over_the_c_abi(name):
 
 
 @needs_tool
-@pytest.mark.skipif(os.environ.get("SGPU_RUN_NEW") is None, reason="first GPU run pending (set SGPU_RUN_NEW=1)")
 @pytest.mark.gpu
 def test_tool_takes_gzipped_fastq_like_the_original():
     """same reads as a gzipped FASTQ with N-containing reads added: the library's ingest (kseq semantics + LongestValid) in front of
@@ -87,13 +86,7 @@ def test_gbuilder_tool_refuses_without_gpu():
     assert p.returncode == 3 and "no CPU fallback" in p.stderr
 
 
-# written after the last GPU session of round 1: runs for the first time in round 2 (scripts/gpu_round2_sweep.sh sets the variable),
-# afterwards the guard goes away
-first_run_pending = pytest.mark.skipif(os.environ.get("SGPU_RUN_NEW") is None, reason="first GPU run pending (set SGPU_RUN_NEW=1)")
-
-
 @pytest.mark.skipif(not os.path.exists(GBUILDER), reason="integration/_build/spades_gbuilder_gpu not built")
-@first_run_pending
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,early_tc", [("ecoli_k21_B40_graph", 0), ("loops_k21_B10_graph", 0), ("ecoli_k55_B16_graph", 0), ("syn_k21_B10_tcgraph", 79)])
 def test_reference_graph_construction_over_gpu_arrays(name, early_tc):
