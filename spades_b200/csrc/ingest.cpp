@@ -43,6 +43,7 @@ struct GzReader {
     std::vector<char> buf;
     size_t pos = 0, end = 0;
     bool eof = false;
+    std::string io_error;          // set when zlib reports a read / decompression error (truncated or corrupt .gz)
     std::string carry;
     bool open(const char *path) {
         f = gzopen(path, "rb");       // transparently reads plain files too
@@ -55,7 +56,15 @@ struct GzReader {
     bool refill() {
         if (eof) return false;
         const int n = gzread(f, buf.data(), (unsigned)buf.size());
-        if (n <= 0) { eof = true; return false; }
+        if (n <= 0) {
+            // gzread() <= 0 is only a clean end of input when zlib agrees: a truncated or corrupt stream (Z_BUF_ERROR / Z_DATA_ERROR)
+            // must not yield a silently smaller read set
+            int zerr = Z_OK;
+            const char *msg = gzerror(f, &zerr);
+            if (n < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) io_error = std::string("read error: ") + (msg && *msg ? msg : "gzread failed");
+            eof = true;
+            return false;
+        }
         pos = 0; end = (size_t)n;
         return true;
     }
@@ -302,7 +311,12 @@ bool parse_fastx(const char *path, bool longest_valid, int nthreads, sgpu_read_b
     GzLines in;
     if (!in.r.open(path)) { b->err = std::string("cannot open ") + path; return false; }
     size_t next = 0;
-    return parse_lines(in, longest_valid, (size_t)-1, b, &next, (size_t)-1);
+    const bool ok = parse_lines(in, longest_valid, (size_t)-1, b, &next, (size_t)-1);
+    // a truncated / corrupt gzip stream ends the line source early: report it (SGPU_EIO) instead of returning a partial read set.
+    // (The reference's FastaFastqGzParser treats kseq_read() == -2, a quality string of the wrong length, as END OF STREAM and
+    // keeps what it has; this library is stricter on purpose and fails with "quality string is of a different length".)
+    if (!in.r.io_error.empty()) { b->err = in.r.io_error + " (" + path + ")"; return false; }
+    return ok;
 }
 
 bool parse_seqfile(const char *prefix, sgpu_read_batch *b) {

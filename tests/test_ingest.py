@@ -110,6 +110,27 @@ def test_truncated_fastq_is_an_error(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(ECOLI), reason="reference test data set not present")
+def test_truncated_or_corrupt_gzip_is_an_error_not_a_smaller_read_set(tmp_path):
+    """a .gz cut in the middle of the deflate stream (or with flipped bytes) must fail with SGPU_EIO -- zlib's gzread() <= 0 is only a
+    clean end of input when gzerror() agrees"""
+    import gzip
+    import random
+    rnd = random.Random(5)
+    fq = "".join("@r%d\n%s\n+\n%s\n" % (i, "".join(rnd.choice("ACGT") for _ in range(100)), "I" * 100) for i in range(3000))
+    blob = gzip.compress(fq.encode())
+    good = tmp_path / "ok.fq.gz"; good.write_bytes(blob)
+    assert len(read_fastx(good)) == 3000
+    cut = tmp_path / "cut.fq.gz"; cut.write_bytes(blob[: len(blob) // 2])
+    with pytest.raises(IOError, match="read error|truncated|different length"):
+        read_fastx(cut)
+    bad = bytearray(blob)
+    for i in range(len(bad) // 2, len(bad) // 2 + 64):
+        bad[i] ^= 0x5A
+    corrupt = tmp_path / "corrupt.fq.gz"; corrupt.write_bytes(bytes(bad))
+    with pytest.raises(IOError):
+        read_fastx(corrupt)
+
+
 def test_ecoli_test_dataset_matches_python_gzip():
     for f in ("ecoli_1K_1.fq.gz", "ecoli_1K_2.fq.gz"):
         lines = gzip.open(os.path.join(ECOLI, f), "rt").read().split("\n")
