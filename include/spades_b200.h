@@ -172,17 +172,23 @@ void sgpu_graph_free(sgpu_graph *g);
  * sgpu_dist_exchange is ONE kernel on the owner that pulls its pieces from all peers' staging buffers over NVLink peer memory
  * (cudaIpc mappings of the peers' memory arenas, opened once per process) and merges them partition by partition. The host
  * language only moves small tables between ranks (torch.distributed / MPI all_gather) and provides the barriers:
- *   begin -> local_counts -> [all_gather counts] -> plan -> ipc_handle -> [all_gather descriptors] -> open_peers ->
- *   for each pass: scatter [barrier] exchange [barrier] sort   -> end (k-mer set holding this rank's buckets) */
+ *   begin -> local_counts -> [all_gather counts] -> plan ->
+ *   repeat: free_bytes -> [all_reduce MIN] -> next_pass (-1 = done) -> ipc_handle -> [all_gather descriptors] -> open_peers ->
+ *           scatter [barrier] exchange [barrier] sort
+ *   -> end (k-mer set holding this rank's buckets)
+ * Passes are planned one at a time against the memory every rank has free at that moment (like sgpu_count's bucket-group passes). */
 typedef struct sgpu_dist sgpu_dist;
 int sgpu_dist_begin(sgpu_ctx *ctx, int K, int num_buckets, int mode, int world, int rank, sgpu_dist **out);
 int64_t sgpu_dist_num_partitions(const sgpu_dist *d);
 int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out);                 /* num_partitions host entries */
-/* budget_bytes: device bytes every rank can still allocate (the minimum over ranks); identical inputs give identical plans */
-int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_partitions, rank-major, host */, uint64_t budget_bytes,
-                   int *npass, uint64_t *exchange_records);
+int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts /* world x num_partitions, rank-major, host */, uint64_t *total_records);
+int sgpu_dist_free_bytes(sgpu_dist *d, uint64_t *out);                  /* device bytes this rank can allocate for the next pass */
+/* budget_bytes: the MINIMUM of sgpu_dist_free_bytes over the ranks (identical inputs give identical decisions on every rank).
+ * *pass = index of the pass that was planned and whose buffers were allocated, or -1 when all buckets are done */
+int sgpu_dist_next_pass(sgpu_dist *d, uint64_t budget_bytes, int *pass);
 #define SGPU_IPC_BYTES 96
-/* this rank's descriptor: cudaIpcMemHandle_t of its memory arena + the offsets of its staging buffer and piece tables inside it */
+/* this rank's descriptor for the current pass: cudaIpcMemHandle_t of its memory arena + the offsets of its staging buffer and
+ * piece tables inside it */
 int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out /* SGPU_IPC_BYTES */);
 int sgpu_dist_open_peers(sgpu_dist *d, const uint8_t *descriptors /* world x SGPU_IPC_BYTES, rank-major */);
 int sgpu_dist_scatter(sgpu_dist *d, int pass);                          /* partition this rank's shard into its staging buffer */

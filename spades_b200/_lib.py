@@ -21,7 +21,7 @@ SYMBOLS = [
     "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
     "sgpu_graph_build", "sgpu_graph_build_ex", "sgpu_graph_tip_clipper_stats", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
-    "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_ipc_handle",
+    "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_free_bytes", "sgpu_dist_next_pass", "sgpu_dist_ipc_handle",
     "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_exchange", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
     "sgpu_selftest",
 ]
@@ -104,7 +104,9 @@ def load():
     L.sgpu_dist_begin.restype = i32; L.sgpu_dist_begin.argtypes = [vp, i32, i32, i32, i32, i32, pp]
     L.sgpu_dist_num_partitions.restype = i64; L.sgpu_dist_num_partitions.argtypes = [vp]
     L.sgpu_dist_local_counts.restype = i32; L.sgpu_dist_local_counts.argtypes = [vp, vp]
-    L.sgpu_dist_plan.restype = i32; L.sgpu_dist_plan.argtypes = [vp, vp, u64, C.POINTER(i32), C.POINTER(u64)]
+    L.sgpu_dist_plan.restype = i32; L.sgpu_dist_plan.argtypes = [vp, vp, C.POINTER(u64)]
+    L.sgpu_dist_free_bytes.restype = i32; L.sgpu_dist_free_bytes.argtypes = [vp, C.POINTER(u64)]
+    L.sgpu_dist_next_pass.restype = i32; L.sgpu_dist_next_pass.argtypes = [vp, u64, C.POINTER(i32)]
     L.sgpu_dist_ipc_handle.restype = i32; L.sgpu_dist_ipc_handle.argtypes = [vp, vp]
     L.sgpu_dist_open_peers.restype = i32; L.sgpu_dist_open_peers.argtypes = [vp, vp]
     L.sgpu_dist_scatter.restype = i32; L.sgpu_dist_scatter.argtypes = [vp, i32]

@@ -406,9 +406,18 @@ int sgpu_dist_local_counts(sgpu_dist *d, uint64_t *out) {
     if (!d || !out) return SGPU_EINVAL;
     API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_local_counts(d->d, out); })
 }
-int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts, uint64_t budget_bytes, int *npass, uint64_t *exchange_records) {
-    if (!d || !all_counts || !npass || !exchange_records) return SGPU_EINVAL;
-    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_plan(d->d, all_counts, budget_bytes, npass, exchange_records); })
+int sgpu_dist_plan(sgpu_dist *d, const uint64_t *all_counts, uint64_t *total_records) {
+    if (!d || !all_counts || !total_records) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); dist_plan(d->d, all_counts, total_records); })
+}
+int sgpu_dist_free_bytes(sgpu_dist *d, uint64_t *out) {
+    if (!d || !out) return SGPU_EINVAL;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); *out = dist_free_bytes(d->d); })
+}
+int sgpu_dist_next_pass(sgpu_dist *d, uint64_t budget_bytes, int *pass) {
+    if (!d || !pass) return SGPU_EINVAL;
+    *pass = -1;
+    API_TRY(d->c, { SG_CUDA(cudaSetDevice(d->c->device)); *pass = dist_next_pass(d->d, budget_bytes); })
 }
 int sgpu_dist_ipc_handle(sgpu_dist *d, uint8_t *out) {
     if (!d || !out) return SGPU_EINVAL;

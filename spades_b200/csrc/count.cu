@@ -23,6 +23,7 @@
 
 #include "sgpu_internal.h"
 #include "pair_mailbox.cuh"
+#include "smem_sort.cuh"
 
 namespace sg {
 
@@ -550,6 +551,166 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
         __syncthreads();
     }
     for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
+}
+
+// ---- the radix-partition kernel, third generation: id sweep -> key batch -> ballot-ranked sort -> run flush -----------------------
+// What bounded the kernel above (round 1 + the round-2 sweep): every record costs a shared-memory atomic on its cursor and leaves as
+// a lone 16-byte store into one of ~512 open streams (0.9-1.1 TB/s whatever the instruction count). Here a CTA never touches the
+// cursors per record. Per tile it only LOOKS at the 2-byte ids: a window that belongs to the sub-range becomes a 32-bit key
+// (partition | read in tile | window), keys are collected without atomics (block scan of the per-thread counts), sorted by partition
+// with smem_sort.cuh (ballots, no atomics), and the sorted batch is flushed run by run: consecutive threads extract consecutive
+// records of ONE partition from the staged reads and store them to consecutive addresses, so sectors and lines leave the SM full.
+// Cursors advance once per (batch, partition). Windows of other sub-ranges / passes cost an id compare -- they are never rolled,
+// never extracted. Tiles that cannot be staged (reads > 320 bp) or hold a read with more than 512 windows, and rounds whose records
+// exceed the batch, take the direct path of the kernel above.
+static const int kSortedUnits = 256;             // units (chunks of 24 windows) whose ids one round looks at: even if every window of the
+                                                 // round belongs to the sub-range (single-pass jobs) its keys fit one batch
+static const int kSortedCap = kSortedUnits * kRollC;        // keys per batch = 6144 (12 sort rounds of the 512-thread CTA)
+static const int kSortedRounds = kSortedCap / kRollThreads;
+static_assert(kSortedCap % kRollThreads == 0, "batch = whole sort rounds");
+static const int kKeyItShift = 9, kKeyPartShift = 17;       // key = partition << 17 | read-in-tile << 9 | window (< 512)
+
+template <int NW>
+__global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_sorted_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
+                                                                          const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
+                                                                          uint32_t id_lo, uint32_t row_stride, uint32_t q_lo, int part_bits) {
+    extern __shared__ uint32_t sm_dyn[];
+    unsigned long long *cur = reinterpret_cast<unsigned long long *>(sm_dyn);       // PA: absolute record cursor of (this CTA, partition)
+    uint32_t *runstart = reinterpret_cast<uint32_t *>(cur + p.PA);                  // PA: first sorted position of the partition's run in the batch
+    uint32_t *keyA = runstart + p.PA;                                               // kSortedCap
+    uint32_t *keyB = keyA + kSortedCap;                                             // kSortedCap
+    __shared__ RollTile rt;
+    __shared__ TileStage ts;
+    __shared__ SmemSortScratch<kRollThreads> sc;
+    __shared__ uint32_t wtot[kRollThreads / 32 + 1];
+    uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) cur[i] = mybase[i];
+    __syncthreads();
+    const int K = p.K;
+    const uint32_t PA = p.PA;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
+
+    // sorted batch -> global memory. All threads call it with the same n.
+    auto flush = [&](uint32_t n) {
+        const uint32_t *S = smem_sort_field<kRollThreads, kSortedRounds>(keyA, keyB, n, kKeyPartShift, part_bits, sc);
+        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
+            const uint32_t part = S[q] >> kKeyPartShift;
+            if (q == 0 || (S[q - 1] >> kKeyPartShift) != part) runstart[part] = q;
+        }
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
+            const uint32_t key = S[q];
+            const uint32_t part = key >> kKeyPartShift, it = (key >> kKeyItShift) & 255u, j = key & 511u;
+            const Kmer<NW> f = kmer_window<NW>(static_cast<const uint64_t *>(ts.words + ts.off[it]), (int64_t)j, K);
+            const Kmer<NW> r = kmer_rc<NW>(f, K);
+            const Kmer<NW> k = kmer_is_minimal<NW>(f, r) ? f : r;
+            store_rec_stream<NW>(out + (cur[part] + (q - runstart[part])) * NW, k);
+        }
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
+            const uint32_t part = S[q] >> kKeyPartShift;
+            if (q + 1 == n || (S[q + 1] >> kKeyPartShift) != part) cur[part] += (unsigned long long)(q - runstart[part] + 1);
+        }
+        __syncthreads();
+    };
+
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t item0 = t * kATile;
+        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+        uint32_t unif = 0;
+        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
+        const bool staged = tile_stage(src, item0, nitems, ts);
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]);
+        const int too_long = __syncthreads_or((int)threadIdx.x < nitems && (int)rt.len[threadIdx.x] - K + 1 > 512);
+        const bool fast = staged && !too_long;
+        uint32_t npend = 0;                                    // the same value in every thread
+        for (uint32_t u0 = 0; u0 < nunits; u0 += kSortedUnits) {
+            const uint32_t u = u0 + threadIdx.x;
+            const bool have = threadIdx.x < (uint32_t)kSortedUnits && u < nunits;
+            uint64_t idw[kRollC / 4];
+            RollUnit q; q.it = 0; q.j0 = 0; q.cnt = 0;
+            uint32_t mask = 0;                                  // bit s: window j0 + s belongs to this sub-range
+            if (have) {
+#pragma unroll
+                for (int v = 0; v < kRollC / 8; ++v) {
+                    const ulonglong2 x = __ldg(row + (size_t)u * (kRollC / 8) + v);
+                    idw[2 * v] = x.x; idw[2 * v + 1] = x.y;
+                }
+                q = roll_unit(rt, nitems, u, unif, K);
+#pragma unroll
+                for (int s = 0; s < kRollC; ++s) {
+                    const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;      // 0xffff - id_lo stays >= PA
+                    if (s < q.cnt && part < PA) mask |= 1u << s;
+                }
+            }
+            // records of this round and this thread's offset among them (block scan, no atomics)
+            const uint32_t c = (uint32_t)__popc(mask);
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += x;
+            }
+            if (lane == 31) wtot[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t w = lane < kRollThreads / 32 ? wtot[lane] : 0u;
+                uint32_t winc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o);
+                    if (lane >= o) winc += x;
+                }
+                if (lane < kRollThreads / 32) wtot[lane] = winc - w;
+                if (lane == kRollThreads / 32 - 1) wtot[kRollThreads / 32] = winc;
+            }
+            __syncthreads();
+            const uint32_t T = wtot[kRollThreads / 32];
+            uint32_t off = wtot[warp] + inc - c;
+            __syncthreads();                                    // wtot is rewritten by the next round
+            if (fast) {                                          // T <= kSortedUnits * kRollC = kSortedCap
+                if (npend + T > (uint32_t)kSortedCap) { flush(npend); npend = 0; }
+                off += npend;
+                if (mask) {
+#pragma unroll
+                    for (int s = 0; s < kRollC; ++s) {          // static indexing keeps the id words in registers
+                        if (mask & (1u << s)) {
+                            const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;
+                            keyA[off++] = (part << kKeyPartShift) | ((uint32_t)q.it << kKeyItShift) | (uint32_t)(q.j0 + s);
+                        }
+                    }
+                }
+                npend += T;
+            } else if (T) {
+                // direct path (rare): roll through the unit, one shared-memory atomic per record on the cursor
+                if (npend) { flush(npend); npend = 0; }
+                if (mask) {
+                    const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
+                    RollState<NW> st;
+                    roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
+#pragma unroll
+                    for (int s = 0; s < kRollC; ++s) {
+                        if (s < q.cnt) {
+                            if (s > 0) roll_next<NW>(st, seq, K);
+                            if (mask & (1u << s)) {
+                                const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;
+                                const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                                const unsigned long long pos = atomicAdd(&cur[part], 1ull);
+                                store_rec_stream<NW>(out + pos * NW, k);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();                                // cursors are read non-atomically by the next flush
+            }
+        }
+        if (npend) flush(npend);                                // keys refer to THIS tile's staged reads
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur[i];   // chained launches continue here
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1179,6 +1340,7 @@ struct Tuning {
     uint32_t pa_max = 4096;
     uint32_t rmax = 11;
     int a_sub = 0;
+    bool a_sorted = true;        // SGPU_A_SORTED=0: second-generation partition kernel (A/B runs of this round)
     bool trace = false;
 };
 static const Tuning &tuning() {
@@ -1187,6 +1349,7 @@ static const Tuning &tuning() {
         if (const char *e = getenv("SGPU_PA_MAX")) x.pa_max = (uint32_t)std::min(8192, std::max(1, atoi(e)));
         if (const char *e = getenv("SGPU_RMAX")) x.rmax = (uint32_t)std::min(11, std::max(1, atoi(e)));
         if (const char *e = getenv("SGPU_A_SUB")) x.a_sub = std::min(64, std::max(0, atoi(e)));
+        if (const char *e = getenv("SGPU_A_SORTED")) x.a_sorted = atoi(e) != 0;
         x.trace = getenv("SGPU_TRACE") != nullptr;
         return x;
     }();
@@ -1451,6 +1614,20 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
             const size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (job.use_ids && tuning().a_sorted) {
+                // third generation: id sweep -> ballot-sorted key batches -> run flush; one launch per source covers the whole pass
+                int part_bits = 0;
+                while ((1u << part_bits) < PA) ++part_bits;
+                const size_t smem_s = (size_t)PA * (sizeof(unsigned long long) + sizeof(uint32_t)) + (size_t)2 * kSortedCap * sizeof(uint32_t);
+                SG_CUDA(cudaFuncSetAttribute(levelA_scatter_sorted_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                for (size_t si = 0; si < job.srcs.size(); ++si) {
+                    const Src &src = job.srcs[si];
+                    if (src.n == 0) continue;
+                    levelA_scatter_sorted_k<NW><<<G, kRollThreads, smem_s, st>>>(src, pa, base.p, X, job.tile_off[si].p, job.ids[si].p, p_lo, PA, 0u, part_bits);
+                    ctx->launches++;
+                }
+            } else {
+            // second generation (kept for sources without the id array): roll + one shared-memory atomic per record.
             // partition sub-ranges (only with the id array, where a foreign window costs just the roll): fewer lines and pages open
             // per CTA. A sub-range costs one more roll over ALL windows of the source: worth it when the pass holds most of the job's
             // records (measured: 20 M reads / 1 pass: 46.5 / 36.7 / 31.5 ms with 1 / 2 / 4 sub-ranges; 100 M reads / 5 passes: 184 ms
@@ -1474,6 +1651,7 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
                         levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X, nullptr, nullptr, 0u, PA, 0u);
                     ctx->launches++;
                 }
+            }
             }
         }
     } else {
@@ -1721,56 +1899,90 @@ void kset_checksum(const KSet *ks, uint64_t *out4) {
 // stores are not write-combined and ran at ~1 GB/s.)
 // ------------------------------------------------------------------------------------------------------------
 struct DistPlan {
-    int world = 1, rank = 0, B = 0, rA = 0, npass = 1;
+    int world = 1, rank = 0, B = 0, rA = 0;
     uint32_t PA_all = 0;
-    std::vector<int> pass_b;                   // npass+1 bucket boundaries
+    std::vector<int> pass_b;                   // bucket boundaries of the passes planned so far (starts as {0})
     std::vector<uint64_t> tot;                 // PA_all: records per partition summed over ranks
-    uint64_t max_recv = 0;                     // records, max over (pass, rank)
-    uint64_t max_send = 0;                     // records a rank partitions locally in one pass, max over (pass, rank)
-    int own_lo(int p, int g) const { int nb = pass_b[p + 1] - pass_b[p]; return pass_b[p] + (int)((int64_t)nb * g / world); }
-    uint64_t recv(int p, int g) const {
-        uint64_t s = 0;
-        for (size_t q = (size_t)own_lo(p, g) << rA; q < ((size_t)own_lo(p, g + 1) << rA); ++q) s += tot[q];
-        return s;
+    std::vector<uint64_t> Tb;                  // B+1: records in buckets < b, all ranks
+    std::vector<uint64_t> Ps;                  // world x (B+1): records of rank s in buckets < b
+    uint64_t pass_target = 0;                  // records per pass aimed for (equal passes: a tiny last pass still costs a full id sweep)
+    int npass() const { return (int)pass_b.size() - 1; }
+    static int own_lo_of(int b_lo, int b_hi, int world, int g) { return b_lo + (int)((int64_t)(b_hi - b_lo) * g / world); }
+    int own_lo(int p, int g) const { return own_lo_of(pass_b[p], pass_b[p + 1], world, g); }
+    // largest number of records an owner receives / a rank sends if [b_lo, b_hi) is one pass
+    void maxima(int b_lo, int b_hi, uint64_t *mx, uint64_t *ms) const {
+        *mx = 0; *ms = 0;
+        for (int g = 0; g < world; ++g) *mx = std::max(*mx, Tb[own_lo_of(b_lo, b_hi, world, g + 1)] - Tb[own_lo_of(b_lo, b_hi, world, g)]);
+        for (int s = 0; s < world; ++s) *ms = std::max(*ms, Ps[(size_t)s * (B + 1) + b_hi] - Ps[(size_t)s * (B + 1) + b_lo]);
     }
 };
 
 static const double kDistHeadroom = 1.05;      // staging / merged buffers are sized 5 % above the planned maximum
 
-// device bytes a plan with these maxima needs: staging buffer (doubles as ping-pong partner, so >= recv), merged buffer, the
-// outputs of all passes (distinct/instances <= 0.6 assumed) and the per-pass tables
-static double dist_plan_bytes(uint64_t mx, uint64_t ms, int np, size_t W, uint64_t fixed_bytes) {
-    return ((double)std::max(mx, ms) + (double)mx) * W * (kDistHeadroom + 0.05) + (double)mx * (W + 4) * 0.6 * np + (double)fixed_bytes;
+// device bytes one pass needs next to what is already resident: staging buffer (doubles as the sort's ping-pong partner, so
+// >= recv), merged buffer, its own output (distinct/instances <= 0.6 assumed, like the single-GPU planner) and the per-pass tables
+static double dist_pass_bytes(uint64_t mx, uint64_t ms, size_t W, uint64_t fixed_bytes) {
+    return ((double)std::max(mx, ms) + (double)mx) * W * (kDistHeadroom + 0.03) + (double)mx * (W + 4) * 0.6 + (double)fixed_bytes;
 }
 
-// pure host function (also exported for the CPU/gloo tests): identical on every rank given the same inputs
-void dist_make_plan(DistPlan &pl, int world, int rank, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, size_t W, uint64_t fixed_bytes) {
+// pure host functions (also exported for the CPU/gloo tests): identical on every rank given the same inputs
+void dist_plan_tables(DistPlan &pl, int world, int rank, int B, int rA, const uint64_t *cnt_all) {
     pl.world = world; pl.rank = rank; pl.B = B; pl.rA = rA; pl.PA_all = (uint32_t)B << rA;
     pl.tot.assign(pl.PA_all, 0);
-    for (int s = 0; s < world; ++s)
+    pl.Tb.assign((size_t)B + 1, 0);
+    pl.Ps.assign((size_t)world * (B + 1), 0);
+    for (int s = 0; s < world; ++s) {
         for (uint32_t q = 0; q < pl.PA_all; ++q) pl.tot[q] += cnt_all[(size_t)s * pl.PA_all + q];
-    auto evaluate = [&](int np) {
-        pl.npass = np;
-        pl.pass_b.assign(np + 1, 0);
-        for (int p = 0; p <= np; ++p) pl.pass_b[p] = (int)((int64_t)B * p / np);
-        uint64_t mx = 0, ms = 0;
-        for (int p = 0; p < np; ++p) {
-            for (int g = 0; g < world; ++g) mx = std::max(mx, pl.recv(p, g));
-            for (int s = 0; s < world; ++s) {
-                uint64_t t = 0;
-                for (size_t q = (size_t)pl.pass_b[p] << rA; q < ((size_t)pl.pass_b[p + 1] << rA); ++q) t += cnt_all[(size_t)s * pl.PA_all + q];
-                ms = std::max(ms, t);
-            }
+        for (int b = 0; b < B; ++b) {
+            uint64_t t = 0;
+            for (uint32_t q = (uint32_t)b << rA; q < ((uint32_t)(b + 1) << rA); ++q) t += cnt_all[(size_t)s * pl.PA_all + q];
+            pl.Ps[(size_t)s * (B + 1) + b + 1] = pl.Ps[(size_t)s * (B + 1) + b] + t;
         }
-        pl.max_recv = mx; pl.max_send = ms;
-    };
-    for (int np = 1;; ++np) {
-        evaluate(np);
-        // every pass must hold at least one bucket, and its partitions must fit the scatter kernel's shared-memory tables
-        const bool tables_fit = (((size_t)(B + np - 1) / np) << rA) <= (size_t)kLevelAMaxParts;
-        if (np >= B) break;
-        if (tables_fit && dist_plan_bytes(pl.max_recv, pl.max_send, np, W, fixed_bytes) <= (double)budget_bytes) break;
     }
+    for (int b = 0; b <= B; ++b) {           // Tb = sum over ranks of Ps
+        uint64_t t = 0;
+        for (int s = 0; s < world; ++s) t += pl.Ps[(size_t)s * (B + 1) + b];
+        pl.Tb[b] = t;
+    }
+    pl.pass_b.assign(1, 0);
+    pl.pass_target = 0;
+}
+// the greedy "as many whole buckets as fit" step shared by the simulation and the real planning: returns b_hi > b_lo
+static int dist_greedy_pass(const DistPlan &pl, int b_lo, double budget, size_t W, uint64_t fixed_bytes, uint64_t target) {
+    int b_hi = b_lo;
+    while (b_hi < pl.B) {
+        uint64_t mx, ms;
+        pl.maxima(b_lo, b_hi + 1, &mx, &ms);
+        const uint64_t recs = pl.Tb[b_hi + 1] - pl.Tb[b_lo];
+        if (b_hi > b_lo && (dist_pass_bytes(mx, ms, W, fixed_bytes) > budget || (target && recs > target) ||
+                            ((size_t)(b_hi + 1 - b_lo) << pl.rA) > (size_t)kLevelAMaxParts)) break;
+        ++b_hi;
+    }
+    return b_hi;
+}
+// plan the next pass against `budget_bytes` = what every rank can allocate NOW (minimum over ranks). Returns false when all
+// buckets are done. The first call also fixes the pass size aimed for by simulating the whole job (outputs of earlier passes
+// stay resident: ~half a record's bytes per record, as measured on read sets with errors).
+bool dist_next_pass(DistPlan &pl, uint64_t budget_bytes, size_t W, uint64_t fixed_bytes, uint64_t *mx_out, uint64_t *ms_out) {
+    const int b_lo = pl.pass_b.back();
+    if (b_lo >= pl.B) return false;
+    if (pl.pass_target == 0) {
+        double lim = (double)budget_bytes;
+        int np = 0, b = 0;
+        while (b < pl.B) {
+            const int e = dist_greedy_pass(pl, b, lim, W, fixed_bytes, 0);
+            uint64_t mx, ms;
+            pl.maxima(b, e, &mx, &ms);
+            lim -= (double)mx * (W + 4) * 0.5;
+            b = e; ++np;
+        }
+        const uint64_t total = pl.Tb[pl.B];
+        pl.pass_target = total / (uint64_t)np + total / 64 + 1;
+    }
+    const int b_hi = dist_greedy_pass(pl, b_lo, (double)budget_bytes, W, fixed_bytes, pl.pass_target);
+    pl.pass_b.push_back(b_hi);
+    pl.maxima(b_lo, b_hi, mx_out, ms_out);
+    return true;
 }
 
 struct PullSrc { const uint64_t *sbuf; const uint64_t *pbase; const uint32_t *blk; };     // one source rank, as seen from this GPU
@@ -1987,23 +2199,42 @@ DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
 uint32_t dist_num_partitions(const DistState *d) { return d->plan.PA_all; }
 void dist_local_counts(DistState *d, uint64_t *h_out) { d->local_counts(h_out); }
 
-void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records) {
+static const uint64_t kDistFixedBytes = (uint64_t)192 << 20;      // per-pass tables (segments, work lists, scans) next to the big buffers
+
+void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t *total_records) {
     Ctx *ctx = d->ctx;
-    const size_t W = (size_t)8 * d->nw;
-    dist_make_plan(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all, budget_bytes, W, (uint64_t)256 << 20);
+    dist_plan_tables(d->plan, d->plan.world, d->plan.rank, d->B, d->plan.rA, cnt_all);
     d->h_cnt_all.assign(cnt_all, cnt_all + (size_t)d->plan.world * d->plan.PA_all);
     d->d_bsz.alloc(ctx, (size_t)d->B);
     SG_CUDA(cudaMemsetAsync(d->d_bsz.p, 0, (size_t)d->B * 8, ctx->stream));
     d->out = new KSet();
     d->out->ctx = ctx; d->out->K = d->K; d->out->nw = d->nw; d->out->B = d->B; d->out->has_counts = d->want_counts;
-    // buffers the peers read must live inside the arena (one driver allocation, mapped by the peers as a whole)
-    uint32_t max_pa = 1;
-    for (int p = 0; p < d->plan.npass; ++p) max_pa = std::max(max_pa, (uint32_t)(d->plan.pass_b[p + 1] - d->plan.pass_b[p]) << d->plan.rA);
-    d->sbuf.alloc(ctx, (size_t)((double)std::max(d->plan.max_recv, d->plan.max_send) * kDistHeadroom) * d->nw + 16);
-    d->xbuf.alloc(ctx, (size_t)((double)d->plan.max_recv * kDistHeadroom) * d->nw + 16);
-    d->pbase.alloc(ctx, (size_t)d->G * max_pa);
     SG_CUDA(cudaStreamSynchronize(ctx->stream));
-    *npass = d->plan.npass; *xchg_records = d->plan.max_recv;
+    *total_records = d->plan.Tb[d->B];
+}
+
+// bytes this rank could allocate for the next pass (the previous pass's staging / merged buffers are given back first)
+uint64_t dist_free_bytes(DistState *d) {
+    d->sbuf.release(); d->xbuf.release(); d->pbase.release();
+    return (uint64_t)d->ctx->free_bytes();
+}
+
+// plan the next pass against budget_bytes (the minimum of dist_free_bytes over the ranks, so that every rank takes the same
+// decision) and allocate its buffers. Returns the pass index, or -1 when every bucket has been processed.
+int dist_next_pass(DistState *d, uint64_t budget_bytes) {
+    Ctx *ctx = d->ctx;
+    const size_t W = (size_t)8 * d->nw;
+    d->sbuf.release(); d->xbuf.release(); d->pbase.release();
+    uint64_t mx = 0, ms = 0;
+    if (!dist_next_pass(d->plan, budget_bytes, W, kDistFixedBytes, &mx, &ms)) return -1;
+    const int p = d->plan.npass() - 1;
+    // buffers the peers read must live inside the arena (one driver allocation, mapped by the peers as a whole)
+    const uint32_t pa = (uint32_t)(d->plan.pass_b[p + 1] - d->plan.pass_b[p]) << d->plan.rA;
+    d->sbuf.alloc(ctx, (size_t)((double)std::max(mx, ms) * kDistHeadroom) * d->nw + 16);
+    d->xbuf.alloc(ctx, (size_t)((double)mx * kDistHeadroom) * d->nw + 16);
+    d->pbase.alloc(ctx, (size_t)d->G * pa);
+    d->peers.clear();
+    return p;
 }
 
 // descriptor a rank publishes (all_gather) after dist_plan: arena handle + where its peer-readable buffers are inside the arena
@@ -2061,18 +2292,18 @@ void dist_open_peers(DistState *d, const uint8_t *descs) {
 }
 
 void dist_scatter(DistState *d, int p) {
-    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    SG_CHECK(p >= 0 && p == d->plan.npass() - 1 && d->sbuf.p, 2, "bad pass (sgpu_dist_next_pass decides the current one)");
     d->scatter(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // the staging buffer is complete; peers may read it after the next barrier
 }
 void dist_exchange(DistState *d, int p) {
-    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    SG_CHECK(p >= 0 && p == d->plan.npass() - 1 && d->sbuf.p, 2, "bad pass (sgpu_dist_next_pass decides the current one)");
     SG_CHECK((int)d->peers.size() == d->plan.world, 2, "sgpu_dist_open_peers has not run");
     d->pull(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));        // this rank no longer reads any peer's staging buffer
 }
 void dist_sort(DistState *d, int p) {
-    SG_CHECK(p >= 0 && p < d->plan.npass, 2, "bad pass");
+    SG_CHECK(p >= 0 && p == d->plan.npass() - 1 && d->sbuf.p, 2, "bad pass (sgpu_dist_next_pass decides the current one)");
     d->sort(p);
     SG_CUDA(cudaStreamSynchronize(d->ctx->stream));
 }
@@ -2092,12 +2323,20 @@ KSet *dist_end(DistState *d) {
 }
 void dist_free(DistState *d) { delete d; }
 
+// the whole pass sequence for a FIXED budget (CPU tests): every pass is planned against the budget minus the estimated outputs of
+// the passes before it
 int dist_plan_host(int world, int B, int rA, const uint64_t *cnt_all, uint64_t budget_bytes, int record_bytes, int *pass_b, uint64_t *max_recv) {
     DistPlan pl;
-    dist_make_plan(pl, world, 0, B, rA, cnt_all, budget_bytes, (size_t)record_bytes, 0);
-    for (int p = 0; p <= pl.npass; ++p) pass_b[p] = pl.pass_b[p];
-    *max_recv = pl.max_recv;
-    return pl.npass;
+    dist_plan_tables(pl, world, 0, B, rA, cnt_all);
+    double lim = (double)budget_bytes;
+    uint64_t mx = 0, ms = 0, worst = 0;
+    while (dist_next_pass(pl, (uint64_t)std::max(0.0, lim), (size_t)record_bytes, 0, &mx, &ms)) {
+        worst = std::max(worst, mx);
+        lim -= (double)mx * (record_bytes + 4) * 0.5;
+    }
+    for (int p = 0; p <= pl.npass(); ++p) pass_b[p] = pl.pass_b[p];
+    *max_recv = worst;
+    return pl.npass();
 }
 
 }  // namespace sg

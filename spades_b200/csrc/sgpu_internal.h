@@ -280,7 +280,9 @@ struct DistPlan;
 DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank);
 uint32_t dist_num_partitions(const DistState *d);
 void dist_local_counts(DistState *d, uint64_t *h_out);
-void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t budget_bytes, int *npass, uint64_t *xchg_records);
+void dist_plan(DistState *d, const uint64_t *cnt_all, uint64_t *total_records);
+uint64_t dist_free_bytes(DistState *d);
+int dist_next_pass(DistState *d, uint64_t budget_bytes);
 void dist_ipc_handle(DistState *d, uint8_t *out96);
 void dist_open_peers(DistState *d, const uint8_t *descs);
 void dist_scatter(DistState *d, int p);

@@ -35,16 +35,15 @@ __device__ __forceinline__ void smem_lsd_pass(const uint32_t *A, uint32_t *Bout,
     const uint32_t rounds = (n + 32u * W - 1u) / (32u * W);          // per warp; <= MAX_ROUNDS
     const uint32_t w0 = (uint32_t)warp * rounds * 32u;
     uint32_t *mycnt = sc.cnt + warp * kSortBins;
-    uint32_t x[MAX_ROUNDS];
-    uint32_t rk[MAX_ROUNDS];
+    uint32_t rk[MAX_ROUNDS];                                           // rank of the round's item inside (warp, digit); the item itself is re-read
 #pragma unroll
     for (int r = 0; r < MAX_ROUNDS; ++r) {
-        x[r] = 0xffffffffu; rk[r] = 0;
+        rk[r] = 0;
         if ((uint32_t)r < rounds) {                                    // uniform across the CTA
             const uint32_t i = w0 + (uint32_t)r * 32u + (uint32_t)lane;
             const bool valid = i < n;
-            if (valid) x[r] = A[i];
-            const uint32_t d = (x[r] >> lo) & dmask;
+            const uint32_t x = valid ? A[i] : 0xffffffffu;
+            const uint32_t d = (x >> lo) & dmask;
             uint32_t peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
             for (int b = 0; b < kSortDigitBits; ++b) {
@@ -81,8 +80,9 @@ __device__ __forceinline__ void smem_lsd_pass(const uint32_t *A, uint32_t *Bout,
         if ((uint32_t)r < rounds) {
             const uint32_t i = w0 + (uint32_t)r * 32u + (uint32_t)lane;
             if (i < n) {
-                const uint32_t d = (x[r] >> lo) & dmask;
-                Bout[sc.binbase[d] + mycnt[d] + rk[r]] = x[r];
+                const uint32_t x = A[i];
+                const uint32_t d = (x >> lo) & dmask;
+                Bout[sc.binbase[d] + mycnt[d] + rk[r]] = x;
             }
         }
     }

@@ -40,30 +40,40 @@ class DistributedKMerCounter:
             gathered = [torch.empty_like(t_local) for _ in range(world)]
             dist.all_gather(gathered, t_local, group=self.group)
             all_counts = np.ascontiguousarray(torch.stack(gathered).cpu().numpy().view(np.uint64))
-            if budget_bytes is None:
-                # what every rank can still allocate inside its arena (the level-A tables and partition ids are already resident)
-                tb = torch.tensor([ctx.times()["cached_bytes"]], dtype=torch.int64, device=backend_dev)
-                dist.all_reduce(tb, op=dist.ReduceOp.MIN, group=self.group)
-                budget_bytes = int(int(tb.item()) * 0.92)
-            npass, xrec = C.c_int(), C.c_uint64()
-            ctx.check(L.sgpu_dist_plan(h, all_counts.ctypes.data_as(C.c_void_p), budget_bytes, C.byref(npass), C.byref(xrec)))
-            desc = np.zeros(SGPU_IPC_BYTES, np.uint8)
-            ctx.check(L.sgpu_dist_ipc_handle(h, desc.ctypes.data_as(C.c_void_p)))
-            t_h = torch.from_numpy(desc).to(backend_dev)
-            hs = [torch.empty_like(t_h) for _ in range(world)]
-            dist.all_gather(hs, t_h, group=self.group)
-            descs = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
-            ctx.check(L.sgpu_dist_open_peers(h, descs.ctypes.data_as(C.c_void_p)))     # peers' arenas are mapped once per process
-            for p in range(npass.value):
-                ctx.check(L.sgpu_dist_scatter(h, p))    # local partition into the staging buffer
-                dist.barrier(group=self.group)          # every rank's staging buffer is complete
-                ctx.check(L.sgpu_dist_exchange(h, p))   # one kernel: pull my pieces from all peers over NVLink + merge
-                dist.barrier(group=self.group)          # nobody reads my staging buffer any more (it becomes the sort's partner)
-                ctx.check(L.sgpu_dist_sort(h, p))
+            total = C.c_uint64()
+            ctx.check(L.sgpu_dist_plan(h, all_counts.ctypes.data_as(C.c_void_p), C.byref(total)))
+            npass = 0
+            while True:
+                # every pass is planned against what ALL ranks can allocate right now (earlier passes' outputs are resident)
+                if budget_bytes is None:
+                    fb = C.c_uint64()
+                    ctx.check(L.sgpu_dist_free_bytes(h, C.byref(fb)))
+                    tb = torch.tensor([fb.value], dtype=torch.int64, device=backend_dev)
+                    dist.all_reduce(tb, op=dist.ReduceOp.MIN, group=self.group)
+                    budget = int(int(tb.item()) * 0.90)
+                else:
+                    budget = int(budget_bytes)                 # tests: a fixed per-pass budget
+                p = C.c_int()
+                ctx.check(L.sgpu_dist_next_pass(h, budget, C.byref(p)))
+                if p.value < 0:
+                    break
+                desc = np.zeros(SGPU_IPC_BYTES, np.uint8)
+                ctx.check(L.sgpu_dist_ipc_handle(h, desc.ctypes.data_as(C.c_void_p)))
+                t_h = torch.from_numpy(desc).to(backend_dev)
+                hs = [torch.empty_like(t_h) for _ in range(world)]
+                dist.all_gather(hs, t_h, group=self.group)
+                descs = np.ascontiguousarray(torch.stack(hs).cpu().numpy())
+                ctx.check(L.sgpu_dist_open_peers(h, descs.ctypes.data_as(C.c_void_p)))     # peers' arenas are mapped once per process
+                ctx.check(L.sgpu_dist_scatter(h, p.value))    # local partition into the staging buffer
+                dist.barrier(group=self.group)                # every rank's staging buffer is complete
+                ctx.check(L.sgpu_dist_exchange(h, p.value))   # one kernel: pull my pieces from all peers over NVLink + merge
+                dist.barrier(group=self.group)                # nobody reads my staging buffer any more (it becomes the sort's partner)
+                ctx.check(L.sgpu_dist_sort(h, p.value))
+                npass += 1
             dist.barrier(group=self.group)
             ks = C.c_void_p()
             ctx.check(L.sgpu_dist_end(h, C.byref(ks)))
-            self.npass = npass.value
+            self.npass = npass
             return KMerDiskStorage(ctx, ks)
         finally:
             L.sgpu_dist_free(h)
