@@ -33,16 +33,30 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
             : KMerCounter<RtSeq>(K), work_dir_(work_dir), ctx_(ctx), mode_(mode) { check(sgpu_reads_clear(ctx_)); }
     ~GpuKMerDiskCounter() override { if (last_) sgpu_kset_free(last_); }
 
-    // the payload of the reference's binary read records: Sequence::data(), ceil(size/32) words (sequence.hpp:808-830)
+    // the payload of the reference's binary read records: Sequence::data(), ceil(size/32) words (sequence.hpp:808-830). Reads are
+    // collected in a host batch and cross the C ABI kBatchReads at a time (one call per read would be 100 M calls for config 3).
     void AddRead(const Sequence &s) {
         if (s.size() == 0) return;
-        words_.resize(0);
-        const size_t nw = (s.size() + 31) / 32;
-        words_.resize(nw, 0);
-        for (size_t i = 0; i < s.size(); ++i) words_[i >> 5] |= (uint64_t)s[i] << ((i & 31) << 1);      // rtseq.hpp:379-382 packing
-        const uint64_t off = 0;
-        const uint32_t len = (uint32_t)s.size();
-        check(sgpu_reads_append_packed(ctx_, words_.data(), nw, &off, &len, 1));
+        const size_t nw = (s.size() + 31) / 32, w0 = words_.size();
+        words_.resize(w0 + nw, 0);
+        uint64_t *w = words_.data() + w0;
+        for (size_t i = 0; i < s.size(); ++i) w[i >> 5] |= (uint64_t)s[i] << ((i & 31) << 1);          // rtseq.hpp:379-382 packing
+        offs_.push_back((uint64_t)w0);
+        lens_.push_back((uint32_t)s.size());
+        if (lens_.size() >= kBatchReads) Flush();
+    }
+    // every read of a stream (io::ReadStream<io::SingleReadSeq> and friends: `stream >> read` until eof(), read.sequence())
+    template<class Stream>
+    size_t AddStream(Stream &stream) {
+        typename Stream::ReadT r;
+        size_t n = 0;
+        while (!stream.eof()) { stream >> r; AddRead(r.sequence()); ++n; }
+        return n;
+    }
+    void Flush() {
+        if (lens_.empty()) return;
+        check(sgpu_reads_append_packed(ctx_, words_.data(), words_.size(), offs_.data(), lens_.data(), (int64_t)lens_.size()));
+        words_.clear(); offs_.clear(); lens_.clear();
     }
 
     // a whole FASTA / FASTQ (plain or gzip) file through the library's ingest (kseq semantics + LongestValid, like io::EasyStream,
@@ -54,6 +68,7 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
             sgpu_read_batch_free(b);
             FATAL_ERROR("spades_b200: " << why);
         }
+        Flush();                                                     // keep the order of reads added one by one before the file
         const size_t n = (size_t)sgpu_read_batch_num_reads(b);
         const int rc = sgpu_reads_append_batch(ctx_, b);
         sgpu_read_batch_free(b);
@@ -64,6 +79,7 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
     size_t kmer_size() const override { return RtSeq::GetDataSize(this->k()) * sizeof(RtSeq::DataType); }
 
     KMerDiskStorage<RtSeq> Count(unsigned num_buckets, unsigned /* num_threads */) override {
+        Flush();
         if (last_) { sgpu_kset_free(last_); last_ = nullptr; }
         check(sgpu_count(ctx_, (int)this->k(), (int)num_buckets, mode_, &last_));
         INFO("K-mer counting done on the GPU. There are " << sgpu_kset_size(last_) << " kmers in total. ");
@@ -92,7 +108,52 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
     sgpu_ctx *ctx_;
     int mode_;
     sgpu_kset *last_ = nullptr;
-    std::vector<uint64_t> words_;
+    static constexpr size_t kBatchReads = 1u << 20;
+    std::vector<uint64_t> words_, offs_;
+    std::vector<uint32_t> lens_;
+};
+
+// The splitter-level seam: kmers::KMerSplitter<RtSeq> (kmer_splitter.hpp:25-53). Split() leaves, per bucket, ONE sorted-unique run
+// of W-byte records in <tmp>/kmers_raw.<i> plus <file>.idx holding its length (what KMerSortingSplitter::DumpBuffers appends per
+// dump, kmer_splitter.hpp:123-170), so the reference's own KMerDiskCounter<RtSeq>(work_dir, GpuKMerSplitter(...)) merges them
+// (one run each: a copy) and everything downstream is untouched:
+//     kmers::KMerDiskCounter<RtSeq> counter(workdir, kmers::GpuKMerSplitter(workdir, K, ctx, SGPU_CANONICAL));
+//     auto storage = counter.Count(num_buckets, nthreads);
+// Reads are added to the context beforehand (GpuKMerDiskCounter::AddRead / AddFile or sgpu_reads_* directly).
+class GpuKMerSplitter : public KMerSplitter<RtSeq> {
+  public:
+    using typename KMerSplitter<RtSeq>::RawKMers;
+    GpuKMerSplitter(fs::TmpDir work_dir, unsigned K, sgpu_ctx *ctx, int mode) : KMerSplitter<RtSeq>(work_dir, K), ctx_(ctx), mode_(mode) {}
+    GpuKMerSplitter(const std::filesystem::path &work_dir, unsigned K, sgpu_ctx *ctx, int mode)
+            : KMerSplitter<RtSeq>(work_dir, K), ctx_(ctx), mode_(mode) {}
+
+    RawKMers Split(size_t num_files, unsigned /* nthreads */) override {
+        this->bucket_.reset(num_files);
+        sgpu_kset *ks = nullptr;
+        if (sgpu_count(ctx_, (int)this->K_, (int)num_files, mode_, &ks)) FATAL_ERROR("spades_b200: " << sgpu_last_error(ctx_));
+        RawKMers out;
+        auto tmp_prefix = this->work_dir_->tmp_file("kmers_raw");
+        for (unsigned i = 0; i < num_files; ++i) out.emplace_back(tmp_prefix->CreateDep(std::to_string(i)));
+        std::string prefix = out[0]->file().native();
+        prefix.resize(prefix.rfind('.'));
+        if (sgpu_kset_write_buckets(ks, prefix.c_str())) { sgpu_kset_free(ks); FATAL_ERROR("spades_b200: " << sgpu_last_error(ctx_)); }
+        std::vector<int64_t> bsz(num_files);
+        sgpu_kset_bucket_sizes(ks, bsz.data());
+        for (unsigned i = 0; i < num_files; ++i) {                   // run lengths: one run per bucket
+            const std::string idx = out[i]->file().native() + ".idx";
+            FILE *f = fopen(idx.c_str(), "wb");
+            if (!f) FATAL_ERROR("spades_b200: cannot write " << idx);
+            const size_t n = (size_t)bsz[i];
+            if (n) fwrite(&n, sizeof n, 1, f);
+            fclose(f);
+        }
+        sgpu_kset_free(ks);
+        return out;
+    }
+
+  private:
+    sgpu_ctx *ctx_;
+    int mode_;
 };
 
 // index: kmers::KMerIndex<traits>. KMerIndex befriends only KMerIndexBuilder (kmer_index.hpp:149-150) but deserialize is public

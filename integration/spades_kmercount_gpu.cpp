@@ -12,6 +12,7 @@
 //   3. both indices map every k-mer of final_kmers to the same slot (and that map is a bijection onto [0, n)).
 // Exit code 0 only if all of that holds.
 #include "gpu_kmer_counter.hpp"
+#include <iterator>
 
 #include "kmer_index/kmer_mph/kmer_index_traits.hpp"
 #include "utils/logger/log_writers.hpp"
@@ -89,6 +90,18 @@ int main(int argc, char **argv) {
         const std::filesystem::path out = workdir / "final_kmers";
         std::rename(final_kmers->file().c_str(), out.c_str());       // kmercount.cpp:222-223
         INFO("K-mer counting done, kmers saved to " << out);
+
+        // 4. the splitter-level seam: the reference's OWN KMerDiskCounter over kmers::GpuKMerSplitter (one sorted-unique run + .idx per
+        //    bucket) must arrive at the same final_kmers
+        {
+            kmers::KMerDiskCounter<RtSeq> ref_counter(workdir, kmers::GpuKMerSplitter(workdir, K, ctx, SGPU_ALL_WINDOWS));
+            auto st2 = ref_counter.CountAll(B, 1, /* merge */ true);
+            std::ifstream a(out, std::ios::binary), b2(st2.final_kmers()->file(), std::ios::binary);
+            const std::string sa((std::istreambuf_iterator<char>(a)), std::istreambuf_iterator<char>());
+            const std::string sb((std::istreambuf_iterator<char>(b2)), std::istreambuf_iterator<char>());
+            if (st2.total_kmers() != total || sa != sb) { ERROR("KMerDiskCounter over GpuKMerSplitter differs from GpuKMerDiskCounter"); ++bad; }
+            else INFO("reference KMerDiskCounter over GpuKMerSplitter: identical final_kmers (" << st2.total_kmers() << " k-mers)");
+        }
     }
     sgpu_destroy(ctx);
     return bad ? 1 : 0;

@@ -6,7 +6,6 @@
 #include "../../include/spades_b200.h"
 #include "graph.h"
 #include "sgpu_internal.h"
-#include "smem_sort.cuh"
 
 using namespace sg;
 
@@ -525,35 +524,6 @@ static void selftest_nw(Ctx *c, int on_device, int op, int K, uint64_t arg, cons
     SG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     SG_CUDA(cudaStreamSynchronize(c->stream));
 }
-// ops 12 / 13 / 14: smem_sort.cuh (ballot-ranked stable LSD sort in shared memory) for CTAs of 512 x 16, 256 x 8 and 1024 x 8 items.
-// keys[i] (low 32 bits) = item i, arg = (lo << 8) | nbits; out[i] = item at sorted position i (the caller compares with a stable host sort)
-template <int THREADS, int ROUNDS>
-__global__ void __launch_bounds__(THREADS) selftest_sort_k(const uint64_t *keys, uint32_t n, int lo, int nbits, uint64_t *out) {
-    extern __shared__ uint32_t sm_sort[];
-    uint32_t *A = sm_sort, *B = sm_sort + THREADS * ROUNDS;
-    __shared__ SmemSortScratch<THREADS> sc;
-    for (uint32_t i = threadIdx.x; i < n; i += THREADS) A[i] = (uint32_t)keys[i];
-    __syncthreads();
-    const uint32_t *S = smem_sort_field<THREADS, ROUNDS>(A, B, n, lo, nbits, sc);
-    for (uint32_t i = threadIdx.x; i < n; i += THREADS) out[i] = S[i];
-}
-template <int THREADS, int ROUNDS>
-static void selftest_sort(Ctx *c, uint64_t arg, const uint64_t *keys, int64_t n, uint64_t *out) {
-    SG_CHECK(c, SGPU_EINVAL, "device self test needs a context");
-    SG_CHECK(n >= 0 && n <= THREADS * ROUNDS, SGPU_EINVAL, "sort self test: too many items");
-    const int lo = (int)(arg >> 8), nbits = (int)(arg & 255);
-    SG_CHECK(lo >= 0 && nbits >= 0 && lo + nbits <= 32, SGPU_EINVAL, "sort self test: bad bit field");
-    DArr<uint64_t> dk(c, (size_t)n + 1), dout(c, (size_t)n + 1);
-    SG_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    const size_t smem = (size_t)2 * THREADS * ROUNDS * sizeof(uint32_t);
-    SG_CUDA(cudaFuncSetAttribute(selftest_sort_k<THREADS, ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    selftest_sort_k<THREADS, ROUNDS><<<1, THREADS, smem, c->stream>>>(dk.p, (uint32_t)n, lo, nbits, dout.p);
-    c->launches++;
-    SG_CUDA(cudaGetLastError());
-    SG_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-    SG_CUDA(cudaStreamSynchronize(c->stream));
-}
-
 // op 11 (host only): the sector-pairing mailbox protocol of pair_mailbox.cuh under real concurrency, see selftest_host.cpp
 extern "C" int sg_selftest_pair_mailbox(uint64_t arg, int64_t per_thread, uint64_t *out);
 
@@ -564,15 +534,6 @@ extern "C" int sgpu_selftest(sgpu_ctx *ctx, int on_device, int op, int K, uint64
     if (op == 11) {
         if (on_device || n < 3) return SGPU_EINVAL;
         return sg_selftest_pair_mailbox(arg, (int64_t)keys[0], out);
-    }
-    if (op >= 12 && op <= 14) {
-        if (!on_device) return SGPU_EINVAL;
-        API_TRY(c, {
-            SG_CUDA(cudaSetDevice(c->device));
-            if (op == 12) selftest_sort<512, 16>(c, arg, keys, n, out);
-            else if (op == 13) selftest_sort<256, 8>(c, arg, keys, n, out);
-            else selftest_sort<1024, 8>(c, arg, keys, n, out);
-        })
     }
     API_TRY(c, {
         if (on_device) SG_CUDA(cudaSetDevice(c->device));

@@ -23,7 +23,6 @@
 
 #include "sgpu_internal.h"
 #include "pair_mailbox.cuh"
-#include "smem_sort.cuh"
 
 namespace sg {
 
@@ -553,165 +552,11 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
     for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
 }
 
-// ---- the radix-partition kernel, third generation: id sweep -> key batch -> ballot-ranked sort -> run flush -----------------------
-// What bounded the kernel above (round 1 + the round-2 sweep): every record costs a shared-memory atomic on its cursor and leaves as
-// a lone 16-byte store into one of ~512 open streams (0.9-1.1 TB/s whatever the instruction count). Here a CTA never touches the
-// cursors per record. Per tile it only LOOKS at the 2-byte ids: a window that belongs to the sub-range becomes a 32-bit key
-// (partition | read in tile | window), keys are collected without atomics (block scan of the per-thread counts), sorted by partition
-// with smem_sort.cuh (ballots, no atomics), and the sorted batch is flushed run by run: consecutive threads extract consecutive
-// records of ONE partition from the staged reads and store them to consecutive addresses, so sectors and lines leave the SM full.
-// Cursors advance once per (batch, partition). Windows of other sub-ranges / passes cost an id compare -- they are never rolled,
-// never extracted. Tiles that cannot be staged (reads > 320 bp) or hold a read with more than 512 windows, and rounds whose records
-// exceed the batch, take the direct path of the kernel above.
-static const int kSortedUnits = 256;             // units (chunks of 24 windows) whose ids one round looks at: even if every window of the
-                                                 // round belongs to the sub-range (single-pass jobs) its keys fit one batch
-static const int kSortedCap = kSortedUnits * kRollC;        // keys per batch = 6144 (12 sort rounds of the 512-thread CTA)
-static const int kSortedRounds = kSortedCap / kRollThreads;
-static_assert(kSortedCap % kRollThreads == 0, "batch = whole sort rounds");
-static const int kKeyItShift = 9, kKeyPartShift = 17;       // key = partition << 17 | read-in-tile << 9 | window (< 512)
-
-template <int NW>
-__global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_sorted_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
-                                                                          const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
-                                                                          uint32_t id_lo, uint32_t row_stride, uint32_t q_lo, int part_bits) {
-    extern __shared__ uint32_t sm_dyn[];
-    unsigned long long *cur = reinterpret_cast<unsigned long long *>(sm_dyn);       // PA: absolute record cursor of (this CTA, partition)
-    uint32_t *runstart = reinterpret_cast<uint32_t *>(cur + p.PA);                  // PA: first sorted position of the partition's run in the batch
-    uint32_t *keyA = runstart + p.PA;                                               // kSortedCap
-    uint32_t *keyB = keyA + kSortedCap;                                             // kSortedCap
-    __shared__ RollTile rt;
-    __shared__ TileStage ts;
-    __shared__ SmemSortScratch<kRollThreads> sc;
-    __shared__ uint32_t wtot[kRollThreads / 32 + 1];
-    uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
-    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) cur[i] = mybase[i];
-    __syncthreads();
-    const int K = p.K;
-    const uint32_t PA = p.PA;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t ntiles = (src.n + kATile - 1) / kATile;
-    const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
-
-    // sorted batch -> global memory. All threads call it with the same n.
-    auto flush = [&](uint32_t n) {
-        const uint32_t *S = smem_sort_field<kRollThreads, kSortedRounds>(keyA, keyB, n, kKeyPartShift, part_bits, sc);
-        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
-            const uint32_t part = S[q] >> kKeyPartShift;
-            if (q == 0 || (S[q - 1] >> kKeyPartShift) != part) runstart[part] = q;
-        }
-        __syncthreads();
-        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
-            const uint32_t key = S[q];
-            const uint32_t part = key >> kKeyPartShift, it = (key >> kKeyItShift) & 255u, j = key & 511u;
-            const Kmer<NW> f = kmer_window<NW>(static_cast<const uint64_t *>(ts.words + ts.off[it]), (int64_t)j, K);
-            const Kmer<NW> r = kmer_rc<NW>(f, K);
-            const Kmer<NW> k = kmer_is_minimal<NW>(f, r) ? f : r;
-            store_rec_stream<NW>(out + (cur[part] + (q - runstart[part])) * NW, k);
-        }
-        __syncthreads();
-        for (uint32_t q = threadIdx.x; q < n; q += kRollThreads) {
-            const uint32_t part = S[q] >> kKeyPartShift;
-            if (q + 1 == n || (S[q + 1] >> kKeyPartShift) != part) cur[part] += (unsigned long long)(q - runstart[part] + 1);
-        }
-        __syncthreads();
-    };
-
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t item0 = t * kATile;
-        const int nitems = (int)min((int64_t)kATile, src.n - item0);
-        uint32_t unif = 0;
-        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
-        const bool staged = tile_stage(src, item0, nitems, ts);
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]);
-        const int too_long = __syncthreads_or((int)threadIdx.x < nitems && (int)rt.len[threadIdx.x] - K + 1 > 512);
-        const bool fast = staged && !too_long;
-        uint32_t npend = 0;                                    // the same value in every thread
-        for (uint32_t u0 = 0; u0 < nunits; u0 += kSortedUnits) {
-            const uint32_t u = u0 + threadIdx.x;
-            const bool have = threadIdx.x < (uint32_t)kSortedUnits && u < nunits;
-            uint64_t idw[kRollC / 4];
-            RollUnit q; q.it = 0; q.j0 = 0; q.cnt = 0;
-            uint32_t mask = 0;                                  // bit s: window j0 + s belongs to this sub-range
-            if (have) {
-#pragma unroll
-                for (int v = 0; v < kRollC / 8; ++v) {
-                    const ulonglong2 x = __ldg(row + (size_t)u * (kRollC / 8) + v);
-                    idw[2 * v] = x.x; idw[2 * v + 1] = x.y;
-                }
-                q = roll_unit(rt, nitems, u, unif, K);
-#pragma unroll
-                for (int s = 0; s < kRollC; ++s) {
-                    const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;      // 0xffff - id_lo stays >= PA
-                    if (s < q.cnt && part < PA) mask |= 1u << s;
-                }
-            }
-            // records of this round and this thread's offset among them (block scan, no atomics)
-            const uint32_t c = (uint32_t)__popc(mask);
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += x;
-            }
-            if (lane == 31) wtot[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t w = lane < kRollThreads / 32 ? wtot[lane] : 0u;
-                uint32_t winc = w;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o);
-                    if (lane >= o) winc += x;
-                }
-                if (lane < kRollThreads / 32) wtot[lane] = winc - w;
-                if (lane == kRollThreads / 32 - 1) wtot[kRollThreads / 32] = winc;
-            }
-            __syncthreads();
-            const uint32_t T = wtot[kRollThreads / 32];
-            uint32_t off = wtot[warp] + inc - c;
-            __syncthreads();                                    // wtot is rewritten by the next round
-            if (fast) {                                          // T <= kSortedUnits * kRollC = kSortedCap
-                if (npend + T > (uint32_t)kSortedCap) { flush(npend); npend = 0; }
-                off += npend;
-                if (mask) {
-#pragma unroll
-                    for (int s = 0; s < kRollC; ++s) {          // static indexing keeps the id words in registers
-                        if (mask & (1u << s)) {
-                            const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;
-                            keyA[off++] = (part << kKeyPartShift) | ((uint32_t)q.it << kKeyItShift) | (uint32_t)(q.j0 + s);
-                        }
-                    }
-                }
-                npend += T;
-            } else if (T) {
-                // direct path (rare): roll through the unit, one shared-memory atomic per record on the cursor
-                if (npend) { flush(npend); npend = 0; }
-                if (mask) {
-                    const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
-                    RollState<NW> st;
-                    roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
-#pragma unroll
-                    for (int s = 0; s < kRollC; ++s) {
-                        if (s < q.cnt) {
-                            if (s > 0) roll_next<NW>(st, seq, K);
-                            if (mask & (1u << s)) {
-                                const uint32_t part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;
-                                const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
-                                const unsigned long long pos = atomicAdd(&cur[part], 1ull);
-                                store_rec_stream<NW>(out + pos * NW, k);
-                            }
-                        }
-                    }
-                }
-                __syncthreads();                                // cursors are read non-atomically by the next flush
-            }
-        }
-        if (npend) flush(npend);                                // keys refer to THIS tile's staged reads
-        __syncthreads();
-    }
-    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur[i];   // chained launches continue here
-}
+// (Round 2 measured a third generation of this kernel -- id sweep, 32-bit keys collected without atomics, ballot-ranked LSD sort
+// of the batch in shared memory, run-by-run flush with consecutive threads storing consecutive records of one partition. Parity
+// clean, full-sector stores, and SLOWER: 251 vs 180 ms at 100 M reads, 42.8 vs 31.1 ms at 20 M: ~310 thread instructions per
+// record at IPC ~1.3 (barriers + dependent ballot / shared-memory chains) against ~170 for roll + atomic + 16-byte store.
+// profiles/r02d_sorted_partition_kernel_AB.log. Removed.)
 
 // ------------------------------------------------------------------------------------------------------------
 // segments
@@ -1294,6 +1139,10 @@ __global__ void __launch_bounds__(kSThreads) local_sort3_k(const Seg *__restrict
     }
 }
 
+// (Round 2 measured a fourth generation -- (21-bit digit | index) keys sorted with three ballot-ranked 7-bit LSD passes, equal
+// records found as neighbours, no shared-memory atomics at all. Parity clean and 1.7x SLOWER than the kernel above: 427 vs 250 ms
+// at 100 M reads, 89 vs 50 ms at 20 M. profiles/r02e_local_sort4_AB.log. Removed together with the sort primitive.)
+
 // compaction: one warp per segment copies its distinct records / counts to the dense output
 template <int NW>
 __global__ void compact_k(const Seg *__restrict__ segs, uint64_t nsegs, const uint32_t *__restrict__ ndist, const uint64_t *__restrict__ dbase,
@@ -1340,7 +1189,6 @@ struct Tuning {
     uint32_t pa_max = 4096;
     uint32_t rmax = 11;
     int a_sub = 0;
-    bool a_sorted = true;        // SGPU_A_SORTED=0: second-generation partition kernel (A/B runs of this round)
     bool trace = false;
 };
 static const Tuning &tuning() {
@@ -1349,7 +1197,6 @@ static const Tuning &tuning() {
         if (const char *e = getenv("SGPU_PA_MAX")) x.pa_max = (uint32_t)std::min(8192, std::max(1, atoi(e)));
         if (const char *e = getenv("SGPU_RMAX")) x.rmax = (uint32_t)std::min(11, std::max(1, atoi(e)));
         if (const char *e = getenv("SGPU_A_SUB")) x.a_sub = std::min(64, std::max(0, atoi(e)));
-        if (const char *e = getenv("SGPU_A_SORTED")) x.a_sorted = atoi(e) != 0;
         x.trace = getenv("SGPU_TRACE") != nullptr;
         return x;
     }();
@@ -1445,17 +1292,18 @@ static void sort_pass(Ctx *ctx, int K, DArr<uint64_t> &X, DArr<uint64_t> &Y, con
     SG_CUDA(cudaMemsetAsync(wcounter.p, 0, 8, st));
     tm.start();
     {
+        auto launch = [&](auto kernel, size_t smem) {
+            SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 1;
+            SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSThreads, smem));
+            if (occ < 1) occ = 1;
+            int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
+            if (grid < 1) grid = 1;
+            kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+        };
         constexpr int bins = 1 << kSortBinBits;
-        auto kernel = local_sort3_k<NW, kSortBinBits, CAP>;
-        const size_t smem = (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * bins * sizeof(uint32_t) +
-                            ((size_t)2 * bins + 2 + kResCap) * sizeof(uint16_t) + 16;
-        SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSThreads, smem));
-        if (occ < 1) occ = 1;
-        int grid = (int)std::min<uint64_t>(nsegs, (uint64_t)ctx->num_sms * occ);
-        if (grid < 1) grid = 1;
-        kernel<<<grid, kSThreads, smem, st>>>(segs.p, nsegs, K, X.p, Y.p, ndist.p, wcounter.p, stats.p);
+        launch(local_sort3_k<NW, kSortBinBits, CAP>, (size_t)(CAP + kResCap) * NW * sizeof(uint64_t) + (size_t)3 * bins * sizeof(uint32_t) +
+                                                         ((size_t)2 * bins + 2 + kResCap) * sizeof(uint16_t) + 16);
         ctx->launches++;
         SG_CUDA(cudaGetLastError());
     }
@@ -1614,20 +1462,7 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
             const size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (job.use_ids && tuning().a_sorted) {
-                // third generation: id sweep -> ballot-sorted key batches -> run flush; one launch per source covers the whole pass
-                int part_bits = 0;
-                while ((1u << part_bits) < PA) ++part_bits;
-                const size_t smem_s = (size_t)PA * (sizeof(unsigned long long) + sizeof(uint32_t)) + (size_t)2 * kSortedCap * sizeof(uint32_t);
-                SG_CUDA(cudaFuncSetAttribute(levelA_scatter_sorted_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-                for (size_t si = 0; si < job.srcs.size(); ++si) {
-                    const Src &src = job.srcs[si];
-                    if (src.n == 0) continue;
-                    levelA_scatter_sorted_k<NW><<<G, kRollThreads, smem_s, st>>>(src, pa, base.p, X, job.tile_off[si].p, job.ids[si].p, p_lo, PA, 0u, part_bits);
-                    ctx->launches++;
-                }
-            } else {
-            // second generation (kept for sources without the id array): roll + one shared-memory atomic per record.
+            {
             // partition sub-ranges (only with the id array, where a foreign window costs just the roll): fewer lines and pages open
             // per CTA. A sub-range costs one more roll over ALL windows of the source: worth it when the pass holds most of the job's
             // records (measured: 20 M reads / 1 pass: 46.5 / 36.7 / 31.5 ms with 1 / 2 / 4 sub-ranges; 100 M reads / 5 passes: 184 ms

@@ -34,10 +34,9 @@ def _compare(a, b, B):
 
 def test_device_arithmetic():
     from gpu_util import ctx
-    from test_hostdev_helpers import check_all, check_roll, check_smem_sort
+    from test_hostdev_helpers import check_all, check_roll
     check_all(ctx().h, 1)
     check_roll(ctx().h, 1)
-    check_smem_sort(ctx().h)
 
 
 @pytest.mark.parametrize("name", G.names("graph"))

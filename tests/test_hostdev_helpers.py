@@ -90,21 +90,6 @@ def check_roll(ctx_h, on_device):
                 assert int(out[u]) == (cnt << 32), (K, L, u, hex(int(out[u])))
 
 
-def check_smem_sort(ctx_h):
-    """ops 12-14 (device only): smem_sort.cuh's ballot-ranked LSD sort against numpy's stable sort on the same bit field"""
-    rng = np.random.default_rng(17)
-    for op, cap in ((12, 512 * 16), (13, 256 * 8), (14, 1024 * 8)):
-        for n in (0, 1, 31, 32, 33, 1000, cap - 1, cap):
-            for lo, nbits in ((0, 5), (17, 9), (17, 13), (3, 11), (0, 1), (20, 12), (0, 0)):
-                items = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
-                if n > 10:
-                    items[: n // 3] = items[0]                       # heavy duplicates
-                got = run_selftest(ctx_h, 1, op, 21, (lo << 8) | nbits, items) if n else np.zeros(0, np.uint64)
-                field = (items >> np.uint64(lo)) & np.uint64((1 << nbits) - 1)
-                want = items[np.argsort(field, kind="stable")]
-                assert np.array_equal(got, want), (op, n, lo, nbits)
-
-
 def test_pair_mailbox_protocol_under_host_threads():
     """op 11: the sector-pairing mailbox protocol (pair_mailbox.cuh; opt-in level-A variant for round 2) hammered by real host
     threads: whatever the interleaving every position is written exactly once with its own record, and pairs do form."""

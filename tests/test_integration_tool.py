@@ -38,6 +38,17 @@ def test_adapter_is_built_where_the_reference_is():
         assert os.path.exists(TOOL), "run __graft_entry__.build()"
 
 
+def test_construction_phase_subclass_compiles_against_the_reference():
+    """integration/construction_gpu_phase.cpp (KMerCountingGpu : Construction::Phase, the pipeline seam) is compiled against the
+    UNMODIFIED reference wherever the reference exists; the object must define the phase's run()"""
+    obj = os.path.join(ROOT, "integration", "_build", "construction_gpu_phase.o")
+    if not os.path.isdir("/root/reference/src") and not os.path.exists(obj):
+        pytest.skip("needs /root/reference to build")
+    assert os.path.exists(obj), "run __graft_entry__.build()"
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    assert "KMerCountingGpu::run" in syms and "GpuKMerDiskCounter::Count" in syms
+
+
 @needs_tool
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", G.names("count"))
@@ -52,6 +63,7 @@ def test_reference_host_code_over_the_c_abi(name):
         fk = np.fromfile(os.path.join(w, "final_kmers"), np.uint8)
     assert np.array_equal(fk, g["final_kmers"])
     assert "reference-built and GPU-built KMerIndex agree" in p.stdout
+    assert "reference KMerDiskCounter over GpuKMerSplitter: identical final_kmers" in p.stdout        # the KMerSplitter-level seam
 
 
 @needs_tool
