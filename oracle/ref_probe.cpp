@@ -210,6 +210,18 @@ int main(int argc, char **argv) {
         ms.write(ext.raw_data(), ext.raw_size());
     }
 
+    // PROBE_EARLY_AT=1: the RNA pipeline's early low-complexity clipper (stages/construction.cpp:317-340: at_ratio 0.8, min 10, max 200)
+    // between the mask fill and everything downstream; masks_at.bin = the array after it, at_removed.txt = the two return values
+    if (getenv("PROBE_EARLY_AT")) {
+        EarlyLowComplexityClipperProcessor at(ext, 0.8, 10, 200);
+        size_t e = at.RemoveATEdges();
+        size_t t = at.RemoveATTips();
+        std::ofstream ms(outdir / "masks_at.bin", std::ios::binary);
+        ms.write(ext.raw_data(), ext.raw_size());
+        std::ofstream rs(outdir / "at_removed.txt");
+        rs << e << "\n" << t << "\n";
+    }
+
     // PROBE_EARLY_TC=<length bound>: the pipeline's early tip clipper (stages/construction.cpp:289-302) between the mask
     // fill and the unitig extraction; masks.bin above is the array before, masks_tc.bin the array after
     if (const char *tc = getenv("PROBE_EARLY_TC")) {

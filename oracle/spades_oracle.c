@@ -633,6 +633,124 @@ int64_t orc_early_tip_clip(const kset_t *km, const mphf_t *mk, uint8_t *masks, i
     return removed;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Early low-complexity (poly A/T) clipper of the RNA pipeline: EarlyLowComplexityClipperProcessor
+ * (assembly_graph/construction/early_simplification.hpp:164-347; phase EarlyATClipper, stages/construction.cpp:317-340,448:
+ * at_ratio 0.8, min_length 10, max_length 200). Works on the mask array in place; k-mers are visited in final_kmers order, each
+ * as seq then !seq (:190-191, :277-278).
+ *   RemoveATEdges (:185-256): collects (junction k-mer, c) edges of length 1 on a read-only pass, then deletes each link once.
+ *   RemoveATTips  (:269-334): from every dead end with a unique incoming edge walk back to the junction; low-complexity tips
+ *                 are isolated on the fly, then the phantom links of their roots are removed (RemoveInconsistentForwardLinks).
+ *   snapshot != 0 : the tip decisions see the masks as they were after RemoveATEdges (what a data-parallel implementation
+ *                   computes); tests assert both modes give the same array.
+ * out4 = { edges collected (RemoveATEdges' return value), links removed, k-mers removed (RemoveATTips' return value), clipped tips }
+ * ---------------------------------------------------------------------------------------------- */
+static int almost_equals_d(double a, double b) {      /* gtest FloatingPoint<double>::AlmostEquals, 4 ULPs (math/xmath.h:283-299) */
+    if (isnan(a) || isnan(b)) return 0;
+    uint64_t x, y; memcpy(&x, &a, 8); memcpy(&y, &b, 8);
+    const uint64_t sign = 0x8000000000000000ull;
+    uint64_t bx = (x & sign) ? (~x + 1) : (sign | x), by = (y & sign) ? (~y + 1) : (sign | y);
+    uint64_t d = bx >= by ? bx - by : by - bx;
+    return d <= 4;
+}
+static int math_ls(double a, double b) { return !almost_equals_d(a, b) && a < b; }    /* math::ls, xmath.h:300-306 */
+static void kmer_shr(uint64_t *w, int K, int c) {          /* kwh >> c: c enters at position 0, the last nucleotide drops (rtseq.hpp:569-588) */
+    int nw = nwords(K);
+    uint64_t carry = (uint64_t)c;
+    for (int j = 0; j < nw; ++j) { uint64_t nc = w[j] >> 62; w[j] = (w[j] << 2) | carry; carry = nc; }
+    int bits = 2 * K - 64 * (nw - 1);
+    if (bits < 64) w[nw - 1] &= (1ULL << bits) - 1;
+}
+void orc_early_at_clip(const kset_t *km, const mphf_t *mk, uint8_t *masks, double ratio, int64_t min_len, int64_t max_len, int snapshot, int64_t *out4) {
+    int K = km->K, nw = km->nw;
+    gctx_t g; g.m = mk; g.K = K; g.masks = masks;
+    /* ---- RemoveATEdges */
+    uint64_t *ek = NULL; uint8_t *ec = NULL; int64_t ne = 0, ce = 0;
+    double thr = (double)K * ratio;
+    for (int64_t i = 0; i < km->n; ++i) {
+        for (int o = 0; o < 2; ++o) {
+            uint64_t kh[MAXW];
+            if (o == 0) memcpy(kh, km->keys + i * nw, 8 * nw); else orc_rc(km->keys + i * nw, K, kh);
+            uint8_t m = g_mask(&g, kh);
+            if (!m_is_junction(m)) continue;
+            size_t counts[4] = {0, 0, 0, 0};
+            for (int p = 0; p < K; ++p) counts[getnuc(kh, p)]++;
+            size_t curm = counts[0];
+            for (int c = 1; c < 4; ++c) if (counts[c] > curm) curm = counts[c];
+            if (math_ls((double)curm, thr)) continue;
+            for (int c = 0; c < 4; ++c) {
+                if (!(m & (1 << c))) continue;
+                uint64_t nx[MAXW]; memcpy(nx, kh, 8 * nw); kmer_shl(nx, K, c);
+                uint8_t mn = g_mask(&g, nx);
+                if (!m_is_junction(mn) && (mn & 15) != 0) continue;       /* next must be a junction or a dead end */
+                if (ne == ce) { ce = ce ? 2 * ce : 64; ek = (uint64_t *)realloc(ek, (size_t)ce * nw * 8); ec = (uint8_t *)realloc(ec, (size_t)ce); }
+                memcpy(ek + ne * nw, kh, 8 * nw); ec[ne] = (uint8_t)c; ++ne;
+            }
+        }
+    }
+    int64_t removed_links = 0;
+    for (int64_t e = 0; e < ne; ++e) {
+        const uint64_t *kh = ek + e * nw; int c = ec[e];
+        if (!(g_mask(&g, kh) & (1 << c))) continue;
+        uint64_t nx[MAXW]; memcpy(nx, kh, 8 * nw); kmer_shl(nx, K, c);
+        int mn; uint64_t idx = canon_idx(mk, kh, K, &mn);
+        masks[idx] &= (uint8_t)~(1u << (mn ? c : 7 - c));                                  /* DeleteOutgoing(kh, c) */
+        int first = getnuc(kh, 0);
+        idx = canon_idx(mk, nx, K, &mn);
+        masks[idx] &= (uint8_t)~(1u << (mn ? 4 + first : 7 - (4 + first)));               /* DeleteIncoming(next, kh[0]) */
+        removed_links += 2;
+    }
+    free(ek); free(ec);
+    /* ---- RemoveATTips */
+    uint8_t *view = masks;
+    if (snapshot) { view = (uint8_t *)malloc((size_t)(km->n ? km->n : 1)); memcpy(view, masks, (size_t)km->n); }
+    g.masks = view;
+    uint64_t *tip = (uint64_t *)malloc((size_t)(max_len + 1) * 8);
+    uint64_t *roots = NULL; int64_t nr = 0, cr = 0;
+    int64_t removed_kmers = 0;
+    for (int64_t i = 0; i < km->n; ++i) {
+        for (int o = 0; o < 2; ++o) {
+            uint64_t kh[MAXW];
+            if (o == 0) memcpy(kh, km->keys + i * nw, 8 * nw); else orc_rc(km->keys + i * nw, K, kh);
+            uint8_t m = g_mask(&g, kh);
+            if ((m & 15) != 0 || m_unique_in(m) < 0) continue;             /* IsDeadEnd && CheckUniqueIncoming */
+            size_t counts[4] = {0, 0, 0, 0};
+            int64_t tsz = 0; int mn;
+            do {
+                tip[tsz++] = canon_idx(mk, kh, K, &mn);
+                counts[getnuc(kh, K - 1)]++;
+                kmer_shr(kh, K, m_unique_in(g_mask(&g, kh)));                /* GetUniqueIncoming (8 -> garbage when not unique: the loop then stops) */
+            } while (tsz < max_len && !m_is_junction(g_mask(&g, kh)));
+            uint8_t mr = g_mask(&g, kh);
+            if ((mr >> 4) == 0 || !m_is_junction(mr)) continue;            /* dead start, or the tip is too long */
+            for (int64_t p = tsz - 1; p < min_len; ++p) counts[getnuc(kh, (int)(K - 1 - p))]++;
+            size_t curm = counts[0];
+            for (int c = 1; c < 4; ++c) if (counts[c] > curm) curm = counts[c];
+            double thr2 = (double)(tsz > min_len ? tsz : min_len) * ratio;
+            if (math_ls((double)curm, thr2)) continue;
+            if (nr == cr) { cr = cr ? 2 * cr : 64; roots = (uint64_t *)realloc(roots, (size_t)cr * nw * 8); }
+            memcpy(roots + nr * nw, kh, 8 * nw); ++nr;
+            removed_kmers += tsz;
+            for (int64_t t = 0; t < tsz; ++t) masks[tip[t]] = 0;            /* IsolateVertex */
+        }
+    }
+    g.masks = masks;
+    int64_t clipped = 0;
+    for (int64_t j = 0; j < nr; ++j) {                                       /* RemoveInconsistentForwardLinks, :21-36 */
+        const uint64_t *kh = roots + j * nw;
+        uint8_t m = g_mask(&g, kh);
+        int mn; uint64_t idx = canon_idx(mk, kh, K, &mn);
+        for (int c = 0; c < 4; ++c) {
+            if (!(m & (1 << c))) continue;
+            uint64_t nx[MAXW]; memcpy(nx, kh, 8 * nw); kmer_shl(nx, K, c);
+            if (!(g_mask(&g, nx) & (1 << (4 + getnuc(kh, 0))))) { masks[idx] &= (uint8_t)~(1u << (mn ? c : 7 - c)); ++clipped; }
+        }
+    }
+    free(tip); free(roots);
+    if (snapshot) free(view);
+    if (out4) { out4[0] = ne; out4[1] = removed_links; out4[2] = removed_kmers; out4[3] = clipped; }
+}
+
 typedef struct { seqvec_t seqs; } unitigs_t;
 
 unitigs_t *orc_unitigs(const kset_t *km, const mphf_t *mk, const uint8_t *masks_in, int keep_loops) {

@@ -19,7 +19,7 @@ SYMBOLS = [
     "sgpu_kset_size", "sgpu_kset_k", "sgpu_kset_num_buckets", "sgpu_kset_record_bytes", "sgpu_kset_bucket_sizes",
     "sgpu_kset_checksum", "sgpu_kset_download_keys", "sgpu_kset_download_counts", "sgpu_kset_write_buckets", "sgpu_kset_write_final", "sgpu_kset_free",
     "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
-    "sgpu_graph_build", "sgpu_graph_build_ex", "sgpu_graph_tip_clipper_stats", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
+    "sgpu_graph_build", "sgpu_graph_build_ex", "sgpu_graph_build_opts", "sgpu_graph_at_clipper_stats", "sgpu_graph_tip_clipper_stats", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
     "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_free_bytes", "sgpu_dist_next_pass", "sgpu_dist_ipc_handle",
     "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_exchange", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
@@ -29,6 +29,11 @@ SYMBOLS = [
 
 class SgpuConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("hbm_budget_bytes", C.c_uint64), ("verbose", C.c_int), ("stream", C.c_uint64)]
+
+
+class SgpuGraphOptions(C.Structure):
+    _fields_ = [("keep_perfect_loops", C.c_int), ("early_tip_length_bound", C.c_uint64), ("early_at_clipper", C.c_int), ("at_ratio", C.c_double),
+                ("at_min_length", C.c_uint64), ("at_max_length", C.c_uint64)]
 
 
 class SgpuTimes(C.Structure):
@@ -91,6 +96,8 @@ def load():
     L.sgpu_mphf_free.restype = None; L.sgpu_mphf_free.argtypes = [vp]
     L.sgpu_graph_build.restype = i32; L.sgpu_graph_build.argtypes = [vp, vp, vp, vp, vp, i32, pp]
     L.sgpu_graph_build_ex.restype = i32; L.sgpu_graph_build_ex.argtypes = [vp, vp, vp, vp, vp, i32, u64, pp]
+    L.sgpu_graph_build_opts.restype = i32; L.sgpu_graph_build_opts.argtypes = [vp, vp, vp, vp, vp, C.POINTER(SgpuGraphOptions), pp]
+    L.sgpu_graph_at_clipper_stats.restype = i32; L.sgpu_graph_at_clipper_stats.argtypes = [vp, vp]
     L.sgpu_graph_tip_clipper_stats.restype = i32; L.sgpu_graph_tip_clipper_stats.argtypes = [vp, vp]
     L.sgpu_graph_masks.restype = i32; L.sgpu_graph_masks.argtypes = [vp, vp, i64]
     L.sgpu_graph_coverage.restype = i32; L.sgpu_graph_coverage.argtypes = [vp, vp, i64]

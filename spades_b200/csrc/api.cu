@@ -299,7 +299,9 @@ int sgpu_graph_build(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *k
     Ctx *c = &ctx->c;
     API_TRY(c, {
         SG_CUDA(cudaSetDevice(c->device));
-        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0);
+        GraphOptions opt;
+        opt.keep_perfect_loops = keep_perfect_loops != 0;
+        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, opt);
         *out = new sgpu_graph{g};
         child_add(c);
     })
@@ -311,11 +313,36 @@ int sgpu_graph_build_ex(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset
     Ctx *c = &ctx->c;
     API_TRY(c, {
         SG_CUDA(cudaSetDevice(c->device));
-        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, keep_perfect_loops != 0,
-                               early_tip_length_bound);
+        GraphOptions opt;
+        opt.keep_perfect_loops = keep_perfect_loops != 0;
+        opt.early_tip_length_bound = early_tip_length_bound;
+        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, opt);
         *out = new sgpu_graph{g};
         child_add(c);
     })
+}
+int sgpu_graph_build_opts(sgpu_ctx *ctx, const sgpu_kset *kpomers, const sgpu_kset *kmers, const sgpu_mphf *kmer_index, const sgpu_mphf *kpomer_index,
+                          const sgpu_graph_options *o, sgpu_graph **out) {
+    if (!ctx || !kpomers || !kmers || !kmer_index || !o || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CHECK(!o->early_at_clipper || (o->at_ratio > 0.0 && o->at_ratio <= 1.0 && o->at_max_length >= 1), SGPU_EINVAL, "bad A/T clipper parameters");
+        SG_CUDA(cudaSetDevice(c->device));
+        GraphOptions opt;
+        opt.keep_perfect_loops = o->keep_perfect_loops != 0;
+        opt.early_tip_length_bound = o->early_tip_length_bound;
+        opt.early_at = o->early_at_clipper != 0;
+        opt.at_ratio = o->at_ratio; opt.at_min_len = o->at_min_length; opt.at_max_len = o->at_max_length;
+        Graph *g = graph_build(c, kpomers->s, kmers->s, kmer_index->m, kpomer_index ? kpomer_index->m : nullptr, opt);
+        *out = new sgpu_graph{g};
+        child_add(c);
+    })
+}
+int sgpu_graph_at_clipper_stats(const sgpu_graph *g, uint64_t *out4) {
+    if (!g || !out4) return SGPU_EINVAL;
+    for (int i = 0; i < 4; ++i) out4[i] = g->g->at_stats[i];
+    return SGPU_OK;
 }
 int sgpu_graph_tip_clipper_stats(const sgpu_graph *g, uint64_t *out3) {
     if (!g || !out3) return SGPU_EINVAL;

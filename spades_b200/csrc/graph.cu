@@ -315,7 +315,7 @@ __global__ void tc_apply_k(uint8_t *__restrict__ masks, const uint8_t *__restric
 }
 template <int NW>
 __global__ void tc_links_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__restrict__ masks, const uint32_t *__restrict__ tipped,
-                           unsigned long long *__restrict__ stats) {
+                           unsigned long long *__restrict__ stat_clipped) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= 2 * n || !tipped[tid]) return;
     const Kmer<NW> key = table_key<NW>(t, tid >> 1);
@@ -331,9 +331,131 @@ __global__ void tc_links_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__
         if (!(oriented_mask<NW>(mk, masks, nx, K) & (1u << (4 + first)))) {            // !CheckIncoming(next_kh, kh[0])
             const unsigned bit = 1u << (ci.is_min ? c : 7 - c);                          // DeleteOutgoing(kh, c), inout_mask.hpp:108-114
             atomicAnd(reinterpret_cast<unsigned *>(masks) + (ci.idx >> 2), ~(bit << (8 * (ci.idx & 3))));
-            atomicAdd(&stats[2], 1ull);
+            atomicAdd(stat_clipped, 1ull);
         }
     }
+}
+
+// ---- early low-complexity (poly A/T) clipper ----------------------------------------------------------------------------------
+// EarlyLowComplexityClipperProcessor (assembly_graph/construction/early_simplification.hpp:164-347), the EarlyATClipper phase of the
+// RNA pipeline (stages/construction.cpp:317-340,447-448: at_ratio 0.8, min_length 10, max_length 200); runs before the tip clipper.
+//   RemoveATEdges (:185-256)  at_edges_probe_k : per (k-mer, orientation) on the untouched masks: junction + low-complexity k-mer ->
+//                                                 the outgoing edges of length 1 (next is a junction or a dead end) are flagged
+//                             at_edges_apply_k : every flagged link is deleted once (the reference deletes it through whichever of
+//                                                 its two representations comes first and skips the other, :237-238: here the
+//                                                 representation with the smaller (thread, nucleotide) pair acts)
+//   RemoveATTips  (:269-334)  at_tips_probe_k  : per dead end with a unique incoming edge: walk back to the junction (<= max_length),
+//                                                 complexity of the tip (+ the root's last nucleotides up to min_length), mark
+//                                                 the vertices and the root. The reference isolates tips while other threads
+//                                                 walk; the result does not depend on the order (tips are disjoint chains whose
+//                                                 decisions read only their own vertices and the root's mask -- checked: unmodified
+//                                                 reference with 1 and 8 threads == oracle sequential == oracle snapshot)
+//                             tc_apply_k, tc_links_k : IsolateVertex, RemoveInconsistentForwardLinks on the updated masks
+__device__ __forceinline__ bool almost_equals_f64(double a, double b) {     // gtest FloatingPoint<double>::AlmostEquals, 4 ULPs (math/xmath.h:283-299)
+    if (a != a || b != b) return false;
+    const unsigned long long x = (unsigned long long)__double_as_longlong(a), y = (unsigned long long)__double_as_longlong(b);
+    const unsigned long long sign = 0x8000000000000000ull;
+    const unsigned long long bx = (x & sign) ? (~x + 1ull) : (sign | x), by = (y & sign) ? (~y + 1ull) : (sign | y);
+    return (bx >= by ? bx - by : by - bx) <= 4ull;
+}
+__device__ __forceinline__ bool math_ls(double a, double b) { return !almost_equals_f64(a, b) && a < b; }      // math::ls, xmath.h:300-306
+__device__ __forceinline__ bool mask_is_junction(uint8_t m) { return uniq4(m & 15) < 0 || uniq4(m >> 4) < 0; }  // InOutMask::IsJunction
+
+struct AtParams { double ratio; uint32_t min_len, max_len; };
+
+template <int NW>
+__global__ void at_edges_probe_k(KeyTable t, int64_t n, int K, MphfDev mk, const uint8_t *__restrict__ masks, AtParams ap,
+                                 uint8_t *__restrict__ eflag /*[2n]*/, unsigned long long *__restrict__ stats) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * n) return;
+    eflag[tid] = 0;
+    const Kmer<NW> key = table_key<NW>(t, tid >> 1);
+    const int o = (int)(tid & 1);
+    const uint8_t mfw = masks[mphf_lookup_dev<NW>(mk, key)];
+    const uint8_t m = o ? inv_byte(mfw) : mfw;
+    if (!mask_is_junction(m)) return;
+    const Kmer<NW> kh = o ? kmer_rc<NW>(key, K) : key;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    for (int p = 0; p < K; ++p) cnt[kmer_nuc<NW>(kh, p)]++;
+    const uint32_t curm = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
+    if (math_ls((double)curm, (double)K * ap.ratio)) return;
+    uint8_t f = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!(m & (1u << c))) continue;
+        Kmer<NW> nx = kh;
+        kmer_shl<NW>(nx, K, c);
+        const uint8_t mn = oriented_mask<NW>(mk, masks, nx, K);
+        if (!mask_is_junction(mn) && (mn & 15) != 0) continue;          // an edge of length 1: next is a junction or a dead end
+        f |= (uint8_t)(1u << c);
+    }
+    eflag[tid] = f;
+    if (f) atomicAdd(&stats[0], (unsigned long long)__popc(f));
+}
+__device__ __forceinline__ void mask_clear_bit(uint8_t *masks, uint64_t idx, unsigned bit) {
+    atomicAnd(reinterpret_cast<unsigned *>(masks) + (idx >> 2), ~((1u << bit) << (8 * (idx & 3))));
+}
+template <int NW>
+__global__ void at_edges_apply_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__restrict__ masks, const uint8_t *__restrict__ eflag,
+                                 unsigned long long *__restrict__ stats) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * n || !eflag[tid]) return;
+    const Kmer<NW> key = table_key<NW>(t, tid >> 1);
+    const Kmer<NW> kh = (tid & 1) ? kmer_rc<NW>(key, K) : key;
+    const CanonIdx<NW> ci = canon_lookup<NW>(mk, kh, K);
+    const int first = (int)(kh.w[0] & 3);                                // kh[0]
+    for (int c = 0; c < 4; ++c) {
+        if (!(eflag[tid] & (1u << c))) continue;
+        Kmer<NW> nx = kh;
+        kmer_shl<NW>(nx, K, c);
+        const CanonIdx<NW> cn = canon_lookup<NW>(mk, nx, K);
+        // the same link seen from the other strand: (rc(next), complement of kh[0]); rc(next) is the table key iff next is NOT minimal
+        const int64_t tid2 = (int64_t)(2 * cn.idx) + (cn.is_min ? 1 : 0);
+        const int c2 = 3 - first;
+        if ((eflag[tid2] & (1u << c2)) && (tid2 < tid || (tid2 == tid && c2 < c))) continue;
+        mask_clear_bit(masks, ci.idx, (unsigned)(ci.is_min ? c : 7 - c));                        // DeleteOutgoing(kh, c)
+        mask_clear_bit(masks, cn.idx, (unsigned)(cn.is_min ? 4 + first : 7 - (4 + first)));      // DeleteIncoming(next, kh[0])
+        atomicAdd(&stats[1], 2ull);
+    }
+}
+template <int NW>
+__global__ void at_tips_probe_k(KeyTable t, int64_t n, int K, MphfDev mk, const uint8_t *__restrict__ masks, AtParams ap, uint8_t *__restrict__ mark,
+                                uint32_t *__restrict__ rooted /*[2n]*/, unsigned long long *__restrict__ stats) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * n) return;
+    const Kmer<NW> key = table_key<NW>(t, tid >> 1);
+    const int o = (int)(tid & 1);
+    const uint64_t idx0 = mphf_lookup_dev<NW>(mk, key);
+    const uint8_t mfw = masks[idx0];
+    const uint8_t m0 = o ? inv_byte(mfw) : mfw;
+    if ((m0 & 15) != 0 || uniq4(m0 >> 4) < 0) return;                   // IsDeadEnd && CheckUniqueIncoming
+    const Kmer<NW> start = o ? kmer_rc<NW>(key, K) : key;
+    Kmer<NW> kh = start;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    uint32_t tsz = 0;
+    uint8_t m = m0;
+    do {                                                                 // walk back to the junction, :292-296
+        ++tsz;
+        cnt[kmer_nuc<NW>(kh, K - 1)]++;
+        kmer_shr<NW>(kh, K, uniq4(m >> 4));
+        m = oriented_mask<NW>(mk, masks, kh, K);
+    } while (tsz < ap.max_len && !mask_is_junction(m));
+    if ((m >> 4) == 0 || !mask_is_junction(m)) return;                   // dead start (isolated short edge) or too long, :301-302
+    for (uint32_t p = tsz - 1; p < ap.min_len; ++p) cnt[kmer_nuc<NW>(kh, K - 1 - (int)p)]++;
+    const uint32_t curm = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
+    if (math_ls((double)curm, (double)max(tsz, ap.min_len) * ap.ratio)) return;
+    // a low-complexity tip: mark its vertices (second walk) and its root
+    const CanonIdx<NW> cr = canon_lookup<NW>(mk, kh, K);
+    rooted[2 * cr.idx + (cr.is_min ? 0 : 1)] = 1;
+    Kmer<NW> w = start;
+    uint8_t mw = m0;
+    for (uint32_t s2 = 0; s2 < tsz; ++s2) {
+        uint64_t idx;
+        if (s2) mw = oriented_mask<NW>(mk, masks, w, K, &idx); else idx = idx0;
+        mark[idx] = 1;
+        kmer_shr<NW>(w, K, uniq4(mw >> 4));
+    }
+    atomicAdd(&stats[2], (unsigned long long)tsz);
 }
 
 // ---- perfect loops (CollectLoops :359-397). Rare; one thread per candidate / per loop is enough. ---------------------
@@ -501,7 +623,8 @@ __global__ void loop_write_k(const LoopInfo *__restrict__ info, int64_t nl, int 
 
 // ---- host orchestration ----------------------------------------------------------------------------------------------
 template <int NW, int NWS>
-static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops, uint64_t early_tc_bound) {
+static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
+    const bool keep_loops = opt.keep_perfect_loops;
     cudaStream_t st = ctx->stream;
     const KSet *kp = g->kp, *km = g->km;
     const int K = km->K;
@@ -531,6 +654,31 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops, uint64_t early_t
     }
     SG_CUDA(cudaStreamSynchronize(st));
     g->tc_stats[0] = g->tc_stats[1] = g->tc_stats[2] = 0;
+    for (int i = 0; i < 4; ++i) g->at_stats[i] = 0;
+    if (opt.early_at && nk) {
+        SG_CHECK(opt.at_min_len <= (uint64_t)K, 2, "early A/T clipper: min_length must not exceed k (the reference indexes kh[k - 1 - i])");
+        KeyTable tt = make_table(km);
+        AtParams ap; ap.ratio = opt.at_ratio; ap.min_len = (uint32_t)std::min<uint64_t>(opt.at_min_len, 0x7fffffffu); ap.max_len = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(opt.at_max_len, 1), 0x7fffffffu);
+        DArr<uint8_t> eflag(ctx, 2 * nk + 8), mark(ctx, nk + 8);
+        DArr<uint32_t> rooted(ctx, 2 * nk + 1);
+        DArr<unsigned long long> stats(ctx, 4);
+        SG_CUDA(cudaMemsetAsync(mark.p, 0, mark.bytes(), st));
+        SG_CUDA(cudaMemsetAsync(rooted.p, 0, rooted.bytes(), st));
+        SG_CUDA(cudaMemsetAsync(stats.p, 0, 32, st));
+        const int grid2 = div_up((int64_t)(2 * nk), 128);
+        at_edges_probe_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, ap, eflag.p, stats.p);
+        at_edges_apply_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, eflag.p, stats.p);
+        at_tips_probe_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, ap, mark.p, rooted.p, stats.p);
+        tc_apply_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(g->masks.p, mark.p, nk);
+        tc_links_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, rooted.p, stats.p + 3);
+        ctx->launches += 5;
+        SG_CUDA(cudaGetLastError());
+        unsigned long long hs[4];
+        SG_CUDA(cudaMemcpyAsync(hs, stats.p, 32, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 4; ++i) g->at_stats[i] = hs[i];
+    }
+    const uint64_t early_tc_bound = opt.early_tip_length_bound;
     if (early_tc_bound && nk) {
         KeyTable tt = make_table(km);
         DArr<uint8_t> mark(ctx, nk + 8);
@@ -541,7 +689,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, bool keep_loops, uint64_t early_t
         const uint32_t bound = (uint32_t)std::min<uint64_t>(early_tc_bound, 0x7fffffffu);
         tc_probe_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, bound, mark.p, tipped.p, stats.p);
         tc_apply_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(g->masks.p, mark.p, nk);
-        tc_links_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, tipped.p, stats.p);
+        tc_links_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, tipped.p, stats.p + 2);
         ctx->launches += 3;
         SG_CUDA(cudaGetLastError());
         unsigned long long hs[4];
@@ -694,7 +842,7 @@ void launch_nonzero_flags(Ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t 
     ctx->launches++;
 }
 
-Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops, uint64_t early_tc_bound) {
+Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, const GraphOptions &opt) {
     SG_CHECK(kp->K == km->K + 1, 2, "graph: (k+1)-mer / k-mer sets do not match");
     SG_CHECK(mk->n == km->n && mk->B == km->B, 2, "graph: k-mer index does not belong to the k-mer set");
     SG_CHECK(km->K % 2 == 1, 2, "graph: k must be odd (gbuilder.cpp:125)");
@@ -702,13 +850,13 @@ Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, con
     g->ctx = ctx; g->k = km->K; g->kp = kp; g->km = km; g->mk = mk; g->mkp = mkp;
     try {
         const int nw = km->nw, nws = kp->nw;
-        if (nw == 1 && nws == 1) graph_build_nw<1, 1>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 1 && nws == 2) graph_build_nw<1, 2>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 2 && nws == 2) graph_build_nw<2, 2>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 2 && nws == 3) graph_build_nw<2, 3>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 3 && nws == 3) graph_build_nw<3, 3>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 3 && nws == 4) graph_build_nw<3, 4>(ctx, g, keep_loops, early_tc_bound);
-        else if (nw == 4 && nws == 4) graph_build_nw<4, 4>(ctx, g, keep_loops, early_tc_bound);
+        if (nw == 1 && nws == 1) graph_build_nw<1, 1>(ctx, g, opt);
+        else if (nw == 1 && nws == 2) graph_build_nw<1, 2>(ctx, g, opt);
+        else if (nw == 2 && nws == 2) graph_build_nw<2, 2>(ctx, g, opt);
+        else if (nw == 2 && nws == 3) graph_build_nw<2, 3>(ctx, g, opt);
+        else if (nw == 3 && nws == 3) graph_build_nw<3, 3>(ctx, g, opt);
+        else if (nw == 3 && nws == 4) graph_build_nw<3, 4>(ctx, g, opt);
+        else if (nw == 4 && nws == 4) graph_build_nw<4, 4>(ctx, g, opt);
         else throw Error(2, "graph: unsupported word combination");
     } catch (...) { delete g; throw; }
     return g;

@@ -22,9 +22,18 @@ struct Graph {
     std::vector<uint64_t> link_start, link_end;   // LinkRecord::hash_and_mask_ (debruijn_graph_constructor.hpp:422-452)
     std::vector<uint32_t> raw_cov;                // CoverageIndex raw coverage per edge
     uint64_t tc_stats[3] = {0, 0, 0};             // early tip clipper: removed k-mers, tipped junctions, clipped links
+    uint64_t at_stats[4] = {0, 0, 0, 0};          // early A/T clipper: edges collected, links removed, k-mers removed, clipped tips
 };
 
-Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, bool keep_loops, uint64_t early_tc_bound = 0);
+struct GraphOptions {
+    bool keep_perfect_loops = true;
+    uint64_t early_tip_length_bound = 0;          // 0 = no early tip clipper
+    bool early_at = false;                        // early low-complexity (poly A/T) clipper of the RNA pipeline, before the tip clipper
+    double at_ratio = 0.8;
+    uint64_t at_min_len = 10, at_max_len = 200;
+};
+
+Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, const GraphOptions &opt);
 std::vector<uint64_t> graph_histogram(Ctx *ctx, const Graph *g);
 
 // host_graph.cpp : FastGraphFromSequencesConstructor::ConstructGraph + GFAWriter

@@ -33,6 +33,12 @@ class DeBruijnGraph:
         self.ctx.check(self.ctx.L.sgpu_graph_tip_clipper_stats(self.h, _p(out)))
         return tuple(int(x) for x in out)
 
+    def at_clipper_stats(self):
+        """(edges collected, links removed, k-mers removed, clipped tips) of the early A/T clipper; zeros when it was off."""
+        out = np.zeros(4, np.uint64)
+        self.ctx.check(self.ctx.L.sgpu_graph_at_clipper_stats(self.h, _p(out)))
+        return [int(x) for x in out]
+
     def coverage(self):
         n = self.kpomers.total_kmers()
         out = np.zeros(max(n, 1), np.uint32)
@@ -88,15 +94,20 @@ class DeBruijnGraphConstructor:
             raise ValueError("k-mer size must be odd")   # projects/spades_tools/gbuilder.cpp:125
         self.ctx, self.k, self.B = ctx, k, num_buckets
 
-    def ConstructGraph(self, keep_perfect_loops=True, with_coverage=True, early_tip_clipper_length=0) -> DeBruijnGraph:
+    def ConstructGraph(self, keep_perfect_loops=True, with_coverage=True, early_tip_clipper_length=0, early_at_clipper=False,
+                       at_ratio=0.8, at_min_length=10, at_max_length=200) -> DeBruijnGraph:
         """early_tip_clipper_length > 0: run the Construction stage's EarlyTipClipper (stages/construction.cpp:289-302) with that
-        length bound (the pipeline uses read length - k) before the unitigs are extracted; 0 = spades-gbuilder's behaviour."""
+        length bound (the pipeline uses read length - k) before the unitigs are extracted; 0 = spades-gbuilder's behaviour.
+        early_at_clipper: the RNA pipeline's EarlyATClipper (stages/construction.cpp:317-340) before it."""
         ctx, k, B = self.ctx, self.k, self.B
         kpomers = KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(k + 1)).Count(B)
         kmers = KMerDiskCounter(ctx, DeBruijnKMerKMerSplitter(k, kpomers)).Count(B)
         kmer_index = KMerIndexBuilder(ctx).BuildIndex(kmers)
         kpomer_index = KMerIndexBuilder(ctx).BuildIndex(kpomers) if with_coverage else None
         h = C.c_void_p()
-        ctx.check(ctx.L.sgpu_graph_build_ex(ctx.h, kpomers.h, kmers.h, kmer_index.h, kpomer_index.h if kpomer_index else None,
-                                            1 if keep_perfect_loops else 0, int(early_tip_clipper_length), C.byref(h)))
+        from ._lib import SgpuGraphOptions
+        opts = SgpuGraphOptions(1 if keep_perfect_loops else 0, int(early_tip_clipper_length), 1 if early_at_clipper else 0, float(at_ratio),
+                                int(at_min_length), int(at_max_length))
+        ctx.check(ctx.L.sgpu_graph_build_opts(ctx.h, kpomers.h, kmers.h, kmer_index.h, kpomer_index.h if kpomer_index else None,
+                                              C.byref(opts), C.byref(h)))
         return DeBruijnGraph(ctx, h, kpomers, kmers, kmer_index, kpomer_index)

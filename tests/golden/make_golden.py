@@ -56,12 +56,30 @@ GTEST_CASES = {
 }
 
 
-def run_probe(mode, reads, k, B, T=2, early_tc=0):
+def at_reads(n, L, glen, err, seed):
+    """RNA-like reads: poly-A tails, poly-T heads, A-rich noisy tails and pure low-complexity reads on top of the SURVEY 8(d) generator"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in synthetic_reads(n, L, glen, err, seed=seed):
+        x = rng.random()
+        if x < 0.15:
+            cut = int(rng.integers(L // 3, L - 5)); r = r[:cut] + "A" * (L - cut)
+        elif x < 0.25:
+            cut = int(rng.integers(5, L // 2)); r = "T" * cut + r[cut:]
+        elif x < 0.30:
+            cut = int(rng.integers(L // 3, L - 5)); r = r[:cut] + "".join(rng.choice(list("AAAAAAAT"), L - cut))
+        out.append(r)
+    return out + ["A" * L] * 5 + ["AT" * (L // 2)] * 3
+
+
+def run_probe(mode, reads, k, B, T=2, early_tc=0, early_at=False):
     with tempfile.TemporaryDirectory() as d:
         rf = os.path.join(d, "reads.txt")
         open(rf, "w").write("\n".join(reads) + "\n")
         out = os.path.join(d, "out")
         env = dict(os.environ)
+        if early_at:
+            env["PROBE_EARLY_AT"] = "1"                # EarlyLowComplexityClipperProcessor (RNA pipeline), before the tip clipper
         if early_tc:
             env["PROBE_EARLY_TC"] = str(early_tc)      # EarlyTipClipperProcessor between mask fill and unitig extraction
         subprocess.check_call([PROBE, mode, rf, str(k), str(B), str(T), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
@@ -75,8 +93,10 @@ def run_probe(mode, reads, k, B, T=2, early_tc=0):
 
 def save(name, mode, reads, k, B, early_tc=0):
     """mode "tcgraph" = graph mode with the pipeline's early tip clipper (length bound early_tc); masks_bin is the array
-    before the clipper, masks_tc_bin after it, everything downstream (unitigs, GFA) comes from the clipped index."""
-    res = run_probe("graph" if mode == "tcgraph" else mode, reads, k, B, early_tc=early_tc)
+    before the clipper, masks_tc_bin after it, everything downstream (unitigs, GFA) comes from the clipped index.
+    mode "atgraph" = graph mode with the RNA pipeline's early A/T clipper (masks_at_bin, at_removed_txt), followed by the tip clipper
+    when early_tc is given (then masks_tc_bin is the array after both)."""
+    res = run_probe("graph" if mode in ("tcgraph", "atgraph") else mode, reads, k, B, early_tc=early_tc, early_at=(mode == "atgraph"))
     if early_tc:
         res["tc_bound"] = np.array([early_tc])
     res["reads"] = np.frombuffer("\n".join(reads).encode(), dtype=np.uint8)
@@ -139,6 +159,11 @@ if __name__ == "__main__":
     save("syn_k21_B10_tcgraph", "tcgraph", synthetic_reads(2000, 100, 3000, 0.02, seed=6), 21, 10, early_tc=79)
     save("loops_k21_B10_tcgraph", "tcgraph", loops_reads() + synthetic_reads(300, 120, 700, 0.02, seed=3), 21, 10, early_tc=99)
     save("dense_k7_B4_tcgraph", "tcgraph", synthetic_reads(800, 60, 400, 0.03, seed=14), 7, 4, early_tc=10)
+    # RNA pipeline: EarlyATClipper (stages/construction.cpp:317-340), alone and followed by the tip clipper (:447-450)
+    save("rna_k21_B8_atgraph", "atgraph", at_reads(3000, 100, 3000, 0.01, 1), 21, 8)
+    save("rna_k33_B5_atgraph", "atgraph", at_reads(2000, 150, 3000, 0.02, 2), 33, 5, early_tc=150 - 33)
+    save("rna_k55_B16_atgraph", "atgraph", at_reads(2000, 150, 4000, 0.01, 3), 55, 16, early_tc=150 - 55)
+    save("rna_k11_B3_atgraph", "atgraph", at_reads(1500, 60, 800, 0.05, 4), 11, 3)
     for nm, (rd, _) in GTEST_CASES.items():
         save("gtest_" + nm + "_k5", "graph", rd, 5, 2)
     # construction_test.cpp:97-105 (SimpleTestEarlyPairedInfo, k=3): its coverage table is the known answer in tests/test_oracle_golden.py

@@ -84,8 +84,11 @@ def check_graph(g, art):
         chk("kmer_index", index_equal(strip_uleb_k(g["kmer_index_bin"].tobytes(), k), art["kmer_index"], B))
     if "kpomer_index" in art:
         chk("kpomer_index", index_equal(strip_uleb_k(g["kpomer_index_bin"].tobytes(), k + 1), art["kpomer_index"], B))
-    if "masks" in art:     # tip-clipper fixtures: `masks` is the array after the clipper (masks_tc.bin)
-        chk("masks", np.array_equal(g["masks_tc_bin"] if "masks_tc_bin" in g else g["masks_bin"], np.asarray(art["masks"], np.uint8)))
+    if "masks" in art:     # clipper fixtures: `masks` is the array after the last clipper that ran (masks_tc.bin, else masks_at.bin)
+        want = g["masks_tc_bin"] if "masks_tc_bin" in g else (g["masks_at_bin"] if "masks_at_bin" in g else g["masks_bin"])
+        chk("masks", np.array_equal(want, np.asarray(art["masks"], np.uint8)))
+    if "at_removed" in art:    # (RemoveATEdges' return value, RemoveATTips' return value)
+        chk("at_removed", [int(x) for x in g["at_removed_txt"].tobytes().decode().split()] == [int(x) for x in art["at_removed"]])
     if "masks_raw" in art and "masks_tc_bin" in g:
         chk("masks_raw", np.array_equal(g["masks_bin"], np.asarray(art["masks_raw"], np.uint8)))
     if "tc_removed" in art:

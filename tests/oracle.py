@@ -145,6 +145,19 @@ def early_tip_clip(km: KSet, mk: Mphf, masks_arr, length_bound, snapshot=False):
     return m, int(removed), int(nt.value), int(nc.value)
 
 
+def early_at_clip(km: KSet, mk: Mphf, masks_arr, ratio=0.8, min_len=10, max_len=200, snapshot=False):
+    """EarlyLowComplexityClipperProcessor::RemoveATEdges + RemoveATTips on a copy of the mask array
+    -> (masks, [edges collected, links removed, k-mers removed, clipped tips])"""
+    m = np.array(masks_arr, np.uint8, copy=True)
+    out = np.zeros(4, np.int64)
+    if m.size:
+        L = lib()
+        L.orc_early_at_clip.restype = None
+        L.orc_early_at_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.orc_early_at_clip(km.h, mk.h, _p(m), float(ratio), int(min_len), int(max_len), 1 if snapshot else 0, _p(out))
+    return m, [int(x) for x in out]
+
+
 class Unitigs:
     def __init__(self, km: KSet, mk: Mphf, masks_arr, keep_loops=True):
         m = np.ascontiguousarray(masks_arr, np.uint8)
@@ -173,7 +186,7 @@ def gfa(u: Unitigs, mk: Mphf, mkp: Mphf = None, cov=None, version="SPAdes-4.3.0-
     return s
 
 
-def full_graph(reads, k, B, early_tc=0):
+def full_graph(reads, k, B, early_tc=0, early_at=False):
     """Whole path on a list of ACGT strings; returns dict of artefacts named like ref_probe's files.
     early_tc > 0: run the early tip clipper with that length bound between the mask fill and the unitig extraction
     (stages/construction.cpp:289-302); `masks` then holds the clipped array and `masks_raw` the one before."""
@@ -188,10 +201,13 @@ def full_graph(reads, k, B, early_tc=0):
     mk_arr = masks(kp, mk, km.n)
     raw = mk_arr
     tc = None
+    at = None
+    if early_at:                  # the RNA pipeline's EarlyATClipper runs before the tip clipper (stages/construction.cpp:447-450)
+        mk_arr, at = early_at_clip(km, mk, mk_arr)
     if early_tc:
         mk_arr, removed, tipped, clipped = early_tip_clip(km, mk, mk_arr, early_tc)
         tc = dict(removed=removed, tipped=tipped, clipped=clipped)
     cov = coverage(kp, mkp)
     u = Unitigs(km, mk, mk_arr, True)
-    return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, masks_raw=raw, tc=tc, cov=cov, hist=histogram(cov), unitigs=u,
+    return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, masks_raw=raw, tc=tc, at=at, cov=cov, hist=histogram(cov), unitigs=u,
                 gfa=gfa(u, mk, mkp, cov))

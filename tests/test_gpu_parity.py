@@ -57,6 +57,31 @@ def test_early_tip_clipper_matches_reference_golden(name):
     assert G.check_graph(g, art) == []
 
 
+@pytest.mark.parametrize("name", G.names("atgraph"))
+def test_early_at_clipper_matches_reference_golden(name):
+    """sgpu_graph_build_opts with the RNA pipeline's early A/T clipper (and the tip clipper after it where the fixture has one)
+    against the unmodified reference's EarlyLowComplexityClipperProcessor: clipped masks, both return values, unitigs, GFA"""
+    from gpu_util import gpu_graph_artifacts
+    g = G.load(name)
+    art, gr = gpu_graph_artifacts(g["reads"], g["k"], g["B"], early_tc=g.get("tc_bound", 0), early_at=True)
+    assert G.check_graph(g, art) == []
+
+
+@pytest.mark.parametrize("k,B,n,L,glen,seed", [(21, 8, 2500, 100, 2500, 61), (55, 12, 2500, 150, 4000, 62), (77, 3, 1500, 150, 2500, 63), (13, 2, 1500, 60, 700, 64)])
+def test_early_at_clipper_matches_oracle_random(k, B, n, L, glen, seed):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import at_reads
+    from gpu_util import gpu_graph_artifacts
+    reads = at_reads(n, L, glen, 0.01, seed)
+    art, gr = gpu_graph_artifacts(reads, k, B, early_tc=L - k, early_at=True)
+    r = O.full_graph(reads, k, B, early_tc=L - k, early_at=True)
+    assert r["at"][0] > 0 and r["at"][2] > 0
+    assert gr.at_clipper_stats() == r["at"]
+    assert gr.tip_clipper_stats() == (r["tc"]["removed"], r["tc"]["tipped"], r["tc"]["clipped"])
+    assert np.array_equal(art["masks"], r["masks"]) and art["unitigs"] == r["unitigs"].seqs and art["gfa"] == r["gfa"]
+
+
 @pytest.mark.parametrize("k,B,n,L,glen,err,seed", [(21, 16, 3000, 100, 4000, 0.02, 51), (55, 20, 3000, 150, 4000, 0.02, 52), (77, 3, 1500, 150, 2000, 0.01, 53),
                                                    (9, 3, 1000, 60, 600, 0.1, 54), (33, 2, 2000, 120, 900, 0.03, 55)])
 def test_early_tip_clipper_matches_oracle_random(k, B, n, L, glen, err, seed):

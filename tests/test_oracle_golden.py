@@ -12,14 +12,32 @@ import oracle as O
 from spades_b200.packing import pack_reads, revcomp, unpack_kmers
 
 
-def oracle_artifacts(reads, k, B, early_tc=0):
-    r = O.full_graph(reads, k, B, early_tc=early_tc)
+def oracle_artifacts(reads, k, B, early_tc=0, early_at=False):
+    r = O.full_graph(reads, k, B, early_tc=early_tc, early_at=early_at)
     art = dict(kpomers=r["kp"].keys, kp_bsz=r["kp"].bsz, kmers=r["km"].keys, kmer_index=r["mk"].serialize(),
                kpomer_index=r["mkp"].serialize(), masks=r["masks"], cov=r["cov"], hist=r["hist"],
                unitigs=r["unitigs"].seqs, gfa=r["gfa"])
     if early_tc:
-        art.update(masks_raw=r["masks_raw"], tc_removed=r["tc"]["removed"])
+        art.update(tc_removed=r["tc"]["removed"])
+        if not early_at:
+            art.update(masks_raw=r["masks_raw"])
+    if early_at:
+        art.update(at_removed=[r["at"][0], r["at"][2]])
     return art, r
+
+
+@pytest.mark.parametrize("name", G.names("atgraph"))
+def test_oracle_early_at_clipper_matches_reference_golden(name):
+    """EarlyLowComplexityClipperProcessor (early_simplification.hpp:164-347; the RNA pipeline's EarlyATClipper), alone and followed by
+    the tip clipper: clipped masks, both return values, unitigs and GFA against the unmodified reference; and the order independence
+    the CUDA version relies on (tip decisions on a snapshot of the masks give the same array as the sequential walk)."""
+    g = G.load(name)
+    art, r = oracle_artifacts(g["reads"], g["k"], g["B"], early_tc=g.get("tc_bound", 0), early_at=True)
+    assert G.check_graph(g, art) == []
+    assert r["at"][0] > 0 and r["at"][2] > 0
+    snap_m, snap_s = O.early_at_clip(r["km"], r["mk"], r["masks_raw"], snapshot=True)
+    seq_m, seq_s = O.early_at_clip(r["km"], r["mk"], r["masks_raw"], snapshot=False)
+    assert np.array_equal(snap_m, seq_m) and snap_s == seq_s == r["at"]
 
 
 @pytest.mark.parametrize("name", G.names("tcgraph"))
