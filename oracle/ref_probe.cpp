@@ -30,6 +30,7 @@
 #include "assembly_graph/construction/debruijn_graph_constructor.hpp"
 #include "assembly_graph/construction/early_simplification.hpp"
 #include "assembly_graph/graph_support/coverage_filling.hpp"
+#include "assembly_graph/index/edge_index_builders.hpp"
 #include "io/graph/gfa_writer.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
@@ -264,6 +265,28 @@ int main(int argc, char **argv) {
         }
         std::ofstream hs(outdir / "histogram.txt");
         for (size_t v : hist) hs << v << "\n";
+    }
+    // PROBE_EDGE_INDEX=<kk> (0 = k+1): the EdgeIndex refill of the pipeline (modules/graph_construction.hpp:74-82, alignment/edge_index.hpp:
+    // Refill -> GraphPositionFillingIndexBuilder, assembly_graph/index/edge_index_builders.hpp:274-307). kk == k+1 takes the (k+1)-mers
+    // straight from the edges (one MPHF, no counting); any other kk goes through DeBruijnGraphKMerSplitter + KMerDiskCounter with B buckets.
+    // edge_index.bin = KMerIndex::serialize; edge_index_values.bin = per slot { u64 edge id, u32 offset } (EdgeInfo, edge_position_index.hpp)
+    if (const char *ei = getenv("PROBE_EDGE_INDEX")) {
+        const unsigned kk = atoi(ei) ? (unsigned)atoi(ei) : k + 1;
+        using Index = KmerFreeEdgeIndex<DeBruijnGraph>;
+        Index index(g, kk);
+        omp_set_num_threads(kk == k + 1 ? T : (int)std::max(1u, B / 10));      // the counting path uses 10 x omp_get_max_threads() buckets
+        if (kk == k + 1) GraphPositionFillingIndexBuilder<Index>().BuildIndexFromGraph(index, g);
+        else GraphPositionFillingIndexBuilder<Index>().BuildIndexFromGraph(index, g, fs::tmp::make_temp_dir(outdir / "tmp", "edge_index"));
+        omp_set_num_threads(T);
+        dump_index(static_cast<const kmers::IndexWrapper<RtSeq, kmers::kmer_index_traits<RtSeq>>&>(index), outdir / "edge_index.bin");
+        std::ofstream vs(outdir / "edge_index_values.bin", std::ios::binary);
+        for (auto I = index.value_cbegin(), E = index.value_cend(); I != E; ++I) {
+            const uint64_t id = I->valid() ? (uint64_t)I->edge().int_id() : (I->removed() ? ~1ull : ~0ull);
+            const uint32_t off = I->offset();
+            vs.write((const char *)&id, 8); vs.write((const char *)&off, 4);
+        }
+        std::ofstream es(outdir / "edge_ids.txt");      // edge ids in graph iteration order with their sequences: the id <-> unitig mapping
+        for (EdgeId e : g.edges()) es << e.int_id() << " " << g.EdgeNucls(e).str() << "\n";
     }
     FillCoverageAndFlankingFromPHM(coverage_map, g, flanking_cov);
     {

@@ -21,6 +21,8 @@ SYMBOLS = [
     "sgpu_mphf_build", "sgpu_mphf_serialized_size", "sgpu_mphf_serialize", "sgpu_mphf_lookup", "sgpu_mphf_free",
     "sgpu_graph_build", "sgpu_graph_build_ex", "sgpu_graph_build_opts", "sgpu_graph_at_clipper_stats", "sgpu_graph_tip_clipper_stats", "sgpu_graph_masks", "sgpu_graph_coverage", "sgpu_graph_histogram", "sgpu_graph_num_unitigs",
     "sgpu_graph_unitig_bases", "sgpu_graph_unitigs", "sgpu_graph_gfa", "sgpu_graph_write_gfa", "sgpu_graph_free",
+    "sgpu_edge_index_build", "sgpu_edge_index_k", "sgpu_edge_index_size", "sgpu_edge_index_serialized_size", "sgpu_edge_index_serialize",
+    "sgpu_edge_index_values", "sgpu_edge_index_lookup", "sgpu_edge_index_free",
     "sgpu_dist_begin", "sgpu_dist_num_partitions", "sgpu_dist_local_counts", "sgpu_dist_plan", "sgpu_dist_free_bytes", "sgpu_dist_next_pass", "sgpu_dist_ipc_handle",
     "sgpu_dist_open_peers", "sgpu_dist_scatter", "sgpu_dist_exchange", "sgpu_dist_sort", "sgpu_dist_end", "sgpu_dist_free", "sgpu_dist_plan_host",
     "sgpu_selftest",
@@ -108,6 +110,14 @@ def load():
     L.sgpu_graph_gfa.restype = i64; L.sgpu_graph_gfa.argtypes = [vp, C.c_char_p, vp, i64]
     L.sgpu_graph_write_gfa.restype = i32; L.sgpu_graph_write_gfa.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.sgpu_graph_free.restype = None; L.sgpu_graph_free.argtypes = [vp]
+    L.sgpu_edge_index_build.restype = i32; L.sgpu_edge_index_build.argtypes = [vp, vp, i32, i32, pp]
+    L.sgpu_edge_index_k.restype = i32; L.sgpu_edge_index_k.argtypes = [vp]
+    L.sgpu_edge_index_size.restype = i64; L.sgpu_edge_index_size.argtypes = [vp]
+    L.sgpu_edge_index_serialized_size.restype = i64; L.sgpu_edge_index_serialized_size.argtypes = [vp]
+    L.sgpu_edge_index_serialize.restype = i32; L.sgpu_edge_index_serialize.argtypes = [vp, vp, i64]
+    L.sgpu_edge_index_values.restype = i32; L.sgpu_edge_index_values.argtypes = [vp, vp, vp, i64]
+    L.sgpu_edge_index_lookup.restype = i32; L.sgpu_edge_index_lookup.argtypes = [vp, vp, i64, vp]
+    L.sgpu_edge_index_free.restype = None; L.sgpu_edge_index_free.argtypes = [vp]
     L.sgpu_dist_begin.restype = i32; L.sgpu_dist_begin.argtypes = [vp, i32, i32, i32, i32, i32, pp]
     L.sgpu_dist_num_partitions.restype = i64; L.sgpu_dist_num_partitions.argtypes = [vp]
     L.sgpu_dist_local_counts.restype = i32; L.sgpu_dist_local_counts.argtypes = [vp, vp]

@@ -28,6 +28,7 @@ static void child_release(Ctx *c) {
 struct sgpu_kset { KSet *s; };
 struct sgpu_mphf { Mphf *m; };
 struct sgpu_graph { Graph *g; };
+struct sgpu_edge_index { EdgeIndex *e; };
 
 static int fail(Ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
@@ -405,6 +406,51 @@ int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *p
         fclose(f);
         SG_CHECK(ok, SGPU_EIO, "short write");
     })
+}
+int sgpu_edge_index_build(sgpu_ctx *ctx, const sgpu_graph *g, int K, int num_buckets, sgpu_edge_index **out) {
+    if (!ctx || !g || !out) return SGPU_EINVAL;
+    *out = nullptr;
+    Ctx *c = &ctx->c;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        EdgeIndex *e = edge_index_build(c, g->g, K, num_buckets);
+        *out = new sgpu_edge_index{e};
+        child_add(c);
+    })
+}
+int sgpu_edge_index_k(const sgpu_edge_index *e) { return e ? e->e->K : -1; }
+int64_t sgpu_edge_index_size(const sgpu_edge_index *e) { return e ? e->e->ks->n : -1; }
+int64_t sgpu_edge_index_serialized_size(const sgpu_edge_index *e) { return e ? (int64_t)mphf_serialized_size(e->e->m) : -1; }
+int sgpu_edge_index_serialize(const sgpu_edge_index *e, uint8_t *out, int64_t cap) {
+    if (!e || !out || cap < 0) return SGPU_EINVAL;
+    Ctx *c = e->e->ctx;
+    API_TRY(c, {
+        SG_CUDA(cudaSetDevice(c->device));
+        mphf_serialize_to(e->e->m, out, (size_t)cap);
+        if (e->e->single_segment) memset(out + mphf_serialized_size(e->e->m) - 8, 0, 8);     // see edge_index.cu: segment_starts_[1] of the single-index branch
+    })
+}
+int sgpu_edge_index_values(const sgpu_edge_index *e, uint64_t *edge_ids, uint32_t *offsets, int64_t n) {
+    if (!e || (n && (!edge_ids || !offsets))) return SGPU_EINVAL;
+    Ctx *c = e->e->ctx;
+    API_TRY(c, {
+        SG_CHECK(n == e->e->ks->n, SGPU_EINVAL, "value array size != number of K-mers in the edge index");
+        SG_CUDA(cudaSetDevice(c->device));
+        if (n) {
+            SG_CUDA(cudaMemcpy(edge_ids, e->e->edge_id.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+            SG_CUDA(cudaMemcpy(offsets, e->e->offset.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        }
+    })
+}
+int sgpu_edge_index_lookup(const sgpu_edge_index *e, const uint64_t *keys, int64_t n, uint64_t *out_idx) {
+    if (!e || (n && (!keys || !out_idx))) return SGPU_EINVAL;
+    Ctx *c = e->e->ctx;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); mphf_lookup_host_keys(c, e->e->m, keys, n, out_idx); })
+}
+void sgpu_edge_index_free(sgpu_edge_index *e) {
+    if (!e) return;
+    if (e->e) { Ctx *c = e->e->ctx; cudaSetDevice(c->device); delete e->e; child_release(c); }
+    delete e;
 }
 void sgpu_graph_free(sgpu_graph *g) {
     if (!g) return;

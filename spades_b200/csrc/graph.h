@@ -36,6 +36,19 @@ struct GraphOptions {
 Graph *graph_build(Ctx *ctx, const KSet *kp, const KSet *km, const Mphf *mk, const Mphf *mkp, const GraphOptions &opt);
 std::vector<uint64_t> graph_histogram(Ctx *ctx, const Graph *g);
 
+// edge_index.cu : KmerFreeEdgeIndex refill over the graph's own unitigs (alignment/edge_index.hpp, assembly_graph/index/edge_index_builders.hpp)
+struct EdgeIndex {
+    Ctx *ctx = nullptr;
+    int K = 0;
+    bool single_segment = false;   // K == k+1: built like KMerIndexBuilder's single-index branch (its segment_starts_[1] stays 0)
+    KSet *ks = nullptr;            // the minimal form of every K-mer of every edge (owned)
+    Mphf *m = nullptr;             // its KMerIndex (owned)
+    DArr<uint64_t> edge_id;        // per MPHF slot: EdgeId::int_id(), ~1 = removed (the K-mer occurs more than once), ~0 = cleared
+    DArr<uint32_t> offset;         // per MPHF slot: offset on that edge (EdgeInfo::TOMBSTONE / CLEARED otherwise)
+    ~EdgeIndex();
+};
+EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int num_buckets);
+
 // host_graph.cpp : FastGraphFromSequencesConstructor::ConstructGraph + GFAWriter
 std::string graph_gfa(const Graph *g, const char *version);
 

@@ -111,3 +111,53 @@ class DeBruijnGraphConstructor:
         ctx.check(ctx.L.sgpu_graph_build_opts(ctx.h, kpomers.h, kmers.h, kmer_index.h, kpomer_index.h if kpomer_index else None,
                                               C.byref(opts), C.byref(h)))
         return DeBruijnGraph(ctx, h, kpomers, kmers, kmer_index, kpomer_index)
+
+
+class EdgeIndex:
+    """debruijn_graph::EdgeIndex<Graph> after Refill() (alignment/edge_index.hpp:88-110): the K-mers of all edges (both strands) ->
+    (EdgeId, offset). num_buckets = 10 x the reference's threads. k=None indexes the (k+1)-mers like the pipeline (one index segment
+    built over that many vertex chunks); any other k goes through the counting path of the reference (edge_index_builders.hpp:274-307)
+    with `num_buckets` buckets."""
+    REMOVED, TOMBSTONE = (1 << 64) - 2, 0x7FFFFFFE
+
+    def __init__(self, graph: DeBruijnGraph, k=None, num_buckets=None):
+        self.ctx = graph.ctx
+        K = 0 if k is None else int(k)
+        B = 1 if num_buckets is None else int(num_buckets)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.sgpu_edge_index_build(self.ctx.h, graph.h, K, B, C.byref(h)))
+        self.h = h
+        self.K = self.ctx.L.sgpu_edge_index_k(h)
+        self.nw = (self.K + 31) // 32
+
+    def size(self):
+        return int(self.ctx.L.sgpu_edge_index_size(self.h))
+
+    def serialize(self) -> bytes:
+        n = self.ctx.L.sgpu_edge_index_serialized_size(self.h)
+        buf = np.zeros(max(n, 1), np.uint8)
+        self.ctx.check(self.ctx.L.sgpu_edge_index_serialize(self.h, _p(buf), n))
+        return buf[:n].tobytes()
+
+    def values(self):
+        """(edge ids u64[n], offsets u32[n]) in slot (MPHF) order"""
+        n = self.size()
+        ids = np.zeros(max(n, 1), np.uint64); offs = np.zeros(max(n, 1), np.uint32)
+        self.ctx.check(self.ctx.L.sgpu_edge_index_values(self.h, _p(ids), _p(offs), n))
+        return ids[:n], offs[:n]
+
+    def seq_idx(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint64).reshape(-1, self.nw)
+        out = np.zeros(max(len(keys), 1), np.uint64)
+        self.ctx.check(self.ctx.L.sgpu_edge_index_lookup(self.h, _p(keys), len(keys), _p(out)))
+        return out[: len(keys)]
+
+    def free(self):
+        if self.h:
+            self.ctx.L.sgpu_edge_index_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -72,12 +72,14 @@ def at_reads(n, L, glen, err, seed):
     return out + ["A" * L] * 5 + ["AT" * (L // 2)] * 3
 
 
-def run_probe(mode, reads, k, B, T=2, early_tc=0, early_at=False):
+def run_probe(mode, reads, k, B, T=2, early_tc=0, early_at=False, edge_index=None):
     with tempfile.TemporaryDirectory() as d:
         rf = os.path.join(d, "reads.txt")
         open(rf, "w").write("\n".join(reads) + "\n")
         out = os.path.join(d, "out")
         env = dict(os.environ)
+        if edge_index is not None:
+            env["PROBE_EDGE_INDEX"] = str(edge_index)  # EdgeIndex refill over the constructed graph: 0 = (k+1)-mers, else that K (counting path)
         if early_at:
             env["PROBE_EARLY_AT"] = "1"                # EarlyLowComplexityClipperProcessor (RNA pipeline), before the tip clipper
         if early_tc:
@@ -91,12 +93,16 @@ def run_probe(mode, reads, k, B, T=2, early_tc=0, early_at=False):
         return res
 
 
-def save(name, mode, reads, k, B, early_tc=0):
+def save(name, mode, reads, k, B, early_tc=0, edge_index=None):
     """mode "tcgraph" = graph mode with the pipeline's early tip clipper (length bound early_tc); masks_bin is the array
     before the clipper, masks_tc_bin after it, everything downstream (unitigs, GFA) comes from the clipped index.
     mode "atgraph" = graph mode with the RNA pipeline's early A/T clipper (masks_at_bin, at_removed_txt), followed by the tip clipper
     when early_tc is given (then masks_tc_bin is the array after both)."""
-    res = run_probe("graph" if mode in ("tcgraph", "atgraph") else mode, reads, k, B, early_tc=early_tc, early_at=(mode == "atgraph"))
+    res = run_probe("graph" if mode in ("tcgraph", "atgraph", "eigraph") else mode, reads, k, B, early_tc=early_tc, early_at=(mode == "atgraph"),
+                    edge_index=edge_index)
+    if edge_index is not None:
+        res["ei_k"] = np.array([edge_index if edge_index else k + 1])
+        res["ei_chunks"] = np.array([10 * 2])          # run_probe's T = 2: the (k+1)-mer path walks the edges in 10 x T vertex chunks
     if early_tc:
         res["tc_bound"] = np.array([early_tc])
     res["reads"] = np.frombuffer("\n".join(reads).encode(), dtype=np.uint8)
@@ -164,6 +170,11 @@ if __name__ == "__main__":
     save("rna_k33_B5_atgraph", "atgraph", at_reads(2000, 150, 3000, 0.02, 2), 33, 5, early_tc=150 - 33)
     save("rna_k55_B16_atgraph", "atgraph", at_reads(2000, 150, 4000, 0.01, 3), 55, 16, early_tc=150 - 55)
     save("rna_k11_B3_atgraph", "atgraph", at_reads(1500, 60, 800, 0.05, 4), 11, 3)
+    # EdgeIndex refill: the (k+1)-mer index of the pipeline and the counting path with a smaller K; B = 10 x 2 threads
+    save("syn_k21_B20_eigraph", "eigraph", synthetic_reads(600, 100, 1500, 0.01, seed=5), 21, 20, edge_index=0)
+    save("syn_k21_B20_K15_eigraph", "eigraph", synthetic_reads(600, 100, 1500, 0.01, seed=5), 21, 20, edge_index=15)
+    save("loops_k21_B10_eigraph", "eigraph", loops_reads(), 21, 10, edge_index=0)
+    save("ecoli_k55_B20_K33_eigraph", "eigraph", ec[:1200], 55, 20, edge_index=33)
     for nm, (rd, _) in GTEST_CASES.items():
         save("gtest_" + nm + "_k5", "graph", rd, 5, 2)
     # construction_test.cpp:97-105 (SimpleTestEarlyPairedInfo, k=3): its coverage table is the known answer in tests/test_oracle_golden.py

@@ -24,6 +24,9 @@ def load(name):
     g["k"] = int(g["k"][0]); g["B"] = int(g["B"][0]); g["mode"] = g["mode"].tobytes().decode()
     if "tc_bound" in g:
         g["tc_bound"] = int(g["tc_bound"][0])
+    for f in ("ei_k", "ei_chunks"):
+        if f in g:
+            g[f] = np.asarray(g[f])
     return g
 
 
@@ -101,6 +104,21 @@ def check_graph(g, art):
         chk("unitigs", g["unitigs_txt"].tobytes().decode().split() == list(art["unitigs"]))
     if "gfa" in art:
         chk("gfa", g["graph_gfa"].tobytes().decode() == art["gfa"])
+    return bad
+
+
+def check_edge_index(g, ei_bytes, ids, offs, nbuckets):
+    """EdgeIndex fixtures: edge_index.bin = ULEB(K) + KMerIndex::serialize, edge_index_values.bin = per slot {u64 edge id, u32 offset}"""
+    bad = []
+    K = int(g["ei_k"][0])
+    if not index_equal(strip_uleb_k(g["edge_index_bin"].tobytes(), K), ei_bytes, nbuckets):
+        bad.append("edge_index")
+    v = g["edge_index_values_bin"].reshape(-1, 12)
+    want_ids = v[:, :8].copy().view(np.uint64).ravel(); want_off = v[:, 8:].copy().view(np.uint32).ravel()
+    if not np.array_equal(want_ids, np.asarray(ids, np.uint64)):
+        bad.append("edge_ids")
+    if not np.array_equal(want_off, np.asarray(offs, np.uint32)):
+        bad.append("edge_offsets")
     return bad
 
 

@@ -211,3 +211,43 @@ def full_graph(reads, k, B, early_tc=0, early_at=False):
     u = Unitigs(km, mk, mk_arr, True)
     return dict(kp=kp, km=km, mk=mk, mkp=mkp, masks=mk_arr, masks_raw=raw, tc=tc, at=at, cov=cov, hist=histogram(cov), unitigs=u,
                 gfa=gfa(u, mk, mkp, cov))
+
+
+def edge_index(unitig_seqs, k, K=None, B=1):
+    """EdgeIndex refill restated on top of the oracle's count / MPHF (test infrastructure; python loops: small cases only).
+    keys   = the minimal form of every K-mer of every edge (GraphPositionFillingIndexBuilder::BuildIndexFromGraph,
+             assembly_graph/index/edge_index_builders.hpp:154-307; KmerFreeEdgeIndex is an InvertableStoring map, storing_traits.hpp:74,
+             92-101) = the canonical count over the primary strands; K = k+1 -> one index segment (KMerFullGraphStorage:
+             segment_policy_.reset(1)), else B buckets.
+    values = EdgeInfoUpdater::UpdateKMers (edge_info_updater.hpp:38-48: windows that are minimal as they stand, on every edge and its
+             conjugate) + PutInIndex (edge_position_index.hpp:152-167): one put -> (edge id, offset), more -> TOMBSTONE. Edge ids:
+             edge i -> 3 + 2i, conjugate +1, self-conjugate edges once (graph_core.hpp:233,514-531).
+    Returns (KSet, Mphf, ids u64[n], offsets u32[n]) in slot order."""
+    from spades_b200.packing import pack_reads, revcomp
+    K = k + 1 if K is None else K
+    words, offs, lens = pack_reads(unitig_seqs)
+    ks = count(words, offs, lens, K, B, 0)
+    m = Mphf(ks)
+    ids = np.full(ks.n, (1 << 64) - 1, np.uint64)
+    off = np.full(ks.n, 0x7FFFFFFF, np.uint32)
+    occ = np.zeros(ks.n, np.int64)
+    puts = []
+    for i, s in enumerate(unitig_seqs):
+        strands = [(s, 3 + 2 * i)]
+        if revcomp(s) != s:
+            strands.append((revcomp(s), 3 + 2 * i + 1))
+        for seq, eid in strands:
+            for j in range(len(seq) - K + 1):
+                kmer = seq[j:j + K]
+                if kmer > revcomp(kmer):              # RtSeq::IsMinimal: nucleotide order from position 0, ties (self-RC) are minimal
+                    continue
+                w, _, _ = pack_reads([kmer])
+                slot = m.lookup(w)
+                occ[slot] += 1
+                puts.append((slot, eid, j))
+    for slot, eid, j in puts:
+        if occ[slot] == 1:
+            ids[slot] = eid; off[slot] = j
+        else:
+            ids[slot] = (1 << 64) - 2; off[slot] = 0x7FFFFFFE
+    return ks, m, ids, off

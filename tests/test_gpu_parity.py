@@ -82,6 +82,47 @@ def test_early_at_clipper_matches_oracle_random(k, B, n, L, glen, seed):
     assert np.array_equal(art["masks"], r["masks"]) and art["unitigs"] == r["unitigs"].seqs and art["gfa"] == r["gfa"]
 
 
+@pytest.mark.parametrize("name", G.names("eigraph"))
+def test_edge_index_refill_matches_reference_golden(name):
+    """sgpu_edge_index_build over the GPU's own unitigs against the unmodified reference's EdgeIndex refill (KmerFreeEdgeIndex +
+    GraphPositionFillingIndexBuilder + EdgeInfoUpdater): serialized KMerIndex, and (edge id, offset / tombstone) of every slot"""
+    from gpu_util import ctx
+    from spades_b200.graph import DeBruijnGraphConstructor, EdgeIndex
+    from spades_b200.packing import pack_reads
+    g = G.load(name)
+    c = ctx()
+    c.set_reads(*pack_reads(g["reads"]))
+    gr = DeBruijnGraphConstructor(c, g["k"], g["B"]).ConstructGraph()
+    assert gr.unitigs() == g["unitigs_txt"].tobytes().decode().split()
+    K = int(g["ei_k"][0])
+    ei = EdgeIndex(gr, None if K == g["k"] + 1 else K, int(g["ei_chunks"][0]) if K == g["k"] + 1 else g["B"])
+    ids, offs = ei.values()
+    assert G.check_edge_index(g, ei.serialize(), ids, offs, 1 if K == g["k"] + 1 else g["B"]) == []
+    ei.free(); gr.free()
+
+
+def test_edge_index_refill_matches_oracle_random():
+    from gpu_util import ctx
+    from spades_b200.graph import DeBruijnGraphConstructor, EdgeIndex
+    from spades_b200.packing import pack_reads
+    c = ctx()
+    for k, B, K, seed in ((21, 6, None, 71), (33, 4, 25, 72), (55, 12, None, 73), (77, 3, 41, 74)):
+        reads = synthetic_reads(800, 150, 1500, 0.01, seed=seed)
+        c.set_reads(*pack_reads(reads))
+        gr = DeBruijnGraphConstructor(c, k, B).ConstructGraph()
+        ei = EdgeIndex(gr, K, B)
+        ids, offs = ei.values()
+        ks, m, want_ids, want_offs = O.edge_index(gr.unitigs(), k, K, 1 if K is None else B)
+        ser = m.serialize()
+        if K is None:                      # B vertex chunks (> 1, fewer than the vertices): the single-index branch leaves segment_starts_[1] = 0
+            ser = ser[:-8] + b"\0" * 8
+        assert ei.size() == ks.n and np.array_equal(ids, want_ids) and np.array_equal(offs, want_offs)
+        assert G.index_equal(ser, ei.serialize(), 1 if K is None else B)
+        # the reads' set is untouched by the refill: counting again gives the same (k+1)-mers
+        assert np.array_equal(DeBruijnGraphConstructor(c, k, B).ConstructGraph().kpomers.kmers(), gr.kpomers.kmers())
+        ei.free(); gr.free()
+
+
 @pytest.mark.parametrize("k,B,n,L,glen,err,seed", [(21, 16, 3000, 100, 4000, 0.02, 51), (55, 20, 3000, 150, 4000, 0.02, 52), (77, 3, 1500, 150, 2000, 0.01, 53),
                                                    (9, 3, 1000, 60, 600, 0.1, 54), (33, 2, 2000, 120, 900, 0.03, 55)])
 def test_early_tip_clipper_matches_oracle_random(k, B, n, L, glen, err, seed):

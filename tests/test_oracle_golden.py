@@ -53,6 +53,29 @@ def test_oracle_early_tip_clipper_matches_reference_golden(name):
     assert np.array_equal(snap[0], r["masks"]) and snap[1:] == (r["tc"]["removed"], r["tc"]["tipped"], r["tc"]["clipped"])
 
 
+@pytest.mark.parametrize("name", G.names("eigraph"))
+def test_oracle_edge_index_matches_reference_golden(name):
+    """EdgeIndex refill (KmerFreeEdgeIndex over the constructed graph; alignment/edge_index.hpp, edge_index_builders.hpp:154-307): the
+    serialized index and every slot's (edge id, offset / tombstone) against the unmodified reference, for the (k+1)-mer index of the
+    pipeline (one segment) and for the counting path with a smaller K (10 x threads buckets)"""
+    g = G.load(name)
+    r = O.full_graph(g["reads"], g["k"], g["B"])
+    assert r["unitigs"].seqs == g["unitigs_txt"].tobytes().decode().split()
+    K = int(g["ei_k"][0])
+    B = 1 if K == g["k"] + 1 else g["B"]
+    ks, m, ids, offs = O.edge_index(r["unitigs"].seqs, g["k"], K, B)
+    ser = m.serialize()
+    # (k+1)-mer path: with more than one vertex chunk KMerIndexBuilder takes its single-index branch, which never fills segment_starts_[1]
+    # (kmer_index_builder.hpp:481-493); vertices = both ends of every edge, each with its conjugate
+    ends = set()
+    for s in r["unitigs"].seqs:
+        for v in (s[:g["k"]], s[-g["k"]:]):
+            ends.add(min(v, revcomp(v)))
+    if K == g["k"] + 1 and (2 * len(ends)) // int(g["ei_chunks"][0]) > 0:
+        ser = ser[:-8] + b"\0" * 8
+    assert G.check_edge_index(g, ser, ids, offs, B) == []
+
+
 @pytest.mark.parametrize("name", G.names("graph"))
 def test_oracle_graph_matches_reference_golden(name):
     g = G.load(name)
