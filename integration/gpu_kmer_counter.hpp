@@ -25,13 +25,19 @@
 
 namespace kmers {
 
-class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
+// Seq = RtSeq for the assembler's own clients (spades-kmercount, Construction, EdgeIndex, MTS' KmerMultiplicityCounter,
+// projects/mts/kmer_multiplicity_counter.cpp:156-161) or a fixed-length Seq<K> such as BayesHammer's hammer::KMer = Seq<21>
+// (projects/hammer/kmer_stat.hpp:32-33, kmer_data.cpp:40-47,333-344): both pack 2 bits per nucleotide from bit 0 of word 0 and hash
+// their words with XXH3 (rtseq.hpp:690-696, seq.hpp:465-471), so records and buckets are the same bytes.
+template<class Seq>
+class GpuKMerDiskCounterT : public KMerCounter<Seq> {
   public:
-    // mode: SGPU_ALL_WINDOWS = spades-kmercount's splitter (every window of reads + RC, kmercount.cpp:48-122),
+    // mode: SGPU_ALL_WINDOWS = every window and its reverse complement (spades-kmercount's splitter, kmercount.cpp:48-122; BayesHammer's
+    //                          BufferFiller pushes seq and !seq, hammer/kmer_data.cpp:75-82),
     //       SGPU_CANONICAL   = DeBruijnReadKMerSplitter with the IsMinimal filter (kmer_splitters.hpp:112-136, storing_traits.hpp:92-101)
-    GpuKMerDiskCounter(fs::TmpDir work_dir, unsigned K, sgpu_ctx *ctx, int mode)
-            : KMerCounter<RtSeq>(K), work_dir_(work_dir), ctx_(ctx), mode_(mode) { check(sgpu_reads_clear(ctx_)); }
-    ~GpuKMerDiskCounter() override { if (last_) sgpu_kset_free(last_); }
+    GpuKMerDiskCounterT(fs::TmpDir work_dir, unsigned K, sgpu_ctx *ctx, int mode)
+            : KMerCounter<Seq>(K), work_dir_(work_dir), ctx_(ctx), mode_(mode) { check(sgpu_reads_clear(ctx_)); }
+    ~GpuKMerDiskCounterT() override { if (last_) sgpu_kset_free(last_); }
 
     // the payload of the reference's binary read records: Sequence::data(), ceil(size/32) words (sequence.hpp:808-830). Reads are
     // collected in a host batch and cross the C ABI kBatchReads at a time (one call per read would be 100 M calls for config 3).
@@ -43,6 +49,25 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
         for (size_t i = 0; i < s.size(); ++i) w[i >> 5] |= (uint64_t)s[i] << ((i & 31) << 1);          // rtseq.hpp:379-382 packing
         offs_.push_back((uint64_t)w0);
         lens_.push_back((uint32_t)s.size());
+        if (lens_.size() >= kBatchReads) Flush();
+    }
+    // a stretch of nucleotides given as text (BayesHammer: the valid stretches ValidKMerGenerator walks, hammer/valid_kmer_generator.hpp)
+    void AddString(const char *acgt, size_t n) {
+        if (n == 0) return;
+        const size_t nw = (n + 31) / 32, w0 = words_.size();
+        words_.resize(w0 + nw, 0);
+        uint64_t *w = words_.data() + w0;
+        for (size_t i = 0; i < n; ++i) w[i >> 5] |= (uint64_t)dignucl(acgt[i]) << ((i & 31) << 1);
+        offs_.push_back((uint64_t)w0);
+        lens_.push_back((uint32_t)n);
+        if (lens_.size() >= kBatchReads) Flush();
+    }
+    // one K-mer as a read of exactly K bases (MTS: DeBruijnKMerKMerSplitter over a k-mer file with K_source == K_target)
+    void AddKMer(const Seq &kmer) {
+        const size_t nw = Seq::GetDataSize(this->k()), w0 = words_.size();
+        words_.insert(words_.end(), kmer.data(), kmer.data() + nw);
+        offs_.push_back((uint64_t)w0);
+        lens_.push_back((uint32_t)this->k());
         if (lens_.size() >= kBatchReads) Flush();
     }
     // every read of a stream (io::ReadStream<io::SingleReadSeq> and friends: `stream >> read` until eof(), read.sequence())
@@ -76,14 +101,14 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
         return n;
     }
 
-    size_t kmer_size() const override { return RtSeq::GetDataSize(this->k()) * sizeof(RtSeq::DataType); }
+    size_t kmer_size() const override { return Seq::GetDataSize(this->k()) * sizeof(typename Seq::DataType); }
 
-    KMerDiskStorage<RtSeq> Count(unsigned num_buckets, unsigned /* num_threads */) override {
+    KMerDiskStorage<Seq> Count(unsigned num_buckets, unsigned /* num_threads */) override {
         Flush();
         if (last_) { sgpu_kset_free(last_); last_ = nullptr; }
         check(sgpu_count(ctx_, (int)this->k(), (int)num_buckets, mode_, &last_));
         INFO("K-mer counting done on the GPU. There are " << sgpu_kset_size(last_) << " kmers in total. ");
-        KMerDiskStorage<RtSeq> res(work_dir_, this->k(), kmer::KMerSegmentPolicy<RtSeq>(num_buckets));
+        KMerDiskStorage<Seq> res(work_dir_, this->k(), kmer::KMerSegmentPolicy<Seq>(num_buckets));
         // the storage creates (and keeps owning) the bucket files <prefix>.<i>; the library fills them
         std::string prefix;
         for (unsigned i = 0; i < num_buckets; ++i) {
@@ -94,7 +119,7 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
         return res;
     }
 
-    KMerDiskStorage<RtSeq> CountAll(unsigned num_buckets, unsigned num_threads, bool merge = true) override {
+    KMerDiskStorage<Seq> CountAll(unsigned num_buckets, unsigned num_threads, bool merge = true) override {
         auto storage = Count(num_buckets, num_threads);
         if (merge) storage.merge();
         return storage;
@@ -112,6 +137,7 @@ class GpuKMerDiskCounter : public KMerCounter<RtSeq> {
     std::vector<uint64_t> words_, offs_;
     std::vector<uint32_t> lens_;
 };
+using GpuKMerDiskCounter = GpuKMerDiskCounterT<RtSeq>;
 
 // The splitter-level seam: kmers::KMerSplitter<RtSeq> (kmer_splitter.hpp:25-53). Split() leaves, per bucket, ONE sorted-unique run
 // of W-byte records in <tmp>/kmers_raw.<i> plus <file>.idx holding its length (what KMerSortingSplitter::DumpBuffers appends per

@@ -15,6 +15,10 @@
 #include <iterator>
 
 #include "kmer_index/kmer_mph/kmer_index_traits.hpp"
+#include "kmer_index/kmer_mph/kmer_splitter.hpp"
+#include "kmer_index/kmer_mph/kmer_splitters.hpp"
+#include "kmer_index/ph_map/storing_traits.hpp"
+#include "sequence/seq.hpp"
 #include "utils/logger/log_writers.hpp"
 #include "utils/filesystem/temporary.hpp"
 
@@ -27,6 +31,62 @@ static void create_console_logger() {
     logger *lg = create_logger("");
     lg->add_writer(std::make_shared<console_writer>());
     attach_logger(lg);
+}
+
+// ---- a second client of the counter API: BayesHammer's k-mer value type (hammer::KMer = Seq<21>, projects/hammer/kmer_stat.hpp:32-33).
+// Reference side: a KMerSortingSplitter<Seq<21>> that pushes every window and its reverse complement, exactly what hammer's BufferFiller
+// does with the k-mers ValidKMerGenerator yields (projects/hammer/kmer_data.cpp:61-85), driven by the reference's own KMerDiskCounter.
+typedef Seq<21> HKMer;
+class RefHammerLikeSplitter : public kmers::KMerSortingSplitter<HKMer> {
+  public:
+    using typename kmers::KMerSortingSplitter<HKMer>::RawKMers;
+    RefHammerLikeSplitter(const std::filesystem::path &work_dir, const std::vector<std::string> &reads)
+            : kmers::KMerSortingSplitter<HKMer>(work_dir, 21), reads_(reads) {}
+    RawKMers Split(size_t num_files, unsigned) override {
+        auto out = this->PrepareBuffers(num_files, 1, 0);
+        for (const std::string &r : reads_) {
+            if (r.size() < 21) continue;
+            HKMer kmer(r.c_str());
+            bool stop = false;
+            for (size_t i = 21;; ++i) {
+                stop |= this->push_back_internal(kmer, 0);
+                stop |= this->push_back_internal(!kmer, 0);
+                if (i >= r.size()) break;
+                kmer = kmer << r[i];
+            }
+            if (stop) this->DumpBuffers(out);
+        }
+        this->DumpBuffers(out);
+        this->ClearBuffers();
+        return out;
+    }
+  private:
+    const std::vector<std::string> &reads_;
+};
+
+static std::string slurp(const std::filesystem::path &p) {
+    std::ifstream f(p, std::ios::binary);
+    return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+// returns the number of problems found
+static int hammer_client_check(sgpu_ctx *ctx, const std::vector<std::string> &reads, const std::filesystem::path &workdir, unsigned B) {
+    int bad = 0;
+    kmers::KMerDiskCounter<HKMer> ref(workdir, RefHammerLikeSplitter(workdir, reads));
+    auto ref_storage = ref.CountAll(B, 1, /* merge */ true);
+    kmers::GpuKMerDiskCounterT<HKMer> gpu(fs::tmp::make_temp_dir(workdir, "hammer_gpu"), 21, ctx, SGPU_ALL_WINDOWS);
+    for (const std::string &r : reads) gpu.AddString(r.data(), r.size());
+    auto gpu_storage = gpu.CountAll(B, 1, /* merge */ true);
+    if (gpu_storage.total_kmers() != ref_storage.total_kmers()) { ERROR("hammer client: k-mer counts differ"); ++bad; }
+    for (unsigned b = 0; b < B; ++b)
+        if (gpu_storage.bucket_size(b) != ref_storage.bucket_size(b)) { ERROR("hammer client: bucket " << b << " differs in size"); ++bad; break; }
+    if (slurp(gpu_storage.final_kmers()->file()) != slurp(ref_storage.final_kmers()->file())) { ERROR("hammer client: final_kmers differ"); ++bad; }
+    typedef kmers::KMerIndex<kmers::kmer_index_traits<HKMer>> HIndex;                // HammerKMerIndex, projects/hammer/kmer_data.hpp:21
+    HIndex index;
+    kmers::KMerIndexBuilder<HIndex>(1).BuildIndex(index, gpu_storage);
+    if (index.size() != gpu_storage.total_kmers()) { ERROR("hammer client: index size"); ++bad; }
+    if (!bad) INFO("hammer::KMer client (Seq<21>): GPU counter == reference KMerDiskCounter<Seq<21>> (" << gpu_storage.total_kmers() << " k-mers), index built");
+    return bad;
 }
 
 int main(int argc, char **argv) {
@@ -49,6 +109,7 @@ int main(int argc, char **argv) {
     int bad = 0;
     {
         kmers::GpuKMerDiskCounter counter(fs::tmp::make_temp_dir(workdir, "kmer_counter"), K, ctx, SGPU_ALL_WINDOWS);
+        std::vector<std::string> plain_reads;                                  // kept for the Seq<21> client check below (K == 21 only)
         {
             std::ifstream is(reads_path, std::ios::binary);
             const int c0 = is.get(), c1 = is.get();
@@ -59,7 +120,7 @@ int main(int argc, char **argv) {
             } else {                                                            // one ACGT read per line (ref_probe's format)
                 std::string line;
                 while (std::getline(is, line))
-                    if (!line.empty()) counter.AddRead(Sequence(line));
+                    if (!line.empty()) { counter.AddRead(Sequence(line)); if (K == 21) plain_reads.push_back(line); }
             }
         }
         auto storage = counter.Count(B, 1);                         // KMerDiskStorage<RtSeq>, buckets written from HBM
@@ -101,6 +162,25 @@ int main(int argc, char **argv) {
             const std::string sb((std::istreambuf_iterator<char>(b2)), std::istreambuf_iterator<char>());
             if (st2.total_kmers() != total || sa != sb) { ERROR("KMerDiskCounter over GpuKMerSplitter differs from GpuKMerDiskCounter"); ++bad; }
             else INFO("reference KMerDiskCounter over GpuKMerSplitter: identical final_kmers (" << st2.total_kmers() << " k-mers)");
+        }
+        // 5. another client of the same API with its own k-mer value type
+        if (K == 21 && !plain_reads.empty()) bad += hammer_client_check(ctx, plain_reads, workdir, B);
+        // 6. MTS' KmerMultiplicityCounter::BuildKmerIndex (projects/mts/kmer_multiplicity_counter.cpp:149-163): a k-mer FILE goes through
+        //    DeBruijnKMerKMerSplitter(K -> K, add_rc) + KMerDiskCounter with 16 buckets = canonicalise + dedup. GPU: every k-mer is a read
+        //    of exactly K bases, canonical count.
+        {
+            using KMerStorage = kmers::KMerDiskStorage<RtSeq>;
+            kmers::DeBruijnKMerKMerSplitter<kmers::StoringTypeFilter<kmers::InvertableStoring>, KMerStorage::kmer_iterator>
+                    splitter(fs::tmp::make_temp_dir(workdir, "mts_ref"), K, K, true, 0);
+            splitter.AddKMers(adt::make_range(KMerStorage::kmer_iterator(out, K), KMerStorage::kmer_iterator()));
+            kmers::KMerDiskCounter<RtSeq> mts_ref_counter(workdir, std::move(splitter));
+            auto ref_st = mts_ref_counter.CountAll(16, 1, true);
+            kmers::GpuKMerDiskCounter gpu_counter(fs::tmp::make_temp_dir(workdir, "mts_gpu"), K, ctx, SGPU_CANONICAL);
+            for (auto it = KMerStorage::kmer_iterator(out, K), e = KMerStorage::kmer_iterator(); it != e; ++it) gpu_counter.AddKMer(RtSeq(K, (*it).first));
+            auto gpu_st = gpu_counter.CountAll(16, 1, true);
+            if (gpu_st.total_kmers() != ref_st.total_kmers() || slurp(gpu_st.final_kmers()->file()) != slurp(ref_st.final_kmers()->file())) {
+                ERROR("MTS client: canonical k-mer sets differ"); ++bad;
+            } else INFO("MTS client (k-mer file -> canonical set, 16 buckets): GPU counter == reference (" << gpu_st.total_kmers() << " k-mers)");
         }
     }
     sgpu_destroy(ctx);

@@ -103,6 +103,10 @@ class KMerDiskStorage:
         self.ctx.check(self.ctx.L.sgpu_kset_download_keys(self.h, first, n, _p(out)))
         return out[:n]
 
+    def download_keys_into(self, host_ptr, n, first=0):
+        """records [first, first+n) of final_kmers order copied to caller memory (e.g. a pinned buffer of n * nw u64)"""
+        self.ctx.check(self.ctx.L.sgpu_kset_download_keys(self.h, first, n, C.c_void_p(host_ptr)))
+
     def counts(self, first=0, n=None):
         n = self._n - first if n is None else n
         out = np.zeros(max(n, 1), np.uint32)

@@ -64,6 +64,9 @@ def test_reference_host_code_over_the_c_abi(name):
     assert np.array_equal(fk, g["final_kmers"])
     assert "reference-built and GPU-built KMerIndex agree" in p.stdout
     assert "reference KMerDiskCounter over GpuKMerSplitter: identical final_kmers" in p.stdout        # the KMerSplitter-level seam
+    assert "MTS client (k-mer file -> canonical set, 16 buckets): GPU counter == reference" in p.stdout   # SURVEY 8f-4 clients
+    if g["k"] == 21:
+        assert "hammer::KMer client (Seq<21>): GPU counter == reference KMerDiskCounter<Seq<21>>" in p.stdout
 
 
 @needs_tool
