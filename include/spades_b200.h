@@ -93,6 +93,16 @@ int sgpu_reads_append_packed(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwor
  * are enqueued on the context's stream and the call returns: the buffers must stay valid and unmodified until the next
  * sgpu_count / sgpu_dist_begin on this context has returned (both synchronise the stream). */
 int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, const uint64_t *offs, const uint32_t *lens, int64_t nreads);
+/* GPU-side packing: the host only locates the sequence of every read inside a text buffer (FASTA/FASTQ file contents:
+ * byte offset + length of each single-line sequence; sgpu_text_index_fastx does it for 2-line FASTA / 4-line FASTQ); the device applies
+ * io::LongestValid (io/reads/longest_valid_wrapper.hpp:16-53; longest_valid = 0: a read with any non-ACGT symbol contributes nothing)
+ * and packs 2 bits per base (Sequence::BinWrite payload). Replaces the context's read set; reads without a valid base keep a slot of
+ * length 0. */
+int sgpu_reads_pack_text(sgpu_ctx *ctx, const char *text, uint64_t text_bytes, const uint64_t *seq_off, const uint32_t *seq_len, int64_t nreads,
+                         int longest_valid);
+/* the context's current (packed) read set: sizes, and a copy to host arrays of those sizes (any pointer may be NULL) */
+int sgpu_reads_info(sgpu_ctx *ctx, int64_t *nreads, uint64_t *nwords);
+int sgpu_reads_download(sgpu_ctx *ctx, uint64_t *words, uint64_t *offs, uint32_t *lens);
 /* use a read set that already lives in device memory (not copied, must stay valid while the context uses it) */
 int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads);
 
@@ -118,6 +128,10 @@ const uint32_t *sgpu_read_batch_lens(const sgpu_read_batch *b);
 int sgpu_read_batch_stats(const sgpu_read_batch *b, uint64_t *out3);   /* records in the file, reads trimmed by LongestValid, reads dropped */
 const char *sgpu_read_batch_error(const sgpu_read_batch *b);
 void sgpu_read_batch_free(sgpu_read_batch *b);
+/* host side of sgpu_reads_pack_text: sequence ranges of a strictly 2-line FASTA ('>') / 4-line FASTQ ('@', '+', quality as long as the
+ * sequence) text; a trailing '\r' is excluded. out arrays must hold max_reads entries; returns the number of reads, -1 if the text is
+ * not in that strict layout (then use sgpu_fastx_parse, which implements kseq's general record semantics), -2 if max_reads is too small */
+int64_t sgpu_text_index_fastx(const char *text, uint64_t text_bytes, uint64_t *seq_off, uint32_t *seq_len, int64_t max_reads);
 /* sgpu_reads_append_packed of a whole batch */
 int sgpu_reads_append_batch(sgpu_ctx *ctx, const sgpu_read_batch *b);
 

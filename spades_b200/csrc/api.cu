@@ -136,6 +136,22 @@ int sgpu_reads_upload(sgpu_ctx *ctx, const uint64_t *words, uint64_t nwords, con
     })
 }
 
+int sgpu_reads_pack_text(sgpu_ctx *ctx, const char *text, uint64_t text_bytes, const uint64_t *seq_off, const uint32_t *seq_len, int64_t nreads, int longest_valid) {
+    if (!ctx || nreads < 0 || (nreads && (!text || !seq_off || !seq_len))) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); reads_pack_text(c, text, text_bytes, seq_off, seq_len, nreads, longest_valid); })
+}
+int sgpu_reads_info(sgpu_ctx *ctx, int64_t *nreads, uint64_t *nwords) {
+    if (!ctx || !nreads || !nwords) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); ensure_reads_on_device(c); *nreads = c->n_reads; *nwords = c->n_words; })
+}
+int sgpu_reads_download(sgpu_ctx *ctx, uint64_t *words, uint64_t *offs, uint32_t *lens) {
+    if (!ctx) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); reads_download(c, words, offs, lens); })
+}
+
 int sgpu_reads_adopt_device(sgpu_ctx *ctx, const uint64_t *d_words, uint64_t nwords, const uint64_t *d_offs, const uint32_t *d_lens, int64_t nreads) {
     if (!ctx || nreads < 0) return SGPU_EINVAL;
     Ctx *c = &ctx->c;

@@ -356,6 +356,41 @@ int sgpu_fastx_parse_threads(const char *path, int longest_valid, int nthreads, 
     *out = b;                                   // returned even on failure so that sgpu_read_batch_error() can be read
     return parse_fastx(path, longest_valid != 0, nthreads, b) ? SGPU_OK : SGPU_EIO;
 }
+int64_t sgpu_text_index_fastx(const char *text, uint64_t text_bytes, uint64_t *seq_off, uint32_t *seq_len, int64_t max_reads) {
+    if (!text && text_bytes) return -1;
+    if (text_bytes == 0) return 0;
+    const int stride = text[0] == '>' ? 2 : (text[0] == '@' ? 4 : 0);
+    if (!stride) return -1;
+    int64_t n = 0;
+    uint64_t pos = 0;
+    int line = 0;
+    uint32_t cur_len = 0;
+    while (pos < text_bytes) {
+        const char *nl = (const char *)memchr(text + pos, '\n', text_bytes - pos);
+        uint64_t end = nl ? (uint64_t)(nl - text) : text_bytes;
+        uint64_t len = end - pos;
+        if (len && text[end - 1] == '\r') --len;
+        const int which = line % stride;
+        if (which == 0) {
+            if (len == 0 && !nl) break;                                  // trailing empty line
+            if (len == 0 || text[pos] != (stride == 2 ? '>' : '@')) return -1;
+        } else if (which == 1) {
+            if (len > 0xffffffffull) return -1;
+            if (len && (text[pos] == '>' || text[pos] == '@' || text[pos] == '+')) return -1;      // would start another record / quality in kseq
+            if (n >= max_reads) return -2;
+            seq_off[n] = pos; seq_len[n] = (uint32_t)len; cur_len = (uint32_t)len;
+            ++n;
+        } else if (which == 2) {
+            if (len == 0 || text[pos] != '+') return -1;
+        } else {
+            if (len != cur_len) return -1;
+        }
+        ++line;
+        pos = nl ? end + 1 : text_bytes;
+    }
+    if (line % stride != 0) return -1;                                    // truncated record
+    return n;
+}
 int sgpu_fastx_parse(const char *path, int longest_valid, sgpu_read_batch **out) { return sgpu_fastx_parse_threads(path, longest_valid, 0, out); }
 int sgpu_seqfile_parse(const char *prefix, sgpu_read_batch **out) {
     if (!prefix || !out) return SGPU_EINVAL;

@@ -267,6 +267,10 @@ void exclusive_scan_u64(Ctx *ctx, const uint64_t *in, uint64_t *out, size_t n);
 void exclusive_scan_u32_to_u64(Ctx *ctx, const uint32_t *in, uint64_t *out, size_t n);
 void ensure_reads_on_device(Ctx *ctx);
 
+// ingest_gpu.cu
+void reads_pack_text(Ctx *ctx, const char *text, uint64_t text_bytes, const uint64_t *seq_off, const uint32_t *seq_len, int64_t n, int longest_valid);
+void reads_download(Ctx *ctx, uint64_t *words, uint64_t *offs, uint32_t *lens);
+
 // count.cu
 enum CountMode { kCanonical = 0, kAllWindows = 1 };
 KSet *count_from_reads(Ctx *ctx, int K, int B, int mode);

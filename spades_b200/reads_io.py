@@ -73,3 +73,36 @@ def read_fastx(path, longest_valid=True, threads=0) -> ReadBatch:
 
 def read_seqfile(prefix) -> ReadBatch:
     return _parse(_lib.load().sgpu_seqfile_parse, str(prefix).encode())
+
+
+def index_text(data: bytes):
+    """host side of the GPU packer: (offsets u64[n], lengths u32[n]) of every read's sequence inside a strictly 2-line FASTA / 4-line FASTQ
+    text, or None when the text is not in that layout (multi-line records, junk: use read_fastx, which has kseq's general semantics)"""
+    L = _lib.load()
+    cap = data.count(b"\n") // 2 + 2
+    off = np.zeros(cap, np.uint64); ln = np.zeros(cap, np.uint32)
+    n = L.sgpu_text_index_fastx(data, len(data), off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p), cap)
+    if n < 0:
+        return None
+    return off[:n], ln[:n]
+
+
+def pack_text_on_gpu(ctx, data: bytes, longest_valid=True):
+    """FASTA/FASTQ text -> the context's packed read set with trimming (LongestValid) and 2-bit packing done by CUDA kernels
+    (sgpu_reads_pack_text); the host only locates the sequence lines. Returns the number of reads (zero-length ones included)."""
+    idx = index_text(data)
+    if idx is None:
+        raise IOError("not a strict 2-line FASTA / 4-line FASTQ text: use read_fastx")
+    off, ln = idx
+    ctx.check(ctx.L.sgpu_reads_pack_text(ctx.h, data, len(data), off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p), len(ln),
+                                         1 if longest_valid else 0))
+    return len(ln)
+
+
+def download_reads(ctx):
+    """the context's packed read set as host arrays (words, offs, lens)"""
+    n, nw = C.c_int64(), C.c_uint64()
+    ctx.check(ctx.L.sgpu_reads_info(ctx.h, C.byref(n), C.byref(nw)))
+    words = np.zeros(max(nw.value, 1), np.uint64); offs = np.zeros(max(n.value, 1), np.uint64); lens = np.zeros(max(n.value, 1), np.uint32)
+    ctx.check(ctx.L.sgpu_reads_download(ctx.h, words.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)))
+    return words[: nw.value], offs[: n.value], lens[: n.value]

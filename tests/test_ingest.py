@@ -281,3 +281,62 @@ def test_parallel_parse_is_exact(tmp_path):
     open(bad, "w").write(files["four_line.fq"] + "@last\nACGT\n+\nII\n")
     with pytest.raises(IOError):
         read_fastx(bad, threads=8)
+
+
+def _awkward_fastq(n=400, seed=9):
+    import random
+    rnd = random.Random(seed)
+    recs = []
+    for i in range(n):
+        L = rnd.choice([0, 1, 31, 32, 33, 64, 100, 150, 151, 300])
+        seq = "".join(rnd.choice("ACGTacgtNn.") if rnd.random() < 0.1 else rnd.choice("ACGT") for _ in range(L))
+        recs.append((seq, "".join(chr(33 + rnd.randrange(40)) for _ in range(L))))
+    return recs
+
+
+def test_text_index_of_strict_fastx_and_refusal_of_everything_else(tmp_path):
+    """host half of the GPU packer (sgpu_text_index_fastx): sequence ranges of strict 4-line FASTQ / 2-line FASTA (also with CRLF and
+    without a final newline) equal what the general parser sees; multi-line records, junk and truncated records are refused"""
+    from spades_b200.reads_io import index_text
+    recs = _awkward_fastq()
+    fq = "".join("@r%d x\n%s\n+\n%s\n" % (i, s, q) for i, (s, q) in enumerate(recs))
+    fa = "".join(">s%d\n%s\n" % (i, s) for i, (s, q) in enumerate(recs))
+    for text in (fq, fq.replace("\n", "\r\n"), fq[:-1], fa, fa[:-1]):
+        data = text.encode()
+        off, ln = index_text(data)
+        assert [data[int(o):int(o) + int(l)].decode() for o, l in zip(off, ln)] == [s for s, _ in recs]
+    f = tmp_path / "x.fq"; f.write_text(fq)
+    want = [longest_valid(s) for s, _ in recs]
+    assert read_fastx(f).strings() == [w.upper() for w in want if w]
+    assert index_text(b"@r\nACGT\nACGT\n+\nIIIIIIII\n") is None            # multi-line sequence
+    assert index_text(b"junk\n@r\nACGT\n+\nIIII\n") is None
+    assert index_text(b"@r\nACGT\n+\nIII\n") is None                        # quality of another length
+    assert index_text(b"@r\nACGT\n+\n") is None                              # truncated
+    assert index_text(b"")[0].size == 0
+
+
+@pytest.mark.gpu
+def test_gpu_packer_matches_host_ingest():
+    """sgpu_reads_pack_text (LongestValid + 2-bit packing in CUDA kernels) against the host ingest on the same awkward FASTQ: identical
+    words / lengths for every read with a valid base, and identical k-mers downstream"""
+    import tempfile
+    from gpu_util import ctx
+    from spades_b200.kmer_index import KMerDiskCounter, ParallelSortingSplitter
+    from spades_b200.reads_io import download_reads, pack_text_on_gpu
+    recs = _awkward_fastq(3000, seed=10)
+    fq = "".join("@r%d\n%s\n+\n%s\n" % (i, s, q) for i, (s, q) in enumerate(recs)).encode()
+    c = ctx()
+    for lv in (True, False):
+        n = pack_text_on_gpu(c, fq, longest_valid=lv)
+        assert n == len(recs)
+        words, offs, lens = download_reads(c)
+        want = [longest_valid(s) if lv else (s if all(ch in "ACGTacgt" for ch in s) else "") for s, _ in recs]
+        assert [int(x) for x in lens] == [len(w) for w in want]
+        hw, ho, hl = pack_reads([w.upper() for w in want if w])
+        got = np.concatenate([words[int(o):int(o) + (int(l) + 31) // 32] for o, l in zip(offs, lens) if l]) if len(hw) else np.zeros(0, np.uint64)
+        assert np.array_equal(got, hw)
+        st = KMerDiskCounter(c, ParallelSortingSplitter(21)).Count(7)
+        k_gpu = st.kmers(); st.free()
+        c.set_reads(hw, ho, hl)
+        st = KMerDiskCounter(c, ParallelSortingSplitter(21)).Count(7)
+        assert np.array_equal(k_gpu, st.kmers()); st.free()
