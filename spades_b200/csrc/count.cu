@@ -1384,7 +1384,7 @@ static void levelA_count(LevelAJob<NW, Src> &job, uint64_t est_records, Timer &t
     job.tile_off.clear(); job.ids.clear();
     job.tile_off.resize(job.srcs.size()); job.ids.resize(job.srcs.size());
     // per-record partition ids (2 bytes per record slot): only when they fit comfortably next to the sort buffers
-    job.use_ids = PA_all < 0xffffu && (double)est_records * 2.0 < (double)ctx->free_bytes() * 0.15;
+    job.use_ids = PA_all < 0xffffu && (double)est_records * 2.0 < (double)ctx->free_bytes() * 0.20;
     if (job.use_ids) {
         for (size_t si = 0; si < job.srcs.size(); ++si) {
             const Src &src = job.srcs[si];

@@ -314,13 +314,17 @@ __global__ void tc_apply_k(uint8_t *__restrict__ masks, const uint8_t *__restric
     if (i < n && mark[i]) masks[i] = 0;
 }
 template <int NW>
+// flags_by_slot = 0: tipped[] is indexed by the thread (table position, orientation), as tc_probe_k writes it; 1: by (MPHF slot, orientation),
+// as at_tips_probe_k marks the roots it reaches by walking
 __global__ void tc_links_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__restrict__ masks, const uint32_t *__restrict__ tipped,
-                           unsigned long long *__restrict__ stat_clipped) {
+                           unsigned long long *__restrict__ stat_clipped, int flags_by_slot) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= 2 * n || !tipped[tid]) return;
+    if (tid >= 2 * n) return;
+    if (!flags_by_slot && !tipped[tid]) return;
     const Kmer<NW> key = table_key<NW>(t, tid >> 1);
     const Kmer<NW> kh = (tid & 1) ? kmer_rc<NW>(key, K) : key;
     const CanonIdx<NW> ci = canon_lookup<NW>(mk, kh, K);
+    if (flags_by_slot && !tipped[2 * ci.idx + (uint64_t)(tid & 1)]) return;
     const uint8_t raw = masks[ci.idx];
     const uint8_t m = ci.is_min ? raw : inv_byte(raw);
     const int first = (int)(kh.w[0] & 3);                        // kh[0]
@@ -368,10 +372,12 @@ __global__ void at_edges_probe_k(KeyTable t, int64_t n, int K, MphfDev mk, const
                                  uint8_t *__restrict__ eflag /*[2n]*/, unsigned long long *__restrict__ stats) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= 2 * n) return;
-    eflag[tid] = 0;
     const Kmer<NW> key = table_key<NW>(t, tid >> 1);
     const int o = (int)(tid & 1);
-    const uint8_t mfw = masks[mphf_lookup_dev<NW>(mk, key)];
+    const uint64_t slot = mphf_lookup_dev<NW>(mk, key);
+    const int64_t fid = (int64_t)(2 * slot) + o;                        // flags are indexed by (MPHF slot, orientation), like the masks
+    eflag[fid] = 0;
+    const uint8_t mfw = masks[slot];
     const uint8_t m = o ? inv_byte(mfw) : mfw;
     if (!mask_is_junction(m)) return;
     const Kmer<NW> kh = o ? kmer_rc<NW>(key, K) : key;
@@ -389,7 +395,7 @@ __global__ void at_edges_probe_k(KeyTable t, int64_t n, int K, MphfDev mk, const
         if (!mask_is_junction(mn) && (mn & 15) != 0) continue;          // an edge of length 1: next is a junction or a dead end
         f |= (uint8_t)(1u << c);
     }
-    eflag[tid] = f;
+    eflag[fid] = f;
     if (f) atomicAdd(&stats[0], (unsigned long long)__popc(f));
 }
 __device__ __forceinline__ void mask_clear_bit(uint8_t *masks, uint64_t idx, unsigned bit) {
@@ -399,20 +405,23 @@ template <int NW>
 __global__ void at_edges_apply_k(KeyTable t, int64_t n, int K, MphfDev mk, uint8_t *__restrict__ masks, const uint8_t *__restrict__ eflag,
                                  unsigned long long *__restrict__ stats) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= 2 * n || !eflag[tid]) return;
+    if (tid >= 2 * n) return;
     const Kmer<NW> key = table_key<NW>(t, tid >> 1);
     const Kmer<NW> kh = (tid & 1) ? kmer_rc<NW>(key, K) : key;
     const CanonIdx<NW> ci = canon_lookup<NW>(mk, kh, K);
+    const int64_t fid = (int64_t)(2 * ci.idx) + (tid & 1);               // kh is the table key (minimal form) iff the orientation bit is 0
+    const uint8_t mine = eflag[fid];
+    if (!mine) return;
     const int first = (int)(kh.w[0] & 3);                                // kh[0]
     for (int c = 0; c < 4; ++c) {
-        if (!(eflag[tid] & (1u << c))) continue;
+        if (!(mine & (1u << c))) continue;
         Kmer<NW> nx = kh;
         kmer_shl<NW>(nx, K, c);
         const CanonIdx<NW> cn = canon_lookup<NW>(mk, nx, K);
         // the same link seen from the other strand: (rc(next), complement of kh[0]); rc(next) is the table key iff next is NOT minimal
-        const int64_t tid2 = (int64_t)(2 * cn.idx) + (cn.is_min ? 1 : 0);
+        const int64_t fid2 = (int64_t)(2 * cn.idx) + (cn.is_min ? 1 : 0);
         const int c2 = 3 - first;
-        if ((eflag[tid2] & (1u << c2)) && (tid2 < tid || (tid2 == tid && c2 < c))) continue;
+        if ((eflag[fid2] & (1u << c2)) && (fid2 < fid || (fid2 == fid && c2 < c))) continue;
         mask_clear_bit(masks, ci.idx, (unsigned)(ci.is_min ? c : 7 - c));                        // DeleteOutgoing(kh, c)
         mask_clear_bit(masks, cn.idx, (unsigned)(cn.is_min ? 4 + first : 7 - (4 + first)));      // DeleteIncoming(next, kh[0])
         atomicAdd(&stats[1], 2ull);
@@ -670,7 +679,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         at_edges_apply_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, eflag.p, stats.p);
         at_tips_probe_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, ap, mark.p, rooted.p, stats.p);
         tc_apply_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(g->masks.p, mark.p, nk);
-        tc_links_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, rooted.p, stats.p + 3);
+        tc_links_k<NW><<<grid2, 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, rooted.p, stats.p + 3, 1);
         ctx->launches += 5;
         SG_CUDA(cudaGetLastError());
         unsigned long long hs[4];
@@ -689,7 +698,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         const uint32_t bound = (uint32_t)std::min<uint64_t>(early_tc_bound, 0x7fffffffu);
         tc_probe_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, bound, mark.p, tipped.p, stats.p);
         tc_apply_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(g->masks.p, mark.p, nk);
-        tc_links_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, tipped.p, stats.p + 2);
+        tc_links_k<NW><<<div_up((int64_t)(2 * nk), 128), 128, 0, st>>>(tt, (int64_t)nk, K, mk, g->masks.p, tipped.p, stats.p + 2, 0);
         ctx->launches += 3;
         SG_CUDA(cudaGetLastError());
         unsigned long long hs[4];
