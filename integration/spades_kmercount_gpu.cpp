@@ -46,7 +46,7 @@ class RefHammerLikeSplitter : public kmers::KMerSortingSplitter<HKMer> {
         auto out = this->PrepareBuffers(num_files, 1, 0);
         for (const std::string &r : reads_) {
             if (r.size() < 21) continue;
-            HKMer kmer(r.c_str());
+            HKMer kmer(r, 0, 21);                               // the (string, offset, count) constructor; Seq(const char*) wants strlen == 21
             bool stop = false;
             for (size_t i = 21;; ++i) {
                 stop |= this->push_back_internal(kmer, 0);
@@ -73,18 +73,21 @@ static std::string slurp(const std::filesystem::path &p) {
 static int hammer_client_check(sgpu_ctx *ctx, const std::vector<std::string> &reads, const std::filesystem::path &workdir, unsigned B) {
     int bad = 0;
     kmers::KMerDiskCounter<HKMer> ref(workdir, RefHammerLikeSplitter(workdir, reads));
-    auto ref_storage = ref.CountAll(B, 1, /* merge */ true);
+    // unmerged storages first: bucket by bucket (KMerDiskStorage::merge drops the bucket list, kmer_index_builder.hpp:190-201)
+    auto ref_storage = ref.CountAll(B, 1, /* merge */ false);
     kmers::GpuKMerDiskCounterT<HKMer> gpu(fs::tmp::make_temp_dir(workdir, "hammer_gpu"), 21, ctx, SGPU_ALL_WINDOWS);
     for (const std::string &r : reads) gpu.AddString(r.data(), r.size());
-    auto gpu_storage = gpu.CountAll(B, 1, /* merge */ true);
+    auto gpu_storage = gpu.CountAll(B, 1, /* merge */ false);
     if (gpu_storage.total_kmers() != ref_storage.total_kmers()) { ERROR("hammer client: k-mer counts differ"); ++bad; }
     for (unsigned b = 0; b < B; ++b)
         if (gpu_storage.bucket_size(b) != ref_storage.bucket_size(b)) { ERROR("hammer client: bucket " << b << " differs in size"); ++bad; break; }
-    if (slurp(gpu_storage.final_kmers()->file()) != slurp(ref_storage.final_kmers()->file())) { ERROR("hammer client: final_kmers differ"); ++bad; }
     typedef kmers::KMerIndex<kmers::kmer_index_traits<HKMer>> HIndex;                // HammerKMerIndex, projects/hammer/kmer_data.hpp:21
     HIndex index;
     kmers::KMerIndexBuilder<HIndex>(1).BuildIndex(index, gpu_storage);
     if (index.size() != gpu_storage.total_kmers()) { ERROR("hammer client: index size"); ++bad; }
+    gpu_storage.merge();
+    ref_storage.merge();
+    if (slurp(gpu_storage.final_kmers()->file()) != slurp(ref_storage.final_kmers()->file())) { ERROR("hammer client: final_kmers differ"); ++bad; }
     if (!bad) INFO("hammer::KMer client (Seq<21>): GPU counter == reference KMerDiskCounter<Seq<21>> (" << gpu_storage.total_kmers() << " k-mers), index built");
     return bad;
 }

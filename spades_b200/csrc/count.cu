@@ -226,7 +226,7 @@ template <int NW>
 __device__ __forceinline__ bool part_of(const LevelA &p, const Kmer<NW> &k, uint32_t *part) {
     uint32_t b = kmer_bucket<NW>(k, p.B);
     if (b < p.b_lo || b >= p.b_hi) return false;
-    *part = ((b - p.b_lo) << p.rA) | (p.rA ? key_bits<NW>(k, p.K, 0, p.rA) : 0u);
+    *part = ((b - p.b_lo) << p.rA) | key_top_bits<NW>(k, p.K, p.rA);
     return true;
 }
 
@@ -495,13 +495,16 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
                                                                         const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
                                                                         uint32_t id_lo, uint32_t row_stride, uint32_t q_lo) {
     extern __shared__ uint32_t sm_dyn[];
-    uint64_t *cur_base = reinterpret_cast<uint64_t *>(sm_dyn);          // PA u64
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(cur_base + p.PA);      // PA u32
+    // one 32-bit cursor per partition, relative to the first record this launch may write (a CTA's share of a pass is far below
+    // 2^32 records): the slot of a record is ONE shared-memory atomic, no base lookup and no 64-bit add behind it
+    uint32_t *cur = sm_dyn;                                             // PA u32
     __shared__ RollTile rt;
     __shared__ TileStage ts;
     uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
-    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) { cur_base[i] = mybase[i]; cnt[i] = 0; }
+    const uint64_t region0 = mybase[0];                                 // cursors of a row ascend with the partition
+    for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) cur[i] = (uint32_t)(mybase[i] - region0);
     __syncthreads();
+    uint64_t *const out0 = out + region0 * NW;
     const int K = p.K;
     const uint32_t PA = p.PA;
     const int64_t ntiles = (src.n + kATile - 1) / kATile;
@@ -530,26 +533,31 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
             roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
 #pragma unroll
             for (int s = 0; s < kRollC; ++s) {
-                if (s < q.cnt) {
-                    if (s > 0) roll_next<NW>(st, seq, K);
-                    uint32_t part;
-                    bool mine;
-                    if (HAS_IDS) {
-                        part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;     // 0xffff - id_lo stays >= PA
-                        mine = part < PA;
-                    }
-                    const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
-                    if (!HAS_IDS) mine = part_of<NW>(p, k, &part);
+                if (s >= q.cnt) break;
+                if (s > 0) roll_next<NW>(st, seq, K);
+                uint32_t part;
+                bool mine;
+                if (HAS_IDS) {
+                    // a foreign window costs the roll and this compare; the canonical choice is made for own windows only
+                    part = (uint32_t)((idw[s >> 2] >> (16 * (s & 3))) & 0xffffu) - id_lo;         // 0xffff - id_lo stays >= PA
+                    mine = part < PA;
                     if (mine) {
-                        const uint32_t slot = atomicAdd(&cnt[part], 1u);
-                        store_rec_stream<NW>(out + (cur_base[part] + slot) * NW, k);
+                        const uint32_t slot = atomicAdd(&cur[part], 1u);
+                        store_rec_stream<NW>(out0 + (size_t)slot * NW, kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r);
+                    }
+                } else {
+                    const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
+                    mine = part_of<NW>(p, k, &part);
+                    if (mine) {
+                        const uint32_t slot = atomicAdd(&cur[part], 1u);
+                        store_rec_stream<NW>(out0 + (size_t)slot * NW, k);
                     }
                 }
             }
         }
         __syncthreads();
     }
-    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = cur_base[i] + cnt[i];   // chained launches continue here
+    for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = region0 + cur[i];   // chained launches continue here
 }
 
 // (Round 2 measured a third generation of this kernel -- id sweep, 32-bit keys collected without atomics, ballot-ranked LSD sort
@@ -1459,7 +1467,7 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
     tm.start();
     if (job.roll) {
         if constexpr (std::is_same<Src, ReadsSrc>::value) {
-            const size_t smem = (size_t)PA * (sizeof(uint64_t) + sizeof(uint32_t));
+            const size_t smem = (size_t)PA * sizeof(uint32_t);
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
@@ -1476,7 +1484,7 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
                 if (q_hi == q_lo) continue;
                 LevelA pa_sub = pa;
                 pa_sub.PA = q_hi - q_lo;
-                const size_t smem_sub = (size_t)pa_sub.PA * (sizeof(uint64_t) + sizeof(uint32_t));
+                const size_t smem_sub = (size_t)pa_sub.PA * sizeof(uint32_t);
                 for (size_t si = 0; si < job.srcs.size(); ++si) {
                     const Src &src = job.srcs[si];
                     if (src.n == 0) continue;

@@ -131,9 +131,18 @@ SG_HD int kmer_word_cmp(const Kmer<NW> &a, const Kmer<NW> &b) {
     }
     return 0;
 }
-// IsMinimal: fwd <= rc in nucleotide order (self-RC counts as minimal)
+// IsMinimal: fwd <= rc in nucleotide order (self-RC counts as minimal). r MUST be the reverse complement of f. Then the
+// nucleotide order from position 0 equals the INTEGER order of the packed words (word NW-1 most significant): the integer
+// compare decides at the highest digit i with f[i] != r[i] = 3 - f[K-1-i], the nucleotide compare at the lowest digit j with
+// f[j] != r[j] = 3 - f[K-1-j]; these are the same pair of positions (j = K-1-i) and both say "f first" iff f[i] + f[j] < 3.
+// A multiword unsigned compare is 2 instructions per word; kmer_nuc_less (first differing digit via ctz) is ~45 and branches.
 template <int NW>
-SG_HD bool kmer_is_minimal(const Kmer<NW> &f, const Kmer<NW> &r) { return !kmer_nuc_less(r, f); }
+SG_HD bool kmer_is_minimal(const Kmer<NW> &f, const Kmer<NW> &r) {
+    bool le = true;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) le = (f.w[j] < r.w[j]) || (f.w[j] == r.w[j] && le);
+    return le;
+}
 
 // K-mer window starting at base `pos` of a packed sequence
 template <int NW, typename Ptr>
@@ -303,7 +312,10 @@ SG_HD Hash128 xxh3_128(const Kmer<NW> &k) {
 template <int NW>
 SG_HD uint32_t kmer_bucket(const Kmer<NW> &k, uint32_t B) {
     if (B == 1) return 0;
-    return (uint32_t)mulhi64(xxh3_64<NW>(k), (uint64_t)B);
+    // mulhi64(hash, B) with a 32-bit B: two 32x32->64 products instead of a full 64x64->128
+    const uint64_t h = xxh3_64<NW>(k);
+    const uint64_t t = (uint64_t)(uint32_t)h * B;
+    return (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * B + (t >> 32)) >> 32);
 }
 
 // ---- boomphf level hashes (BooPHF.h:606-613, :94-100): s0 = high64, s1 = low64 -------------------
@@ -353,6 +365,12 @@ SG_HD uint32_t key_bits(const Kmer<NW> &k, int K, int pos, int r) {
         }
     }
     return (uint32_t)(acc << (r - got));
+}
+// key_bits(k, K, 0, r), r <= 32: the partition digit of level A. With two or more words the first word is full: one shift.
+template <int NW>
+SG_HD uint32_t key_top_bits(const Kmer<NW> &k, int K, int r) {
+    if (NW >= 2) return r ? (uint32_t)(k.w[0] >> (64 - r)) : 0u;
+    return key_bits<NW>(k, K, 0, r);
 }
 SG_HD int key_total_bits(int K) { return 2 * K; }
 
