@@ -576,10 +576,10 @@ __host__ __device__ uint64_t selftest_roll_unit(int K, int L, const uint64_t *se
     if (j0 >= nwin) return 0;
     const int cnt = nwin - j0 < 24 ? (int)(nwin - j0) : 24;
     RollState<NW> st;
-    roll_init<NW>(st, seq, (int)j0, K, cnt > 1);
+    roll_init<NW>(st, seq, (int)j0, K, cnt);
     uint64_t bad = 0;
     for (int s = 0; s < cnt; ++s) {
-        if (s) roll_next<NW>(st, seq, K);
+        if (s) roll_next<NW>(st, K);
         const Kmer<NW> f = kmer_window<NW>(seq, j0 + s, K);
         const Kmer<NW> r = kmer_rc<NW>(f, K);
         if (!kmer_eq<NW>(f, st.f) || !kmer_eq<NW>(r, st.r)) ++bad;

@@ -34,6 +34,7 @@ struct ReadsSrc {
     const uint64_t *offs;
     const uint32_t *lens;
     int64_t n;          // items = reads
+    uint64_t nwords;    // length of `words`
     int K;
     int both;           // 1: every window emits fwd and rc (spades-kmercount), 0: canonical form once
     __device__ __forceinline__ uint32_t nrec(int64_t item) const {
@@ -364,61 +365,88 @@ __global__ void __launch_bounds__(kAThreads) levelA_scatter_k(Src src, LevelA p,
 // only the roll. The 2-byte partition ids of a chunk are 48 contiguous bytes: written as six 8-byte words by the count pass,
 // fetched as three 16-byte loads before the walk starts by every scatter pass. Reads only (canonical mode).
 static const int kRollC = 24;            // windows per chunk
+static_assert(kRollC <= 33 && kRollC % 8 == 0, "roll_init fetches a chunk's bases from two words; an id row is a whole number of 16-byte words");
 static const int kRollThreads = 512;     // 2-3 CTAs per SM; units of a tile are dealt round-robin to the threads
 
-struct RollTile {
-    uint32_t pref[kATile + 1];           // exclusive prefix of chunks per read
-    uint32_t len[kATile];                // read lengths
+// Round 2: the tile of the rolling kernels is a WARP's: 32 consecutive reads, staged, scanned and walked by one warp with
+// shuffles and __syncwarp only. (The CTA-wide tiles of the first version cost five __syncthreads per 256 reads; ncu showed
+// "barrier" and "long scoreboard" as the top stalls of the partition kernel, 2.2 + 2.1 cycles per issued instruction.) A CTA
+// still owns a contiguous range of tiles -- the same range in the count and in every scatter launch, which is what makes the
+// per-CTA histogram of the count the cursor table of the scatter -- and deals them round-robin to its warps.
+static const int kRollTile = 32;                      // reads per warp tile
+static const int kRollWarps = kRollThreads / 32;
+static const int kRollStageWords = 320;               // per warp: 32 reads x 10 words (<= 320 bp each), else global loads
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+struct RollWarp {
+    uint64_t words[kRollStageWords];     // the tile's packed reads
+    uint32_t pref[kRollTile + 1];        // exclusive prefix of chunks per read
+    uint32_t len[kRollTile];             // read lengths
+    uint32_t off[kRollTile];             // first staged word of a read
+    uint32_t pad_;
 };
+static_assert(sizeof(RollWarp) % 8 == 0, "per-warp slices stay 8-byte aligned");
+static size_t roll_smem_bytes(uint32_t nslots) { return (((size_t)nslots * 4 + 15) & ~(size_t)15) + (size_t)kRollWarps * sizeof(RollWarp); }
+__device__ __forceinline__ RollWarp *roll_warp_slice(unsigned char *raw, uint32_t nslots) {
+    return reinterpret_cast<RollWarp *>(raw + (((size_t)nslots * 4 + 15) & ~(size_t)15)) + (threadIdx.x >> 5);
+}
 
-// per-read chunk counts -> exclusive prefix; returns the tile's chunk total. *uniform = chunks per read when every read of
-// the tile has the same (non-zero) count, else 0.
-__device__ __forceinline__ uint32_t roll_tile_prefix(const ReadsSrc &src, int64_t item0, int nitems, RollTile &rt, uint32_t *uniform) {
-    uint32_t c = 0;
-    if ((int)threadIdx.x < nitems) {
-        const int L = (int)src.lens[item0 + threadIdx.x];
-        rt.len[threadIdx.x] = (uint32_t)L;
-        const uint32_t w = L >= src.K ? (uint32_t)(L - src.K + 1) : 0u;
+// one warp: chunk counts of the tile's reads -> exclusive prefix, the reads' words -> shared memory. Returns the tile's chunk
+// total; *uniform = chunks per read when every read has the same (non-zero) count, else 0; *staged = words are in rw.words.
+__device__ __forceinline__ uint32_t roll_warp_setup(const ReadsSrc &src, int64_t item0, int nitems, RollWarp &rw, uint32_t *uniform, bool *staged) {
+    const int lane = threadIdx.x & 31;
+    uint32_t c = 0, L = 0;
+    uint64_t a = 0, b = 0;
+    if (lane < nitems) {
+        L = src.lens[item0 + lane];
+        a = src.offs[item0 + lane];
+        b = a + (((uint64_t)L + 31) >> 5);
+        const uint32_t w = (int)L >= src.K ? (uint32_t)((int)L - src.K + 1) : 0u;
         c = (w + kRollC - 1) / kRollC;
     }
-    __shared__ uint32_t wsum[kATile / 32 + 1];
-    __shared__ uint32_t s_c0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_c0 = c;
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (warp < kATile / 32 && lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int w = 0; w < kATile / 32; ++w) { uint32_t t = wsum[w]; wsum[w] = run; run += t; }
-        wsum[kATile / 32] = run;
-    }
-    const uint32_t c0 = s_c0;
-    const int same = __syncthreads_and((int)threadIdx.x >= nitems || c == c0);
-    if ((int)threadIdx.x < kATile) rt.pref[threadIdx.x] = wsum[warp] + inc - c;
-    const uint32_t total = wsum[kATile / 32];
-    if (threadIdx.x == 0) rt.pref[kATile] = total;
-    __syncthreads();
+    rw.len[lane] = L;
+    rw.pref[lane] = inc - c;
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 31) rw.pref[kRollTile] = total;
+    const uint32_t c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool same = __all_sync(0xffffffffu, lane >= nitems || c == c0);
     *uniform = (same && c0) ? c0 : 0u;
+    const uint64_t w0 = __shfl_sync(0xffffffffu, a, 0);
+    const bool ok = lane >= nitems || (a >= w0 && b >= a && b - w0 <= (uint64_t)kRollStageWords);
+    const bool st = __all_sync(0xffffffffu, ok);
+    if (st) {
+        rw.off[lane] = (uint32_t)(a - w0);
+        uint32_t end = lane < nitems ? (uint32_t)(b - w0) : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) end = max(end, __shfl_xor_sync(0xffffffffu, end, o));
+        // all loads first, then the stores: the copy costs one memory round trip, not one per 32 words
+        uint64_t tmp[kRollStageWords / 32];
+#pragma unroll
+        for (int j = 0; j < kRollStageWords / 32; ++j) tmp[j] = (uint32_t)(lane + 32 * j) < end ? __ldg(src.words + w0 + lane + 32 * j) : 0ull;
+#pragma unroll
+        for (int j = 0; j < kRollStageWords / 32; ++j) if ((uint32_t)(lane + 32 * j) < end) rw.words[lane + 32 * j] = tmp[j];
+    }
+    *staged = st;
+    __syncwarp();
     return total;
 }
 
-// chunks per tile x kRollC = ids per tile (rows of the id array; a multiple of 8 ids = 16 bytes)
+// chunks per warp tile x kRollC = ids per tile (rows of the id array: 48 bytes per chunk, so every row is 16-byte aligned)
 __global__ void roll_tile_ids_k(ReadsSrc src, int64_t ntiles, uint32_t *__restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= ntiles) return;
     const int lane = threadIdx.x & 31;
-    const int64_t item0 = t * kATile;
+    const int64_t item = t * kRollTile + lane;
     uint32_t s = 0;
-    for (int i = lane; i < kATile && item0 + i < src.n; i += 32) {
-        const int L = (int)src.lens[item0 + i];
+    if (item < src.n) {
+        const int L = (int)src.lens[item];
         const uint32_t w = L >= src.K ? (uint32_t)(L - src.K + 1) : 0u;
-        s += (w + kRollC - 1) / kRollC;
+        s = (w + kRollC - 1) / kRollC;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if (lane == 0) out[t] = s * kRollC;
@@ -426,11 +454,11 @@ __global__ void roll_tile_ids_k(ReadsSrc src, int64_t ntiles, uint32_t *__restri
 
 // geometry of one unit (chunk): which read, which windows
 struct RollUnit { int it, j0, cnt; };
-__device__ __forceinline__ RollUnit roll_unit(const RollTile &rt, int nitems, uint32_t u, uint32_t unif, int K) {
+__device__ __forceinline__ RollUnit roll_unit(const RollWarp &rw, int nitems, uint32_t u, uint32_t unif, int K) {
     RollUnit q;
-    q.it = find_item_u(rt.pref, nitems, u, unif);
-    q.j0 = (int)(u - rt.pref[q.it]) * kRollC;
-    const int nwin = (int)rt.len[q.it] - K + 1;
+    q.it = find_item_u(rw.pref, nitems, u, unif);
+    q.j0 = (int)(u - rw.pref[q.it]) * kRollC;
+    const int nwin = (int)rw.len[q.it] - K + 1;
     q.cnt = nwin - q.j0 < kRollC ? nwin - q.j0 : kRollC;
     return q;
 }
@@ -438,28 +466,38 @@ __device__ __forceinline__ RollUnit roll_unit(const RollTile &rt, int nitems, ui
 template <int NW>
 __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc src, LevelA p, uint32_t *__restrict__ blk_counts,
                                                                       const uint64_t *__restrict__ tile_off, uint16_t *__restrict__ ids) {
-    extern __shared__ uint32_t sm_dyn[];
-    uint32_t *hist = sm_dyn;                  // PA
-    __shared__ RollTile rt;
-    __shared__ TileStage ts;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sm_raw);     // PA
+    RollWarp &rw = *roll_warp_slice(sm_raw, p.PA);
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const int K = p.K;
-    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (src.n + kRollTile - 1) / kRollTile;
     const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t item0 = t * kATile;
-        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+    for (int64_t t = t0 + warp; t < t1; t += kRollWarps) {
+        const int64_t item0 = t * kRollTile;
+        const int nitems = (int)min((int64_t)kRollTile, src.n - item0);
         uint32_t unif = 0;
-        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
-        const bool staged = tile_stage(src, item0, nitems, ts);
+        bool staged = false;
+        // the warp's next tile is kRollWarps tiles ahead: its lengths and offsets go to L2 now, its packed reads (and id rows) at the
+        // end of this tile, when the loads of their addresses issued here have long returned
+        const bool has_next = t + kRollWarps < t1;
+        const int64_t nx = (t + kRollWarps) * kRollTile;
+        uint64_t next_w0 = 0;
+        if (has_next) {
+            next_w0 = src.offs[nx];
+            if (lane == 0) prefetch_l2(src.lens + nx);
+            else if (lane == 1 && nx + 16 < src.n) prefetch_l2(src.offs + nx + 16);
+        }
+        const uint32_t nunits = roll_warp_setup(src, item0, nitems, rw, &unif, &staged);
         uint64_t *row = ids ? reinterpret_cast<uint64_t *>(ids + tile_off[t]) : nullptr;
-        for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
-            const RollUnit q = roll_unit(rt, nitems, u, unif, K);
-            const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
+        for (uint32_t u = lane; u < nunits; u += 32) {
+            const RollUnit q = roll_unit(rw, nitems, u, unif, K);
+            const uint64_t *seq = staged ? static_cast<const uint64_t *>(rw.words + rw.off[q.it]) : src.words + src.offs[item0 + q.it];
             RollState<NW> st;
-            roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
+            roll_init<NW>(st, seq, q.j0, K, q.cnt);
 #pragma unroll 1
             for (int g = 0; g < kRollC / 4; ++g) {
                 uint64_t acc = 0;
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc 
                     const int s = 4 * g + e;
                     uint32_t id = 0xffffu;
                     if (s < q.cnt) {
-                        if (s > 0) roll_next<NW>(st, seq, K);
+                        if (s > 0) roll_next<NW>(st, K);
                         const Kmer<NW> k = kmer_is_minimal<NW>(st.f, st.r) ? st.f : st.r;
                         uint32_t part;
                         if (part_of<NW>(p, k, &part)) { atomicAdd(&hist[part], 1u); id = part; }
@@ -478,8 +516,10 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc 
                 if (row) row[(size_t)u * (kRollC / 4) + g] = acc;
             }
         }
-        __syncthreads();
+        if (has_next && lane < 10 && next_w0 + 16 * lane < src.nwords) prefetch_l2(src.words + next_w0 + 16 * lane);   // 10 lines = 32 reads x 5 words
+        __syncwarp();                                   // the slice is rewritten by the next tile's setup
     }
+    __syncthreads();
     uint32_t *out = blk_counts + (size_t)blockIdx.x * p.PA;
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) out[i] += hist[i];
 }
@@ -493,13 +533,12 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_count_roll_k(ReadsSrc 
 template <int NW, bool HAS_IDS>
 __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSrc src, LevelA p, uint64_t *__restrict__ base, uint64_t *__restrict__ out,
                                                                         const uint64_t *__restrict__ tile_off, const uint16_t *__restrict__ ids,
-                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo) {
-    extern __shared__ uint32_t sm_dyn[];
+                                                                        uint32_t id_lo, uint32_t row_stride, uint32_t q_lo, uint64_t ids_len) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     // one 32-bit cursor per partition, relative to the first record this launch may write (a CTA's share of a pass is far below
     // 2^32 records): the slot of a record is ONE shared-memory atomic, no base lookup and no 64-bit add behind it
-    uint32_t *cur = sm_dyn;                                             // PA u32
-    __shared__ RollTile rt;
-    __shared__ TileStage ts;
+    uint32_t *cur = reinterpret_cast<uint32_t *>(sm_raw);               // PA u32
+    RollWarp &rw = *roll_warp_slice(sm_raw, p.PA);
     uint64_t *mybase = base + (size_t)blockIdx.x * row_stride + q_lo;
     const uint64_t region0 = mybase[0];                                 // cursors of a row ascend with the partition
     for (uint32_t i = threadIdx.x; i < p.PA; i += blockDim.x) cur[i] = (uint32_t)(mybase[i] - region0);
@@ -507,17 +546,30 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
     uint64_t *const out0 = out + region0 * NW;
     const int K = p.K;
     const uint32_t PA = p.PA;
-    const int64_t ntiles = (src.n + kATile - 1) / kATile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (src.n + kRollTile - 1) / kRollTile;
     const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * per, t1 = min(ntiles, t0 + per);
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t item0 = t * kATile;
-        const int nitems = (int)min((int64_t)kATile, src.n - item0);
+    for (int64_t t = t0 + warp; t < t1; t += kRollWarps) {
+        const int64_t item0 = t * kRollTile;
+        const int nitems = (int)min((int64_t)kRollTile, src.n - item0);
         uint32_t unif = 0;
-        const uint32_t nunits = roll_tile_prefix(src, item0, nitems, rt, &unif);
-        const bool staged = tile_stage(src, item0, nitems, ts);
+        bool staged = false;
+        // the warp's next tile is kRollWarps tiles ahead: its lengths and offsets go to L2 now, its packed reads (and id rows) at the
+        // end of this tile, when the loads of their addresses issued here have long returned
+        const bool has_next = t + kRollWarps < t1;
+        const int64_t nx = (t + kRollWarps) * kRollTile;
+        uint64_t next_w0 = 0;
+        if (has_next) {
+            next_w0 = src.offs[nx];
+            if (lane == 0) prefetch_l2(src.lens + nx);
+            else if (lane == 1 && nx + 16 < src.n) prefetch_l2(src.offs + nx + 16);
+        }
+        uint64_t next_row = 0;
+        if (HAS_IDS && has_next) next_row = tile_off[t + kRollWarps];
+        const uint32_t nunits = roll_warp_setup(src, item0, nitems, rw, &unif, &staged);
         const ulonglong2 *row = HAS_IDS ? reinterpret_cast<const ulonglong2 *>(ids + tile_off[t]) : nullptr;
-        for (uint32_t u = threadIdx.x; u < nunits; u += blockDim.x) {
+        for (uint32_t u = lane; u < nunits; u += 32) {
             uint64_t idw[kRollC / 4];
             if (HAS_IDS) {
                 // the chunk's 24 ids, in flight while the window is set up
@@ -527,14 +579,16 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
                     idw[2 * v] = x.x; idw[2 * v + 1] = x.y;
                 }
             }
-            const RollUnit q = roll_unit(rt, nitems, u, unif, K);
-            const uint64_t *seq = staged ? static_cast<const uint64_t *>(ts.words + ts.off[q.it]) : src.words + src.offs[item0 + q.it];
+            const RollUnit q = roll_unit(rw, nitems, u, unif, K);
+            const uint64_t *seq = staged ? static_cast<const uint64_t *>(rw.words + rw.off[q.it]) : src.words + src.offs[item0 + q.it];
             RollState<NW> st;
-            roll_init<NW>(st, seq, q.j0, K, q.cnt > 1);
+            roll_init<NW>(st, seq, q.j0, K, q.cnt);
+            // (Delaying a window's store by one window, so that the atomic's latency hides behind the next roll, and 3..6 CTAs per
+            // SM to even out the tail were both measured in round 2: 160-162 ms either way at 100 M reads. profiles/r02n_*.)
 #pragma unroll
             for (int s = 0; s < kRollC; ++s) {
                 if (s >= q.cnt) break;
-                if (s > 0) roll_next<NW>(st, seq, K);
+                if (s > 0) roll_next<NW>(st, K);
                 uint32_t part;
                 bool mine;
                 if (HAS_IDS) {
@@ -555,8 +609,14 @@ __global__ void __launch_bounds__(kRollThreads, 2) levelA_scatter_roll_k(ReadsSr
                 }
             }
         }
-        __syncthreads();
+        if (has_next && lane < 10 && next_w0 + 16 * lane < src.nwords) prefetch_l2(src.words + next_w0 + 16 * lane);   // 10 lines = 32 reads x 5 words
+        if (HAS_IDS && has_next) {                                              // the next tile's id rows: 48 lines for 128 chunks
+            if (next_row + 64 * lane < ids_len) prefetch_l2(ids + next_row + 64 * lane);
+            if (lane < 16 && next_row + 64 * (32 + lane) < ids_len) prefetch_l2(ids + next_row + 64 * (32 + lane));
+        }
+        __syncwarp();                                   // the slice is rewritten by the next tile's setup
     }
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < PA; i += blockDim.x) mybase[i] = region0 + cur[i];   // chained launches continue here
 }
 
@@ -717,11 +777,22 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         if (PIECED) {
-            for (int g = 0; g < pc.G; ++g) {
+            // a WARP streams a piece (a few thousand consecutive records), four independent 512-byte loads in flight per warp:
+            // with the whole CTA striding over one piece at a time a thread had a single 16-byte load outstanding
+            for (int g = (int)(threadIdx.x >> 5); g < pc.G; g += kRThreads / 32) {
                 const uint64_t *ps = buf0 + pc_start[g] * NW;
                 const uint32_t n = pc_len[g];
-                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                    Kmer<NW> k = load_rec<NW>(ps + (uint64_t)i * NW);
+                uint32_t i = threadIdx.x & 31;
+                for (; i + 96 < n; i += 128) {
+                    const Kmer<NW> k0 = load_rec<NW>(ps + (uint64_t)i * NW), k1 = load_rec<NW>(ps + (uint64_t)(i + 32) * NW);
+                    const Kmer<NW> k2 = load_rec<NW>(ps + (uint64_t)(i + 64) * NW), k3 = load_rec<NW>(ps + (uint64_t)(i + 96) * NW);
+                    atomicAdd(&hist[key_bits<NW>(k0, K, (int)s.bits, r)], 1u);
+                    atomicAdd(&hist[key_bits<NW>(k1, K, (int)s.bits, r)], 1u);
+                    atomicAdd(&hist[key_bits<NW>(k2, K, (int)s.bits, r)], 1u);
+                    atomicAdd(&hist[key_bits<NW>(k3, K, (int)s.bits, r)], 1u);
+                }
+                for (; i < n; i += 32) {
+                    const Kmer<NW> k = load_rec<NW>(ps + (uint64_t)i * NW);
                     atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
                 }
             }
@@ -784,10 +855,16 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
             }
         };
         if (PIECED) {
-            for (int g = 0; g < pc.G; ++g) {
+            for (int g = (int)(threadIdx.x >> 5); g < pc.G; g += kRThreads / 32) {
                 const uint64_t *ps = buf0 + pc_start[g] * NW;
                 const uint32_t n = pc_len[g];
-                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) put(load_rec<NW>(ps + (uint64_t)i * NW));
+                uint32_t i = threadIdx.x & 31;
+                for (; i + 96 < n; i += 128) {
+                    const Kmer<NW> k0 = load_rec<NW>(ps + (uint64_t)i * NW), k1 = load_rec<NW>(ps + (uint64_t)(i + 32) * NW);
+                    const Kmer<NW> k2 = load_rec<NW>(ps + (uint64_t)(i + 64) * NW), k3 = load_rec<NW>(ps + (uint64_t)(i + 96) * NW);
+                    put(k0); put(k1); put(k2); put(k3);
+                }
+                for (; i < n; i += 32) put(load_rec<NW>(ps + (uint64_t)i * NW));
             }
         } else {
             for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) put(load_rec<NW>(src + i * NW));
@@ -1365,6 +1442,9 @@ struct LevelAJob {
 };
 
 // total fan-out bits wanted for est_records, minus what the bucket function provides, clamped to the tables
+// CTAs of the level-A grid per SM: the two that are resident. (More waves -- 3, 4, 6 per SM -- were measured for tail balance:
+// 170 / 164 / 156 ms against 162 ms for the partition kernel at 100 M reads, with 3x smaller pieces for the gather. Not kept.)
+static int levelA_ctas_per_sm() { return 2; }
 static int levelA_key_bits(uint64_t est_records, int B, int total_bits, uint32_t target, uint32_t pa_max) {
     const int want = ilog2_floor(est_records / target + 1) + 1;
     const int bbits = ilog2_floor((uint64_t)B) + (((1u << ilog2_floor((uint64_t)B)) < (uint32_t)B) ? 1 : 0);
@@ -1397,7 +1477,7 @@ static void levelA_count(LevelAJob<NW, Src> &job, uint64_t est_records, Timer &t
         for (size_t si = 0; si < job.srcs.size(); ++si) {
             const Src &src = job.srcs[si];
             if (src.n == 0) continue;
-            const int64_t ntiles = (src.n + kATile - 1) / kATile;
+            const int64_t ntiles = (src.n + (job.roll ? kRollTile : kATile) - 1) / (job.roll ? kRollTile : kATile);
             DArr<uint32_t> ttot(ctx, (size_t)ntiles + 1);
             job.tile_off[si].alloc(ctx, (size_t)ntiles + 1);
             SG_CUDA(cudaMemsetAsync(ttot.p + ntiles, 0, 4, st));
@@ -1420,8 +1500,8 @@ static void levelA_count(LevelAJob<NW, Src> &job, uint64_t est_records, Timer &t
         if (src.n == 0) continue;
         if (job.roll) {
             if constexpr (std::is_same<Src, ReadsSrc>::value) {
-                SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
-                levelA_count_roll_k<NW><<<G, kRollThreads, PA_all * sizeof(uint32_t), st>>>(src, pa_all, job.blk_counts.p, job.tile_off[si].p, job.ids[si].p);
+                SG_CUDA(cudaFuncSetAttribute(levelA_count_roll_k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roll_smem_bytes(PA_all)));
+                levelA_count_roll_k<NW><<<G, kRollThreads, roll_smem_bytes(PA_all), st>>>(src, pa_all, job.blk_counts.p, job.tile_off[si].p, job.ids[si].p);
             }
         } else {
             SG_CUDA(cudaFuncSetAttribute(levelA_count_k<NW, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PA_all * sizeof(uint32_t))));
@@ -1467,7 +1547,7 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
     tm.start();
     if (job.roll) {
         if constexpr (std::is_same<Src, ReadsSrc>::value) {
-            const size_t smem = (size_t)PA * sizeof(uint32_t);
+            const size_t smem = roll_smem_bytes(PA);
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SG_CUDA(cudaFuncSetAttribute(levelA_scatter_roll_k<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
@@ -1484,14 +1564,14 @@ static void levelA_scatter(LevelAJob<NW, Src> &job, int b_lo, int b_hi, uint64_t
                 if (q_hi == q_lo) continue;
                 LevelA pa_sub = pa;
                 pa_sub.PA = q_hi - q_lo;
-                const size_t smem_sub = (size_t)pa_sub.PA * sizeof(uint32_t);
+                const size_t smem_sub = roll_smem_bytes(pa_sub.PA);
                 for (size_t si = 0; si < job.srcs.size(); ++si) {
                     const Src &src = job.srcs[si];
                     if (src.n == 0) continue;
                     if (job.use_ids)
-                        levelA_scatter_roll_k<NW, true><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X, job.tile_off[si].p, job.ids[si].p, p_lo + q_lo, PA, q_lo);
+                        levelA_scatter_roll_k<NW, true><<<G, kRollThreads, smem_sub, st>>>(src, pa_sub, base.p, X, job.tile_off[si].p, job.ids[si].p, p_lo + q_lo, PA, q_lo, (uint64_t)job.ids[si].n);
                     else
-                        levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X, nullptr, nullptr, 0u, PA, 0u);
+                        levelA_scatter_roll_k<NW, false><<<G, kRollThreads, smem, st>>>(src, pa, base.p, X, nullptr, nullptr, 0u, PA, 0u, 0ull);
                     ctx->launches++;
                 }
             }
@@ -1538,7 +1618,7 @@ static void run_count(Ctx *ctx, const std::vector<Src> &srcs, int K, int B, bool
     int64_t first = 0;
     for (int s_lo = 0; s_lo < B; s_lo += SR) {
         LevelAJob<NW, Src> job;
-        job.ctx = ctx; job.srcs = srcs; job.K = K; job.B = B; job.rA = rA; job.G = ctx->num_sms * 2;
+        job.ctx = ctx; job.srcs = srcs; job.K = K; job.B = B; job.rA = rA; job.G = ctx->num_sms * levelA_ctas_per_sm();
         job.s_lo = s_lo; job.s_hi = std::min(B, s_lo + SR);
         job.PA_all = (uint32_t)(job.s_hi - job.s_lo) << rA;
         if constexpr (kIsReads) job.roll = !srcs.empty() && !srcs[0].both;
@@ -1631,7 +1711,7 @@ static uint64_t count_windows(Ctx *ctx, int K) {
 
 static ReadsSrc reads_source(Ctx *ctx, int K, bool both) {
     ReadsSrc src;
-    src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.K = K; src.both = both;
+    src.words = ctx->d_words; src.offs = ctx->d_offs; src.lens = ctx->d_lens; src.n = ctx->n_reads; src.nwords = ctx->n_words; src.K = K; src.both = both;
     return src;
 }
 
@@ -2029,7 +2109,7 @@ DistState *dist_begin(Ctx *ctx, int K, int B, int mode, int world, int rank) {
         default: d = new DistStateNW<4>(); break;
     }
     d->ctx = ctx; d->K = K; d->B = B; d->mode = mode; d->nw = nwords_of(K);
-    d->G = ctx->num_sms * 2;
+    d->G = ctx->num_sms * levelA_ctas_per_sm();
     d->want_counts = (mode == kCanonical); d->double_selfrc = (mode == kCanonical) && (K % 2 == 0);
     // every rank must use the same geometry, so it depends on B only. As many level-A partitions as the shared-memory tables allow:
     // an owner's segment is the union of all ranks' records of a partition, so finer partitions keep refinement at one round

@@ -180,24 +180,28 @@ SG_HD int kmer_nuc(const Kmer<NW> &k, int i) { return (int)((k.w[i >> 5] >> ((i 
 template <int NW>
 struct RollState {
     Kmer<NW> f, r;      // window, reverse complement of the window
-    uint64_t cw;        // the packed word the next base comes from, already shifted so that the base is in bits 0..1
-    int pnext;          // position (in the read) of the next base to append
+    uint64_t cw;        // the bases that follow the window, next one in bits 0..1 (up to 32 of them: a whole chunk's worth)
 };
-// window at base j0; `more` = at least one more window follows (then the word holding base j0+K is fetched)
+// window at base j0 of a chunk of `cnt` windows (1 <= cnt <= 33): the cnt-1 bases the walk will append are fetched here, from the
+// one or two packed words that hold them -- the walk itself touches no memory (the first version reloaded a word every 32 bases
+// behind a per-window test; ncu charged that load's latency to nearly every step of a warp, its lanes being in different phases)
 template <int NW, typename Ptr>
-SG_HD void roll_init(RollState<NW> &st, Ptr seq, int j0, int K, bool more) {
+SG_HD void roll_init(RollState<NW> &st, Ptr seq, int j0, int K, int cnt) {
     st.f = kmer_window<NW>(seq, (int64_t)j0, K);
     st.r = kmer_rc<NW>(st.f, K);
-    st.pnext = j0 + K;
-    st.cw = more ? (seq[st.pnext >> 5] >> ((st.pnext & 31) << 1)) : 0;
+    st.cw = 0;
+    if (cnt > 1) {
+        const int p = j0 + K, last = p + cnt - 2;            // first and last base appended
+        const int sh = (p & 31) << 1;
+        st.cw = seq[p >> 5] >> sh;
+        if ((last >> 5) != (p >> 5)) st.cw |= (seq[(p >> 5) + 1] << 1) << (63 - sh);
+    }
 }
-// advance to the next window; only legal while base `pnext` exists in the read
-template <int NW, typename Ptr>
-SG_HD void roll_next(RollState<NW> &st, Ptr seq, int K) {
-    if ((st.pnext & 31) == 0) st.cw = seq[st.pnext >> 5];
+// advance to the next window; only legal cnt-1 times after roll_init(.., cnt)
+template <int NW>
+SG_HD void roll_next(RollState<NW> &st, int K) {
     const uint64_t c = st.cw & 3;
     st.cw >>= 2;
-    ++st.pnext;
     kmer_shl<NW>(st.f, K, (int)c);
 #pragma unroll
     for (int j = NW - 1; j >= 1; --j) st.r.w[j] = (st.r.w[j] << 2) | (st.r.w[j - 1] >> 62);
