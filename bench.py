@@ -515,7 +515,9 @@ def main():
                          "peak_source": peak_src,
                          # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) come from the committed ncu --set full capture of the
                          # SAME workload (profiles/, see NCU_TRAFFIC below); null when no capture of this kernel at this size exists
-                         "traffic": NCU_TRAFFIC.get((n_reads, dom)) if world == 1 else None,
+                         "traffic": (NCU_DRAM_PER_ALGORITHMIC_BYTE[dom][0] * alg[dom] / max(1, launches_per_step.get(dom) or 1)
+                                     if dom in NCU_DRAM_PER_ALGORITHMIC_BYTE else None),
+                         "traffic_source": NCU_DRAM_PER_ALGORITHMIC_BYTE[dom][1] if dom in NCU_DRAM_PER_ALGORITHMIC_BYTE else None,
                          "launches_per_step": launches_per_step.get(dom),
                          "algorithmic_bytes_per_step": int(alg[dom]),
                          "whole_step": {"algorithmic_bytes": int(whole_alg), "achieved": whole_alg / (ms / steps / 1e3) / 1e9, "frac": whole_alg / (ms / steps / 1e3) / 1e9 / peak_gbs},
@@ -529,8 +531,16 @@ def main():
         dist.destroy_process_group()
 
 
-# DRAM bytes per launch of a kernel family from `ncu --set full` captures committed under profiles/ : (reads per GPU, phase) -> bytes
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of a kernel family per ALGORITHMIC byte, from the `ncu --set full` captures committed under
+# profiles/ (ncu cannot profile the 100 M-read / 5-pass configuration itself: its kernel replay backs the 150 GB of device memory up to the
+# host and returns no counters for the kernels that write the largest buffers; the captures are of the same kernels on smaller launches).
+# roofline.traffic = this ratio x the algorithmic bytes of one launch of the timed run.
+NCU_DRAM_PER_ALGORITHMIC_BYTE = {
+    "local_sort_ms": (1.04, "profiles/r02g_ncu_full_100M_arena100_noids.csv: 11.3 GB read + 5.8 GB written for a launch of 0.70 G records"),
+    "refine_ms": (0.80, "profiles/r02k_ncu_full_10M_warp_tiles.csv: 16.2 GB read + 8.1 GB written for 0.95 G records read twice and written once "
+                        "(the second read of a piece is served by L2)"),
+    "extract_count_ms": (7.0, "profiles/r02l_ncu_full_10M_levelA.csv: 0.65 GB read + 1.98 GB written (the 2-byte partition ids) for 0.375 GB of packed reads"),
+}
 
 
 if __name__ == "__main__":

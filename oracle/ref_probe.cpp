@@ -20,6 +20,8 @@
 #include "io/reads/read_stream_vector.hpp"
 #include "io/reads/single_read.hpp"
 #include "io/reads/binary_streams.hpp"
+#include "io/reads/coverage_filtering_read_wrapper.hpp"
+#include "kmer_index/kmer_counting.hpp"
 #include "kmer_index/ph_map/kmer_maps.hpp"
 #include "kmer_index/kmer_mph/kmer_index_builder.hpp"
 #include "kmer_index/kmer_mph/kmer_splitters.hpp"
@@ -159,6 +161,46 @@ int main(int argc, char **argv) {
             for (size_t i = t * per; i < std::min(n, (t + 1) * per); ++i) chunk.emplace_back(seqs[i]);
             streams.push_back(io::RCWrap<Read>(RawStream(chunk)));
         }
+    }
+
+    if (mode == "covfilter") {
+        // SURVEY 8f-3, the pipeline's CoverageFilter phase (stages/construction.cpp:167-198) on the reads + RC streams above:
+        // HLL upper bound of the distinct (k+1)-mers -> qf::cqf sized from it -> counts up to the threshold -> reads whose median
+        // (k+1)-mer multiplicity reaches the threshold survive (io/reads/coverage_filtering_read_wrapper.hpp). PROBE_COV_THR = threshold.
+        // covfilter.txt: "<cardinality upper bound> <hash bits> <range mask> <distinct fingerprints>"; keep.txt: one 0/1 per input read;
+        // hashes.bin: the SymmetricCyclicHash of every (k+1)-window of the first 64 reads (u64 each, read by read).
+        const unsigned thr = getenv("PROBE_COV_THR") ? (unsigned)atoi(getenv("PROBE_COV_THR")) : 2u;
+        const unsigned kp1 = k + 1;
+        rolling_hash::SymmetricCyclicHash<rolling_hash::NDNASeqHash> hasher(kp1);
+        using KmerFilter = kmers::StoringTypeFilter<kmers::InvertableStoring>;
+        const size_t card = kmers::EstimateCardinalityUpperBound(kp1, streams, hasher, KmerFilter());
+        qf::cqf cqf(card);
+        kmers::FillCoverageHistogram(cqf, kp1, hasher, streams, thr, KmerFilter());
+        {
+            std::ofstream os(outdir / "covfilter.txt");
+            os << card << " " << cqf.hash_bits() << " " << cqf.range_mask() << " " << cqf.distinct() << "\n";
+        }
+        io::CoverageFilter<Read, decltype(hasher)> filter(kp1, hasher, cqf, thr);
+        {
+            std::ofstream os(outdir / "keep.txt");
+            for (const auto &s : seqs) os << (filter(Read(s)) ? 1 : 0) << "\n";
+        }
+        {
+            std::ofstream os(outdir / "hashes.bin", std::ios::binary);
+            for (size_t i = 0; i < seqs.size() && i < 64; ++i) {
+                const Sequence &s = seqs[i];
+                if (s.size() < kp1) continue;
+                RtSeq kmer = s.start<RtSeq>(kp1) >> 'A';
+                auto hash = hasher.hash(kmer);
+                for (size_t j = kp1 - 1; j < s.size(); ++j) {
+                    hash = hasher.hash_update(hash, (rolling_hash::chartype)kmer[0], (rolling_hash::chartype)s[j]);
+                    kmer <<= s[j];
+                    const uint64_t v = (uint64_t)hash;
+                    os.write((const char *)&v, 8);
+                }
+            }
+        }
+        return 0;
     }
 
     using Splitter = kmers::DeBruijnReadKMerSplitter<Read, kmers::StoringTypeFilter<kmers::InvertableStoring>>;

@@ -980,4 +980,104 @@ char *orc_gfa(const unitigs_t *u, const mphf_t *mk, const mphf_t *mkp, const uin
     if (!t.b) { t.b = (char *)calloc(1, 1); }
     return t.b;
 }
+/* ------------------------------------------------------------------------------------------------
+ * Coverage pre-filter: stages/construction.cpp:167-198 (CoverageFilter phase).
+ *   hash      adt/cyclichash.hpp:187-259  SymmetricCyclicHash<NDNASeqHash>(n = K): value = fwd + rvs,
+ *             fwd = XOR_p rol(h(s_p), n-1-p), rvs = XOR_p rol(h(3 - s_p), p); character hashes :24-27 (seed 0 -> :51 is the identity).
+ *             KmerSequenceProcessor (kmer_index/kmer_counting.hpp:38-52) rolls it from the hash of 'A' + the first K-1 bases; the
+ *             rolled value equals the direct one (the update :250-256 is exact), which is what is restated here.
+ *   HLL       adt/hll.hpp:16-77: 2^24 one-byte registers, id = top 24 bits, rho = clz of the low 40 bits (as a 64-bit word) - 24 + 1
+ *             (64 - 24 + 1 when they are zero); cardinality :50-64 (sequential double sum in register order), upper bound = 1.1 x.
+ *             EstimateCardinalityUpperBound (kmer_counting.hpp:215-249) adds every window that passes the IsMinimal filter of reads and
+ *             their reverse complements; the hash is symmetric, so that is every window of the forward reads.
+ *   CQF       adt/cqf.hpp:28-37: qbits = max(7, ceil(log2(maxn))) + 1, key = hash & (2^(qbits+8) - 1): an EXACT multiset of keys
+ *             (ext/src/gqf/gqf.c:1430-1477: range = nslots << remainder bits = 2^key_bits). FillCoverageHistogram + CQFProcessor
+ *             (kmer_counting.hpp:96-121,251-282) stop counting a key at the threshold; only ">= threshold" is ever asked.
+ *             A self-RC window passes the filter in the read and in its reverse complement: counted twice (as in coverage).
+ *   filter    io/reads/coverage_filtering_read_wrapper.hpp:37-72: multiplicities of ALL windows of a read, nth_element at size/2,
+ *             keep the read iff that element >= threshold; reads shorter than K are dropped (median 0).
+ * out_stats: [0] cardinality upper bound (size_t(1.1 * cardinality)), [1] key bits, [2] distinct keys, [3] reads kept.
+ * ---------------------------------------------------------------------------------------------- */
+static const uint64_t CYC_H[4] = {0x3c8bfbb395c60474ULL, 0x3193c18562a02b4cULL, 0x20323ed082572324ULL, 0x295549f54be24456ULL};
+static inline uint64_t rol64(uint64_t x, unsigned s) { s &= 63; return s ? (x << s) | (x >> (64 - s)) : x; }
+uint64_t orc_cyclic_hash(const uint64_t *seq, int64_t pos, int K) {
+    uint64_t fwd = 0, rvs = 0;
+    for (int i = 0; i < K; ++i) fwd = rol64(fwd, 1) ^ CYC_H[getnuc(seq, (int)pos + i)];
+    for (int i = 0; i < K; ++i) rvs = rol64(rvs, 1) ^ CYC_H[3 - getnuc(seq, (int)pos + K - 1 - i)];
+    return fwd + rvs;
+}
+typedef struct { uint64_t key; uint32_t cnt; } cfent_t;
+static int cfent_cmp(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+void orc_cov_filter(const uint64_t *words, const uint64_t *offs, const uint32_t *lens, int64_t nreads, int K, unsigned thr,
+                    uint8_t *keep, uint64_t *out_stats) {
+    /* 1. HLL */
+    const unsigned P = 24;
+    const uint64_t m = 1ull << P, mask = (m - 1) << (64 - P);
+    uint8_t *reg = (uint8_t *)calloc(m, 1);
+    size_t nwin = 0;
+    for (int64_t r = 0; r < nreads; ++r) if ((int)lens[r] >= K) nwin += (size_t)lens[r] - K + 1;
+    uint64_t *keys = (uint64_t *)malloc((nwin * 2 + 1) * 8);
+    size_t nk = 0;
+    for (int64_t r = 0; r < nreads; ++r) {
+        const int L = (int)lens[r];
+        if (L < K) continue;
+        const uint64_t *s = words + offs[r];
+        for (int j = 0; j + K <= L; ++j) {
+            const uint64_t d = orc_cyclic_hash(s, j, K);
+            const size_t id = (d & mask) >> (64 - P);
+            const uint64_t low = d & ~mask;
+            const uint8_t rho = (uint8_t)((low == 0 ? 64 : __builtin_clzll(low)) - P + 1);
+            if (reg[id] < rho) reg[id] = rho;
+            keys[nk++] = d;
+            /* self-RC window: minimal in both streams */
+            uint64_t km[MAXW] = {0, 0, 0, 0}, rc[MAXW];
+            for (int i = 0; i < K; ++i) orc_setnuc(km, i, getnuc(s, j + i));
+            orc_rc(km, K, rc);
+            if (memcmp(km, rc, (size_t)nwords(K) * 8) == 0) keys[nk++] = d;
+        }
+    }
+    const double alpha = 0.7213 / (1.0 + 1.079 / (double)m);
+    double res = alpha * (double)m * (double)m, E = 0.0;
+    uint64_t zeros = 0;
+    for (uint64_t i = 0; i < m; ++i) { E += exp2(-(double)reg[i]); zeros += reg[i] == 0; }
+    res /= E;
+    if (res <= 5.0 * (double)m / 2 && zeros > 0) res = (double)m * (log((double)m) - log((double)zeros));
+    free(reg);
+    const size_t maxn = (size_t)(1.1 * res);
+    /* 2. CQF geometry + exact key multiset */
+    unsigned lg = (unsigned)ceil(log2((double)maxn));
+    unsigned qbits = (lg > 7u ? lg : 7u) + 1;
+    const unsigned key_bits = qbits + 8;
+    const uint64_t range_mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
+    for (size_t i = 0; i < nk; ++i) keys[i] &= range_mask;
+    qsort(keys, nk, 8, cfent_cmp);
+    size_t nd = 0;
+    uint32_t *cnt = (uint32_t *)malloc((nk + 1) * 4);
+    for (size_t i = 0; i < nk;) { size_t j = i; while (j < nk && keys[j] == keys[i]) ++j; keys[nd] = keys[i]; cnt[nd] = (uint32_t)(j - i); ++nd; i = j; }
+    /* 3. filter */
+    uint64_t kept = 0;
+    uint32_t *ml = NULL; size_t mlcap = 0;
+    for (int64_t r = 0; r < nreads; ++r) {
+        const int L = (int)lens[r];
+        keep[r] = 0;
+        if (L < K) { if (thr == 0) { keep[r] = 1; ++kept; } continue; }
+        const uint64_t *s = words + offs[r];
+        const size_t w = (size_t)(L - K + 1);
+        if (w > mlcap) { mlcap = w * 2; ml = (uint32_t *)realloc(ml, mlcap * 4); }
+        for (size_t j = 0; j < w; ++j) {
+            const uint64_t d = orc_cyclic_hash(s, (int64_t)j, K) & range_mask;
+            size_t lo = 0, hi = nd;
+            while (lo < hi) { size_t mid = (lo + hi) >> 1; if (keys[mid] < d) lo = mid + 1; else hi = mid; }
+            uint32_t c = (lo < nd && keys[lo] == d) ? cnt[lo] : 0;
+            ml[j] = c < thr ? c : thr;                     /* the filter stops counting at the threshold */
+        }
+        /* nth_element at w/2 == element w/2 of the sorted array */
+        size_t below = 0;
+        for (size_t j = 0; j < w; ++j) below += ml[j] < thr;
+        if (below <= w / 2) { keep[r] = 1; ++kept; }
+    }
+    free(ml); free(cnt); free(keys);
+    out_stats[0] = maxn; out_stats[1] = key_bits; out_stats[2] = nd; out_stats[3] = kept;
+}
+
 void orc_free(void *p) { free(p); }

@@ -1,10 +1,13 @@
 // api.cu -- the extern "C" boundary (include/spades_b200.h). No exceptions cross it; no CPU fallbacks live behind it.
+#include <fcntl.h>
 #include <stdio.h>
+#include <unistd.h>
 
 #include <string>
 
 #include "../../include/spades_b200.h"
 #include "graph.h"
+#include "host_par.h"
 #include "sgpu_internal.h"
 
 using namespace sg;
@@ -140,6 +143,11 @@ int sgpu_reads_pack_text(sgpu_ctx *ctx, const char *text, uint64_t text_bytes, c
     if (!ctx || nreads < 0 || (nreads && (!text || !seq_off || !seq_len))) return SGPU_EINVAL;
     Ctx *c = &ctx->c;
     API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); reads_pack_text(c, text, text_bytes, seq_off, seq_len, nreads, longest_valid); })
+}
+int sgpu_reads_cov_filter(sgpu_ctx *ctx, int K, unsigned threshold, int apply, uint8_t *keep_out, uint64_t *stats) {
+    if (!ctx) return SGPU_EINVAL;
+    Ctx *c = &ctx->c;
+    API_TRY(c, { SG_CUDA(cudaSetDevice(c->device)); cov_filter(c, K, threshold, apply, keep_out, stats); })
 }
 int sgpu_reads_info(sgpu_ctx *ctx, int64_t *nreads, uint64_t *nwords) {
     if (!ctx || !nreads || !nwords) return SGPU_EINVAL;
@@ -415,11 +423,27 @@ int sgpu_graph_write_gfa(const sgpu_graph *g, const char *version, const char *p
     if (!g || !path) return SGPU_EINVAL;
     Ctx *c = g->g->ctx;
     API_TRY(c, {
-        std::string t = graph_gfa(g->g, version ? version : "SPAdes-4.3.0-dev");
-        FILE *f = fopen(path, "wb");
-        SG_CHECK(f, SGPU_EIO, "cannot open GFA file for writing");
-        const bool ok = fwrite(t.data(), 1, t.size(), f) == t.size();
-        fclose(f);
+        std::vector<std::string> ch = graph_gfa_chunks(g->g, version ? version : "SPAdes-4.3.0-dev");
+        // the pieces go to their offsets of the file concurrently (a 5-25 GB text: one writer is the bottleneck of the whole path)
+        const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        SG_CHECK(fd >= 0, SGPU_EIO, "cannot open GFA file for writing");
+        std::vector<uint64_t> off(ch.size() + 1, 0);
+        for (size_t i = 0; i < ch.size(); ++i) off[i + 1] = off[i] + ch[i].size();
+        std::vector<int> okv(ch.size(), 1);
+        par_chunks(ch.size(), (int)std::min<size_t>(ch.size(), 32), [&](int, size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const char *p = ch[i].data();
+                uint64_t left = ch[i].size(), at = off[i];
+                while (left) {
+                    const ssize_t w = pwrite(fd, p, (size_t)std::min<uint64_t>(left, 1ull << 30), (off_t)at);
+                    if (w <= 0) { okv[i] = 0; break; }
+                    p += w; at += (uint64_t)w; left -= (uint64_t)w;
+                }
+                std::string().swap(ch[i]);
+            }
+        });
+        bool ok = close(fd) == 0;
+        for (int v : okv) ok = ok && v;
         SG_CHECK(ok, SGPU_EIO, "short write");
     })
 }

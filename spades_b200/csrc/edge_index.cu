@@ -14,8 +14,11 @@
 //               complementary K-mer is minimal on both strands, so it is always removed). Edge ids as FastGraphFromSequencesConstructor hands them out: edge i -> 3 + 2i, conjugate +1, a self-conjugate
 //               edge has one id and is visited once (graph_core.hpp:233,514-531).
 #include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "graph.h"
+#include "host_par.h"
 #include "mphf_dev.cuh"
 
 namespace sg {
@@ -95,6 +98,10 @@ static void edge_index_fill_nw(Ctx *ctx, EdgeIndex *ei, const UnitigTable &u, ui
 
 EdgeIndex::~EdgeIndex() { delete m; delete ks; }
 
+__global__ void fill_u32_k(uint32_t *__restrict__ p, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int B) {
     if (K == 0) K = g->k + 1;
     SG_CHECK(K >= 1 && K <= g->k + 1 && K <= 128, 2, "edge index: K must be in [1, k+1]");
@@ -110,7 +117,7 @@ EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int B) {
             vk.push_back(g->link_start[i] >> 2);
             if (g->link_end[i] != ~0ull) vk.push_back(g->link_end[i] >> 2);
         }
-        std::sort(vk.begin(), vk.end());
+        par_sort(vk, [](uint64_t a, uint64_t b) { return a < b; });
         const uint64_t vertices = 2 * (uint64_t)(std::unique(vk.begin(), vk.end()) - vk.begin());      // every vertex and its conjugate (k is odd)
         single = B > 1 && vertices / (uint64_t)B > 0;
         B = 1;
@@ -118,26 +125,49 @@ EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int B) {
     cudaStream_t st = ctx->stream;
     const size_t E = g->edge_len.size();
     // ---- unitigs -> 2-bit packed "reads" (primary strand), self-conjugate flags, window prefix
-    std::vector<uint64_t> words, woff(E + 1, 0), wstart(E + 1, 0);
+    std::vector<uint64_t> woff(E + 1, 0), wstart(E + 1, 0);
     std::vector<uint32_t> lens(E + 1, 0);
     std::vector<uint8_t> selfc(E + 1, 0);
     for (size_t i = 0; i < E; ++i) {
         const uint32_t L = g->edge_len[i];
-        const char *s = g->seq.data() + g->edge_off[i];
-        woff[i] = words.size();
         lens[i] = L;
-        words.resize(words.size() + (L + 31) / 32, 0);
-        uint64_t *w = words.data() + woff[i];
-        for (uint32_t p = 0; p < L; ++p) {
-            const char c = s[p];
-            const uint64_t code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
-            w[p >> 5] |= code << ((p & 31) << 1);
-        }
+        woff[i + 1] = woff[i] + (L + 31) / 32;
         selfc[i] = g->link_end[i] == ~0ull ? 1 : 0;              // LinkRecord() of a self-conjugate edge (graph.cu / host_graph.cpp)
         const uint64_t nwin = L >= (uint32_t)K ? (uint64_t)(L - K + 1) : 0;
         wstart[i + 1] = wstart[i] + nwin * (selfc[i] ? 1 : 2);
     }
-    words.resize(words.size() + 4, 0);
+    std::vector<uint64_t> words(woff[E] + 4, 0);
+    {
+        // 2-bit packing of the unitig text on the host threads (10^9..10^10 bases for config 3)
+        unsigned hw = std::thread::hardware_concurrency();
+        const int T = E < 4096 ? 1 : (int)std::min<unsigned>(hw ? hw : 1, 64u);
+        auto pack_range = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const uint32_t L = g->edge_len[i];
+                const char *s = g->seq.data() + g->edge_off[i];
+                uint64_t *w = words.data() + woff[i];
+                for (uint32_t p = 0; p < L; ++p) {
+                    const char c = s[p];
+                    const uint64_t code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+                    w[p >> 5] |= code << ((p & 31) << 1);
+                }
+            }
+        };
+        if (T <= 1) pack_range(0, E);
+        else {
+            // chunks of equal word counts
+            std::vector<std::thread> th;
+            size_t lo = 0;
+            for (int t = 0; t < T; ++t) {
+                const uint64_t target = woff[E] * (uint64_t)(t + 1) / (uint64_t)T;
+                size_t hi = (size_t)(std::upper_bound(woff.begin(), woff.end(), target) - woff.begin());
+                hi = t == T - 1 ? E : std::min(E, std::max(hi ? hi - 1 : 0, lo));
+                th.emplace_back(pack_range, lo, hi);
+                lo = hi;
+            }
+            for (auto &x : th) x.join();
+        }
+    }
     EdgeIndex *ei = new EdgeIndex();
     ei->ctx = ctx; ei->K = K; ei->single_segment = single;
     try {
@@ -164,11 +194,8 @@ EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int B) {
         const uint64_t n = (uint64_t)ei->ks->n;
         ei->edge_id.alloc(ctx, n + 1, true);
         ei->offset.alloc(ctx, n + 1, true);
-        {
-            std::vector<uint32_t> init(n + 1, kEdgeInfoCleared);
-            SG_CUDA(cudaMemcpyAsync(ei->offset.p, init.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
-            SG_CUDA(cudaStreamSynchronize(st));
-        }
+        fill_u32_k<<<ctx->num_sms * 4, 256, 0, st>>>(ei->offset.p, n + 1, kEdgeInfoCleared);
+        ctx->launches++;
         UnitigTable u;
         u.words = d_words.p; u.woff = d_woff.p; u.len = d_lens.p; u.selfc = d_selfc.p; u.wstart = d_wstart.p; u.E = (int64_t)E;
         const uint64_t nwork = wstart[E];

@@ -6,6 +6,8 @@
 //   FastGraphFromSequencesConstructor::CollectLinkRecords (…:473-487) and GraphCoverageFiller (graph_support/coverage_filling.hpp:52-70)
 #include <algorithm>
 
+#include <chrono>
+
 #include "graph.h"
 #include "mphf_dev.cuh"
 
@@ -639,6 +641,16 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
     const int K = km->K;
     const uint64_t nk = (uint64_t)km->n;
     MphfDev mk = mphf_dev(g->mk);
+    // SGPU_TRACE: wall-clock milliseconds of the construction phases on stderr (synchronises the stream at every mark)
+    const bool trace = getenv("SGPU_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto trace_mark = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sgpu graph] %-28s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     const bool have_cov = g->mkp && kp->has_counts;
     MphfDev mkp = have_cov ? mphf_dev(g->mkp) : MphfDev();
     // masks
@@ -662,6 +674,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         SG_CUDA(cudaGetLastError());
     }
     SG_CUDA(cudaStreamSynchronize(st));
+    trace_mark("masks + coverage");
     g->tc_stats[0] = g->tc_stats[1] = g->tc_stats[2] = 0;
     for (int i = 0; i < 4; ++i) g->at_stats[i] = 0;
     if (opt.early_at && nk) {
@@ -710,6 +723,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
     SG_CUDA(cudaMemcpyAsync(g->masks_final.p, g->masks.p, nk, cudaMemcpyDeviceToDevice, st));
     if (nk == 0) { SG_CUDA(cudaStreamSynchronize(st)); return; }
 
+    trace_mark("early clippers");
     KeyTable t = make_table(km);
     // junction list
     DArr<uint32_t> jflag(ctx, nk + 1);
@@ -725,6 +739,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
     compact_list_k<<<div_up((int64_t)nk, 256), 256, 0, st>>>(jflag.p, jpos.p, (int64_t)nk, jlist.p);
     ctx->launches++;
     jflag.release(); jpos.release();
+    trace_mark("junction list");
     // probe
     const uint64_t nslots = njunc * 8;
     DArr<uint32_t> len(ctx, nslots + 1), keepf(ctx, nslots + 1);
@@ -745,6 +760,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
     SG_CUDA(cudaMemcpyAsync(&nbases, eoff.p + nslots, 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
 
+    trace_mark("unitig probe + offsets");
     DArr<char> seq(ctx, nbases + 1);
     DArr<uint64_t> ls(ctx, npaths + 1), le(ctx, npaths + 1);
     DArr<uint32_t> rc(ctx, npaths + 1);
@@ -757,6 +773,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         ctx->launches++;
         SG_CUDA(cudaGetLastError());
     }
+    trace_mark("unitig write");
     // download path edges
     std::vector<uint32_t> h_len(nslots + 1);
     g->edge_len.clear(); g->edge_off.clear();
@@ -776,6 +793,7 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
             if (h_len[i]) { g->edge_off.push_back(off); g->edge_len.push_back(h_len[i]); off += h_len[i]; }
     }
     SG_CHECK(g->edge_len.size() == npaths, 6, "internal: path count mismatch");
+    trace_mark("download + edge table");
     if (!keep_loops) return;
     // ---- loops
     DArr<unsigned long long> d_rem(ctx, 1);

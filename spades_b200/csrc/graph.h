@@ -51,5 +51,6 @@ EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int num_buckets);
 
 // host_graph.cpp : FastGraphFromSequencesConstructor::ConstructGraph + GFAWriter
 std::string graph_gfa(const Graph *g, const char *version);
+std::vector<std::string> graph_gfa_chunks(const Graph *g, const char *version);   // the same text in consecutive pieces (built on the host threads)
 
 }  // namespace sg

@@ -5,12 +5,17 @@
 //   GFAWriter::WriteSegments / WriteLinks / WriteVertexLinks (src/common/io/graph/gfa_writer.cpp:19-116)
 // Inputs are the per-edge link records and raw coverages computed on the GPU (graph.cu).
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "graph.h"
+#include "host_par.h"
 
 namespace sg {
 
@@ -22,29 +27,42 @@ struct Rec {
 };
 const uint64_t kMinId = 3;
 
-void put_u(std::string &s, uint64_t v) {
+inline void put_u(std::string &s, uint64_t v) {
     char tmp[24];
-    int n = snprintf(tmp, sizeof tmp, "%llu", (unsigned long long)v);
-    s.append(tmp, n);
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(tmp[--n]);
 }
+
 }  // namespace
 
-std::string graph_gfa(const Graph *g, const char *version) {
+std::vector<std::string> graph_gfa_chunks(const Graph *g, const char *version) {
     const size_t E = g->edge_len.size();
     const int K = g->k;
+    const bool trace = getenv("SGPU_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto trace_mark = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sgpu gfa]   %-28s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     std::vector<Rec> recs(2 * E);
     std::vector<uint8_t> selfc(E ? E : 1, 0);
-    for (size_t i = 0; i < E; ++i) {
-        const uint64_t e = kMinId + 2 * i;
-        recs[2 * i] = Rec{g->link_start[i], e};
-        if (g->link_end[i] == ~0ull) { selfc[i] = 1; recs[2 * i + 1] = Rec{~0ull, 0}; }      // LinkRecord() of a self-conjugate edge
-        else recs[2 * i + 1] = Rec{g->link_end[i], e};
-    }
-    std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) {                  // CompareByVertexKMerEdgeIdAndMask
+    par_chunks(E, host_threads_for(E), [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const uint64_t e = kMinId + 2 * i;
+            recs[2 * i] = Rec{g->link_start[i], e};
+            if (g->link_end[i] == ~0ull) { selfc[i] = 1; recs[2 * i + 1] = Rec{~0ull, 0}; }      // LinkRecord() of a self-conjugate edge
+            else recs[2 * i + 1] = Rec{g->link_end[i], e};
+        }
+    });
+    par_sort(recs, [](const Rec &a, const Rec &b) {                                        // CompareByVertexKMerEdgeIdAndMask
         const uint64_t ha = a.hm >> 2, hb = b.hm >> 2;
         if (ha != hb) return ha < hb;
         return a.edge_and_mask() < b.edge_and_mask();
     });
+    trace_mark("link records sorted");
     std::vector<size_t> groups;
     for (size_t i = 0; i < recs.size(); ++i) {
         if (i == 0 || (recs[i].hm >> 2) != (recs[i - 1].hm >> 2)) {
@@ -52,55 +70,98 @@ std::string graph_gfa(const Graph *g, const char *version) {
             if (!invalid) groups.push_back(i);
         }
     }
-    std::sort(groups.begin(), groups.end(), [&](size_t a, size_t b) { return recs[a].edge_and_mask() < recs[b].edge_and_mask(); });
+    par_sort(groups, [&](size_t a, size_t b) { return recs[a].edge_and_mask() < recs[b].edge_and_mask(); });
     const size_t V = groups.size();
-    // outgoing edge lists of vertex v (slot 2v) and of its conjugate (slot 2v+1)
-    std::vector<std::vector<uint64_t>> out(2 * V);
-    for (size_t vn = 0; vn < V; ++vn) {
-        const size_t i = groups[vn];
-        for (size_t j = i; j < recs.size() && (recs[j].hm >> 2) == (recs[i].hm >> 2); ++j) {
-            const bool is_start = recs[j].hm & 1, is_rc = recs[j].hm & 2;
-            const uint64_t e = recs[j].edge;
-            const size_t ei = (size_t)((e - kMinId) / 2);
-            const uint64_t ce = selfc[ei] ? e : e + 1;
-            const int side = is_rc ? 1 : 0;                                     // LinkEdge: v1 = is_rc ? conjugate(v) : v
-            if (is_start) out[2 * vn + side].push_back(e);                      // LinkOutgoingEdge(v1, e)
-            else out[2 * vn + (side ^ 1)].push_back(ce);                        // LinkIncomingEdge(v1, e): cvertex(v1) gets conjugate(e)
+    // outgoing edge lists of vertex v (slot 2v) and of its conjugate (slot 2v+1), CSR: a vertex group has at most 8 records
+    std::vector<uint64_t> lst_off(2 * V + 1, 0);
+    const int TV = host_threads_for(V);
+    par_chunks(V, TV, [&](int, size_t lo, size_t hi) {
+        for (size_t vn = lo; vn < hi; ++vn) {
+            const size_t i = groups[vn];
+            uint64_t c0 = 0, c1 = 0;
+            for (size_t j = i; j < recs.size() && (recs[j].hm >> 2) == (recs[i].hm >> 2); ++j) {
+                const bool is_start = recs[j].hm & 1, is_rc = recs[j].hm & 2;
+                const int side = (is_rc ? 1 : 0) ^ (is_start ? 0 : 1);
+                if (side) ++c1; else ++c0;
+            }
+            lst_off[2 * vn + 1] = c0; lst_off[2 * vn + 2] = c1;
         }
-        std::sort(out[2 * vn].begin(), out[2 * vn].end());
-        std::sort(out[2 * vn + 1].begin(), out[2 * vn + 1].end());
-    }
-    std::string t;
-    t.reserve(g->seq.size() + 64 * E + 32 * 4 * V + 64);
-    t += "H\tsp:Z:"; t += version; t += "\n";
-    for (size_t i = 0; i < E; ++i) {
-        t += "S\t"; put_u(t, kMinId + 2 * i); t += "\t";
-        t.append(g->seq, g->edge_off[i], g->edge_len[i]);
-        const uint32_t raw = g->raw_cov[i];
-        const double c = (double)raw / (double)(g->edge_len[i] - K);            // CoverageIndex::coverage, core/coverage.hpp:59-61
-        char tmp[64];
-        int n = snprintf(tmp, sizeof tmp, "\tDP:f:%g\tKC:i:%u\n", (double)(float)c, raw);   // `os << float(cov)`, gfa_writer.cpp:24
-        t.append(tmp, n);
-    }
-    for (size_t vn = 0; vn < V; ++vn) {
-        for (uint64_t x : out[2 * vn + 1]) {                                     // IncomingEdges(v) = conjugates of OutgoingEdges(conj v)
-            const size_t xi = (size_t)((x - kMinId) / 2);
-            const uint64_t inc = selfc[xi] ? x : (((x - kMinId) & 1) ? x - 1 : x + 1);
-            for (uint64_t oe : out[2 * vn]) {
-                const uint64_t ends[2] = {inc, oe};
-                t += "L";
-                for (int q = 0; q < 2; ++q) {
-                    const uint64_t e = ends[q];
-                    const size_t ei = (size_t)((e - kMinId) / 2);
-                    const bool canon = selfc[ei] || (((e - kMinId) & 1) == 0);
-                    t += "\t"; put_u(t, kMinId + 2 * ei); t += canon ? "\t+" : "\t-";
+    });
+    for (size_t i = 1; i <= 2 * V; ++i) lst_off[i] += lst_off[i - 1];
+    std::vector<uint64_t> lst(lst_off[2 * V] + 1);
+    par_chunks(V, TV, [&](int, size_t lo, size_t hi) {
+        for (size_t vn = lo; vn < hi; ++vn) {
+            const size_t i = groups[vn];
+            uint64_t p0 = lst_off[2 * vn], p1 = lst_off[2 * vn + 1];
+            for (size_t j = i; j < recs.size() && (recs[j].hm >> 2) == (recs[i].hm >> 2); ++j) {
+                const bool is_start = recs[j].hm & 1, is_rc = recs[j].hm & 2;
+                const uint64_t e = recs[j].edge;
+                const size_t ei = (size_t)((e - kMinId) / 2);
+                const uint64_t ce = selfc[ei] ? e : e + 1;
+                const int side = is_rc ? 1 : 0;                                     // LinkEdge: v1 = is_rc ? conjugate(v) : v
+                // LinkOutgoingEdge(v1, e)  /  LinkIncomingEdge(v1, e): cvertex(v1) gets conjugate(e)
+                const int slot = is_start ? side : (side ^ 1);
+                const uint64_t val = is_start ? e : ce;
+                if (slot) lst[p1++] = val; else lst[p0++] = val;
+            }
+            std::sort(lst.begin() + lst_off[2 * vn], lst.begin() + lst_off[2 * vn + 1]);
+            std::sort(lst.begin() + lst_off[2 * vn + 1], lst.begin() + lst_off[2 * vn + 2]);
+        }
+    });
+    trace_mark("vertices + edge lists");
+    const int TE = host_threads_for(E);
+    std::vector<std::string> chunks(1 + (size_t)TE + (size_t)TV);
+    chunks[0] = std::string("H\tsp:Z:") + version + "\n";
+    par_chunks(E, TE, [&](int c, size_t lo, size_t hi) {
+        std::string &t = chunks[1 + (size_t)c];
+        size_t bases = 0;
+        for (size_t i = lo; i < hi; ++i) bases += g->edge_len[i];
+        t.reserve(bases + 64 * (hi - lo) + 64);
+        for (size_t i = lo; i < hi; ++i) {
+            t += "S\t"; put_u(t, kMinId + 2 * i); t += "\t";
+            t.append(g->seq, g->edge_off[i], g->edge_len[i]);
+            const uint32_t raw = g->raw_cov[i];
+            const double cv = (double)raw / (double)(g->edge_len[i] - K);          // CoverageIndex::coverage, core/coverage.hpp:59-61
+            char tmp[64];
+            int n = snprintf(tmp, sizeof tmp, "\tDP:f:%g\tKC:i:%u\n", (double)(float)cv, raw);   // `os << float(cov)`, gfa_writer.cpp:24
+            t.append(tmp, n);
+        }
+    });
+    char ktail[32];
+    const int ktail_n = snprintf(ktail, sizeof ktail, "\t%dM\n", K);
+    par_chunks(V, TV, [&](int c, size_t lo, size_t hi) {
+        std::string &t = chunks[1 + (size_t)TE + (size_t)c];
+        t.reserve(40 * (hi - lo) * 2 + 64);
+        for (size_t vn = lo; vn < hi; ++vn) {
+            for (uint64_t a = lst_off[2 * vn + 1]; a < lst_off[2 * vn + 2]; ++a) {   // IncomingEdges(v) = conjugates of OutgoingEdges(conj v)
+                const uint64_t x = lst[a];
+                const size_t xi = (size_t)((x - kMinId) / 2);
+                const uint64_t inc = selfc[xi] ? x : (((x - kMinId) & 1) ? x - 1 : x + 1);
+                for (uint64_t b = lst_off[2 * vn]; b < lst_off[2 * vn + 1]; ++b) {
+                    const uint64_t ends[2] = {inc, lst[b]};
+                    t += "L";
+                    for (int q = 0; q < 2; ++q) {
+                        const uint64_t e = ends[q];
+                        const size_t ei = (size_t)((e - kMinId) / 2);
+                        const bool canon = selfc[ei] || (((e - kMinId) & 1) == 0);
+                        t += "\t"; put_u(t, kMinId + 2 * ei); t += canon ? "\t+" : "\t-";
+                    }
+                    t.append(ktail, ktail_n);
                 }
-                char tmp[32];
-                int n = snprintf(tmp, sizeof tmp, "\t%dM\n", K);
-                t.append(tmp, n);
             }
         }
-    }
+    });
+    trace_mark("S and L lines");
+    return chunks;
+}
+
+std::string graph_gfa(const Graph *g, const char *version) {
+    std::vector<std::string> ch = graph_gfa_chunks(g, version);
+    size_t total = 0;
+    for (const auto &c : ch) total += c.size();
+    std::string t;
+    t.reserve(total);
+    for (auto &c : ch) { t += c; std::string().swap(c); }
     return t;
 }
 

@@ -270,6 +270,7 @@ void ensure_reads_on_device(Ctx *ctx);
 // ingest_gpu.cu
 void reads_pack_text(Ctx *ctx, const char *text, uint64_t text_bytes, const uint64_t *seq_off, const uint32_t *seq_len, int64_t n, int longest_valid);
 void reads_download(Ctx *ctx, uint64_t *words, uint64_t *offs, uint32_t *lens);
+void cov_filter(Ctx *ctx, int K, unsigned thr, int apply, uint8_t *keep_out, uint64_t *stats);   // covfilter.cu
 
 // count.cu
 enum CountMode { kCanonical = 0, kAllWindows = 1 };

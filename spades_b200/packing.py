@@ -62,6 +62,17 @@ def pack_fixed(codes2d: np.ndarray):
     return words, offs, lens
 
 
+def unpack_reads(words, offs, lens):
+    """inverse of pack_reads: the reads of a packed read set as ACGT strings"""
+    out = []
+    for o, L in zip(offs, lens):
+        L = int(L)
+        w = np.asarray(words[int(o): int(o) + (L + 31) // 32], dtype=np.uint64)
+        codes = ((w[:, None] >> (2 * np.arange(32, dtype=np.uint64))[None, :]) & np.uint64(3)).reshape(-1)[:L]
+        out.append("".join("ACGT"[int(c)] for c in codes))
+    return out
+
+
 def unpack_kmers(keys: np.ndarray, K: int):
     """u64 [n, nw] -> list[str]."""
     out = []

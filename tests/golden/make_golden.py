@@ -111,6 +111,36 @@ def save(name, mode, reads, k, B, early_tc=0, edge_index=None):
     print(name, {a: len(b) for a, b in res.items() if a not in ("k", "B", "mode")})
 
 
+def save_covfilter(name, reads, k, thr):
+    """SURVEY 8f-3: ref_probe covfilter = the pipeline's CoverageFilter phase (EstimateCardinalityUpperBound -> qf::cqf ->
+    FillCoverageHistogram -> CoverageFilter on every read) over (k+1)-mers; keeps the cardinality bound, the filter's key bits, the
+    verdict per read and the SymmetricCyclicHash of every window of the first 64 reads."""
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        open(rf, "w").write("\n".join(reads) + "\n")
+        out = os.path.join(d, "out")
+        env = dict(os.environ); env["PROBE_COV_THR"] = str(thr)
+        subprocess.check_call([PROBE, "covfilter", rf, str(k), "4", "2", out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+        card, bits, mask, _ = [int(x) for x in open(os.path.join(out, "covfilter.txt")).read().split()]
+        keep = np.array([int(x) for x in open(os.path.join(out, "keep.txt")).read().split()], dtype=np.uint8)
+        hashes = np.fromfile(os.path.join(out, "hashes.bin"), dtype=np.uint64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), reads=np.frombuffer("\n".join(reads).encode(), dtype=np.uint8), k=np.array([k]),
+                        thr=np.array([thr]), card=np.array([card], dtype=np.uint64), key_bits=np.array([bits]), range_mask=np.array([mask], dtype=np.uint64),
+                        keep=keep, hashes=hashes, mode=np.frombuffer(b"covfilter", dtype=np.uint8))
+    print(name, "reads", len(reads), "kept", int(keep.sum()), "card", card, "key bits", bits)
+
+
+def covfilter_reads(seed):
+    """a well-covered genome, a thinly covered one, palindromes (self-RC (k+1)-mers), short and low-complexity reads"""
+    rng = np.random.default_rng(seed)
+    reads = synthetic_reads(2500, 100, 4000, 0.01, seed=seed) + synthetic_reads(400, 100, 30000, 0.01, seed=seed + 1)
+    x = "".join("ACGT"[i] for i in rng.integers(0, 4, 60))
+    pal = x + revcomp(x)
+    reads += [pal] * 4 + [pal[10:110]] * 2 + ["A" * 100] * 3 + ["ACGT" * 10, "ACGTACGTAC", "AC" * 45]
+    order = rng.permutation(len(reads))
+    return [reads[i] for i in order]
+
+
 REF_FASTX = os.path.join(ROOT, "oracle", "_ref", "ref_fastx")
 
 
@@ -179,3 +209,8 @@ if __name__ == "__main__":
         save("gtest_" + nm + "_k5", "graph", rd, 5, 2)
     # construction_test.cpp:97-105 (SimpleTestEarlyPairedInfo, k=3): its coverage table is the known answer in tests/test_oracle_golden.py
     save("gtest_EarlyPairedInfo_k3", "graph", ["CCCAC", "CCACG", "ACCAC", "CCACA"], 3, 2)
+    # coverage pre-filter, thresholds 2..5, odd and even k+1 (self-RC windows exist only for even k+1)
+    save_covfilter("cov_k21_t2_covfilter", covfilter_reads(31), 21, 2)
+    save_covfilter("cov_k20_t3_covfilter", covfilter_reads(32), 20, 3)
+    save_covfilter("cov_k55_t2_covfilter", covfilter_reads(33), 55, 2)
+    save_covfilter("cov_k31_t5_covfilter", ecoli_reads()[:1500] + covfilter_reads(34)[:800], 31, 5)

@@ -21,7 +21,7 @@ def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     g = {k: z[k] for k in z.files}
     g["reads"] = g["reads"].tobytes().decode().split("\n")
-    g["k"] = int(g["k"][0]); g["B"] = int(g["B"][0]); g["mode"] = g["mode"].tobytes().decode()
+    g["k"] = int(g["k"][0]); g["B"] = int(g["B"][0]) if "B" in g else 0; g["mode"] = g["mode"].tobytes().decode()
     if "tc_bound" in g:
         g["tc_bound"] = int(g["tc_bound"][0])
     for f in ("ei_k", "ei_chunks"):

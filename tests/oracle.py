@@ -46,6 +46,8 @@ def lib():
         L.orc_unitigs_free.restype = None; L.orc_unitigs_free.argtypes = [vp]
         L.orc_gfa.restype = vp; L.orc_gfa.argtypes = [vp, vp, vp, vp, C.c_char_p, vp]
         L.orc_free.restype = None; L.orc_free.argtypes = [vp]
+        L.orc_cyclic_hash.restype = u64; L.orc_cyclic_hash.argtypes = [vp, i64, i32]
+        L.orc_cov_filter.restype = None; L.orc_cov_filter.argtypes = [vp, vp, vp, i64, i32, C.c_uint, vp, vp]
         _LIB = L
     return _LIB
 
@@ -251,3 +253,20 @@ def edge_index(unitig_seqs, k, K=None, B=1):
         else:
             ids[slot] = (1 << 64) - 2; off[slot] = 0x7FFFFFFE
     return ks, m, ids, off
+
+
+def cyclic_hash(words, pos, K):
+    """SymmetricCyclicHash<NDNASeqHash>(K) of the window at base `pos` of a packed sequence (adt/cyclichash.hpp:187-259)"""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    return int(lib().orc_cyclic_hash(_p(w), pos, K))
+
+
+def cov_filter(words, offs, lens, K, thr):
+    """the pipeline's coverage pre-filter over K-mers (K = k+1): (keep flag per read, [cardinality bound, key bits, distinct keys, kept])"""
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    keep = np.zeros(len(lens), dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.uint64)
+    lib().orc_cov_filter(_p(words), _p(offs), _p(lens), len(lens), K, thr, _p(keep), _p(stats))
+    return keep, [int(x) for x in stats]

@@ -369,3 +369,50 @@ def test_million_reads_sha256(case):
     sizes = {f: (len(mine[f]), cs["bytes"][f]) for f in bad}
     g.free()
     assert bad == [], sizes
+
+
+# ---- coverage pre-filter --------------------------------------------------------------------------------------------
+def _kept_reads(c):
+    from spades_b200.reads_io import download_reads
+    from spades_b200.packing import unpack_reads
+    words, offs, lens = download_reads(c)
+    return unpack_reads(words, offs, lens)
+
+
+@pytest.mark.parametrize("name", G.names("covfilter"))
+def test_gpu_coverage_prefilter_matches_reference_golden(name):
+    """cardinality bound, filter key width and the verdict per read against the unmodified reference's CoverageFilter phase; with apply
+    the context's read set becomes the survivors in their original order"""
+    from gpu_util import ctx
+    from spades_b200.reads_io import CovFilteringWrap
+    g = G.load(name)
+    K, thr = g["k"] + 1, int(g["thr"][0])
+    c = ctx()
+    c.set_reads(*pack_reads(g["reads"]))
+    keep, st = CovFilteringWrap(c, K, thr, apply=False)
+    assert st["cardinality_upper_bound"] == int(g["card"][0]) and st["key_bits"] == int(g["key_bits"][0])
+    assert np.array_equal(keep, g["keep"]) and st["kept"] == int(g["keep"].sum())
+    keep2, _ = CovFilteringWrap(c, K, thr, apply=True)
+    assert np.array_equal(keep2, keep)
+    assert _kept_reads(c) == [r for r, f in zip(g["reads"], g["keep"]) if f]
+
+
+@pytest.mark.parametrize("K,thr,seed", [(22, 2, 1), (56, 3, 2), (33, 1, 3), (64, 2, 4), (70, 2, 5), (12, 4, 6), (21, 0, 7)])
+def test_gpu_coverage_prefilter_matches_oracle_random(K, thr, seed):
+    """ragged, short, low-complexity and palindromic reads; K odd / even, one word / two words / K >= 64 (rotation by K mod 64)"""
+    from gpu_util import ctx
+    from spades_b200.reads_io import CovFilteringWrap
+    rng = np.random.default_rng(seed)
+    reads = synthetic_reads(1500, 120, 3000, 0.01, seed=seed) + synthetic_reads(300, 90, 40000, 0.02, seed=seed + 100)
+    x = "".join("ACGT"[i] for i in rng.integers(0, 4, 80))
+    reads += [x + revcomp(x)] * 3 + ["A" * 150, "T" * 97, "AC" * 40, "ACGT", "", x[:K - 1], x[:K]]
+    reads = [r[: int(rng.integers(K - 2, len(r) + 1))] if rng.random() < 0.2 and len(r) > K else r for r in reads]
+    reads = [r for r in reads if r]
+    words, offs, lens = pack_reads(reads)
+    want_keep, want = O.cov_filter(words, offs, lens, K, thr)
+    c = ctx()
+    c.set_reads(words, offs, lens)
+    keep, st = CovFilteringWrap(c, K, thr, apply=True)
+    assert [st["cardinality_upper_bound"], st["key_bits"], st["distinct_keys"], st["kept"]] == want
+    assert np.array_equal(keep, want_keep)
+    assert _kept_reads(c) == [r for r, f in zip(reads, want_keep) if f]

@@ -76,6 +76,23 @@ def test_oracle_edge_index_matches_reference_golden(name):
     assert G.check_edge_index(g, ser, ids, offs, B) == []
 
 
+@pytest.mark.parametrize("name", G.names("covfilter"))
+def test_oracle_coverage_prefilter_matches_reference_golden(name):
+    """SymmetricCyclicHash of every window of the first 64 reads, the HLL cardinality bound, the CQF key width and the
+    verdict per read as the unmodified reference produced them (EstimateCardinalityUpperBound -> qf::cqf -> FillCoverageHistogram ->
+    io::CoverageFilter)"""
+    g = G.load(name)
+    K, thr = g["k"] + 1, int(g["thr"][0])
+    words, offs, lens = pack_reads(g["reads"])
+    hh = [O.cyclic_hash(words[int(offs[i]):], j, K) for i in range(min(64, len(g["reads"]))) for j in range(max(0, len(g["reads"][i]) - K + 1))]
+    assert np.array_equal(np.array(hh, dtype=np.uint64), g["hashes"])
+    keep, stats = O.cov_filter(words, offs, lens, K, thr)
+    assert stats[0] == int(g["card"][0]) and stats[1] == int(g["key_bits"][0])
+    assert (1 << stats[1]) - 1 == int(g["range_mask"][0])
+    assert np.array_equal(keep, g["keep"]) and stats[3] == int(g["keep"].sum())
+    assert 0 < stats[3] < len(keep)                                    # the fixtures exercise both verdicts
+
+
 @pytest.mark.parametrize("name", G.names("graph"))
 def test_oracle_graph_matches_reference_golden(name):
     g = G.load(name)
