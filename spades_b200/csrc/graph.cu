@@ -105,6 +105,15 @@ __global__ void junction_flags_k(KeyTable t, int64_t n, int K, MphfDev mk, const
     const uint8_t m = masks[mphf_lookup_dev<NW>(mk, k)];
     flag[j] = (uniq4(m & 15) < 0 || uniq4(m >> 4) < 0) ? 1u : 0u;       // IsJunction, :194-200
 }
+// kept slots -> dense (offset, length) table of the path edges (eidx = rank among the kept slots, eoff = first base)
+__global__ void edge_table_k(const uint32_t *__restrict__ len, const uint64_t *__restrict__ eidx, const uint64_t *__restrict__ eoff, int64_t nslots,
+                             uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots || !len[i]) return;
+    out_off[eidx[i]] = eoff[i];
+    out_len[eidx[i]] = len[i];
+}
+
 __global__ void compact_list_k(const uint32_t *__restrict__ flag, const uint64_t *__restrict__ pos, int64_t n, uint64_t *__restrict__ list) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -774,10 +783,18 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         SG_CUDA(cudaGetLastError());
     }
     trace_mark("unitig write");
-    // download path edges
-    std::vector<uint32_t> h_len(nslots + 1);
-    g->edge_len.clear(); g->edge_off.clear();
-    SG_CUDA(cudaMemcpyAsync(h_len.data(), len.p, (nslots + 1) * 4, cudaMemcpyDeviceToHost, st));
+    // download path edges: the (offset, length) table is compacted on the device (8 slots per junction, most of them empty)
+    g->edge_len.assign(npaths, 0); g->edge_off.assign(npaths, 0);
+    DArr<uint64_t> c_off(ctx, npaths + 1);
+    DArr<uint32_t> c_len(ctx, npaths + 1);
+    if (nslots) {
+        edge_table_k<<<div_up((int64_t)nslots, 256), 256, 0, st>>>(len.p, eidx.p, eoff.p, (int64_t)nslots, c_off.p, c_len.p);
+        ctx->launches++;
+    }
+    if (npaths) {
+        SG_CUDA(cudaMemcpyAsync(g->edge_off.data(), c_off.p, npaths * 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(g->edge_len.data(), c_len.p, npaths * 4, cudaMemcpyDeviceToHost, st));
+    }
     g->seq.resize(nbases);
     g->link_start.resize(npaths); g->link_end.resize(npaths); g->raw_cov.resize(npaths);
     if (nbases) SG_CUDA(cudaMemcpyAsync(&g->seq[0], seq.p, nbases, cudaMemcpyDeviceToHost, st));
@@ -787,11 +804,6 @@ static void graph_build_nw(Ctx *ctx, Graph *g, const GraphOptions &opt) {
         SG_CUDA(cudaMemcpyAsync(g->raw_cov.data(), rc.p, npaths * 4, cudaMemcpyDeviceToHost, st));
     }
     SG_CUDA(cudaStreamSynchronize(st));
-    {
-        uint64_t off = 0;
-        for (uint64_t i = 0; i < nslots; ++i)
-            if (h_len[i]) { g->edge_off.push_back(off); g->edge_len.push_back(h_len[i]); off += h_len[i]; }
-    }
     SG_CHECK(g->edge_len.size() == npaths, 6, "internal: path count mismatch");
     trace_mark("download + edge table");
     if (!keep_loops) return;

@@ -47,7 +47,7 @@ std::vector<std::string> graph_gfa_chunks(const Graph *g, const char *version) {
         fprintf(stderr, "[sgpu gfa]   %-28s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
-    std::vector<Rec> recs(2 * E);
+    raw_vector<Rec> recs(2 * E);
     std::vector<uint8_t> selfc(E ? E : 1, 0);
     par_chunks(E, host_threads_for(E), [&](int, size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
@@ -63,14 +63,39 @@ std::vector<std::string> graph_gfa_chunks(const Graph *g, const char *version) {
         return a.edge_and_mask() < b.edge_and_mask();
     });
     trace_mark("link records sorted");
-    std::vector<size_t> groups;
-    for (size_t i = 0; i < recs.size(); ++i) {
-        if (i == 0 || (recs[i].hm >> 2) != (recs[i - 1].hm >> 2)) {
-            const bool invalid = (recs[i].hm + 1 == 0) && recs[i].edge == 0;
-            if (!invalid) groups.push_back(i);
-        }
+    // a vertex = a run of records with one k-mer index; the placeholder records of self-conjugate edges form no vertex
+    auto group_start = [&](size_t i) {
+        if (i != 0 && (recs[i].hm >> 2) == (recs[i - 1].hm >> 2)) return false;
+        return !((recs[i].hm + 1 == 0) && recs[i].edge == 0);
+    };
+    raw_vector<size_t> groups;
+    {
+        const int TG = host_threads_for(recs.size());
+        std::vector<size_t> cnt((size_t)TG + 1, 0);
+        par_chunks(recs.size(), TG, [&](int c, size_t lo, size_t hi) {
+            size_t n = 0;
+            for (size_t i = lo; i < hi; ++i) n += group_start(i);
+            cnt[(size_t)c + 1] = n;
+        });
+        for (int c = 0; c < TG; ++c) cnt[(size_t)c + 1] += cnt[(size_t)c];
+        groups.resize(cnt[(size_t)TG]);
+        par_chunks(recs.size(), TG, [&](int c, size_t lo, size_t hi) {
+            size_t o = cnt[(size_t)c];
+            for (size_t i = lo; i < hi; ++i) if (group_start(i)) groups[o++] = i;
+        });
     }
-    par_sort(groups, [&](size_t a, size_t b) { return recs[a].edge_and_mask() < recs[b].edge_and_mask(); });
+    {
+        // vertex order = order of the first record's (edge, mask): sort (key, group) pairs so that the compare touches no other array
+        struct KG { uint64_t key; size_t grp; };
+        raw_vector<KG> kg(groups.size());
+        par_chunks(groups.size(), host_threads_for(groups.size()), [&](int, size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) kg[i] = KG{recs[groups[i]].edge_and_mask(), groups[i]};
+        });
+        par_sort(kg, [](const KG &a, const KG &b) { return a.key < b.key; });
+        par_chunks(groups.size(), host_threads_for(groups.size()), [&](int, size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) groups[i] = kg[i].grp;
+        });
+    }
     const size_t V = groups.size();
     // outgoing edge lists of vertex v (slot 2v) and of its conjugate (slot 2v+1), CSR: a vertex group has at most 8 records
     std::vector<uint64_t> lst_off(2 * V + 1, 0);
@@ -88,7 +113,7 @@ std::vector<std::string> graph_gfa_chunks(const Graph *g, const char *version) {
         }
     });
     for (size_t i = 1; i <= 2 * V; ++i) lst_off[i] += lst_off[i - 1];
-    std::vector<uint64_t> lst(lst_off[2 * V] + 1);
+    raw_vector<uint64_t> lst(lst_off[2 * V] + 1);
     par_chunks(V, TV, [&](int, size_t lo, size_t hi) {
         for (size_t vn = lo; vn < hi; ++vn) {
             const size_t i = groups[vn];
