@@ -1045,7 +1045,7 @@ void orc_cov_filter(const uint64_t *words, const uint64_t *offs, const uint32_t 
     free(reg);
     const size_t maxn = (size_t)(1.1 * res);
     /* 2. CQF geometry + exact key multiset */
-    unsigned lg = (unsigned)ceil(log2((double)maxn));
+    unsigned lg = maxn > 1 ? (unsigned)ceil(log2((double)maxn)) : 0u;
     unsigned qbits = (lg > 7u ? lg : 7u) + 1;
     const unsigned key_bits = qbits + 8;
     const uint64_t range_mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);

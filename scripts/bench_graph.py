@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--buckets", type=int, default=0)
     ap.add_argument("--edge-index", action="store_true", help="also time the EdgeIndex refill (SURVEY 8f-1)")
     ap.add_argument("--early-tc", type=int, default=0)
+    ap.add_argument("--cov-threshold", type=int, default=0, help="run the coverage pre-filter (SURVEY 8f-3) with this threshold first")
     args = ap.parse_args()
     import torch
     from spades_b200.graph import DeBruijnGraph, EdgeIndex
@@ -52,6 +53,10 @@ def main():
         torch.cuda.synchronize(); phases[name] = round((time.perf_counter() - t0) * 1e3, 1)
         return r
 
+    cov_stats = None
+    if args.cov_threshold:
+        from spades_b200.reads_io import CovFilteringWrap
+        _, cov_stats = timed("coverage_prefilter_ms", lambda: CovFilteringWrap(ctx, k + 1, args.cov_threshold, apply=True))
     kpomers = timed("count_kpomers_ms", lambda: KMerDiskCounter(ctx, DeBruijnReadKMerSplitter(k + 1)).Count(nb))
     t_kp = ctx.times()
     kmers = timed("kmers_from_kpomers_ms", lambda: KMerDiskCounter(ctx, DeBruijnKMerKMerSplitter(k, kpomers)).Count(nb))
@@ -82,7 +87,7 @@ def main():
             "Mk-mers/s_whole_path": round(windows / (total / 1e3) / 1e6, 1),
             "distinct_kpomers": kpomers.total_kmers(), "distinct_kmers": kmers.total_kmers(),
             "unitigs": int(ctx.L.sgpu_graph_num_unitigs(g.h)), "unitig_bases": int(ctx.L.sgpu_graph_unitig_bases(g.h)), "gfa_bytes": gfa_bytes,
-            "edge_index_kmers": ei_n,
+            "edge_index_kmers": ei_n, "coverage_prefilter": cov_stats,
             "count_kpomers_detail": {q: t_kp[q] for q in ("extract_count_ms", "extract_scatter_ms", "refine_ms", "local_sort_ms", "compact_ms", "passes")},
             "kmers_from_kpomers_detail": {q: t_km[q] for q in ("extract_count_ms", "extract_scatter_ms", "refine_ms", "local_sort_ms", "compact_ms", "passes")},
             "peak_hbm_gb": round(t["peak_bytes"] / 1e9, 2)}

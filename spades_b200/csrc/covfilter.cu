@@ -220,7 +220,7 @@ void cov_filter(Ctx *ctx, int K, unsigned thr, int apply, uint8_t *keep_out, uin
     }
     const size_t maxn = (size_t)hll_upper_bound(h_reg);
     // 2. qf::cqf(maxn) geometry (cqf.hpp:28-37)
-    const unsigned lg = (unsigned)std::ceil(std::log2((double)maxn));
+    const unsigned lg = maxn > 1 ? (unsigned)std::ceil(std::log2((double)maxn)) : 0u;     // (no reads: the reference's log2(0) is undefined)
     const unsigned qbits = std::max(7u, lg) + 1;
     const unsigned key_bits = qbits + 8;
     SG_CHECK(key_bits <= 47, 2, "coverage filter: more than 2^38 distinct k-mers estimated");

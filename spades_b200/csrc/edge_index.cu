@@ -113,6 +113,7 @@ EdgeIndex *edge_index_build(Ctx *ctx, const Graph *g, int K, int B) {
     bool single = false;
     if (K == g->k + 1) {
         std::vector<uint64_t> vk;
+        vk.reserve(2 * g->edge_len.size());
         for (size_t i = 0; i < g->edge_len.size(); ++i) {
             vk.push_back(g->link_start[i] >> 2);
             if (g->link_end[i] != ~0ull) vk.push_back(g->link_end[i] >> 2);

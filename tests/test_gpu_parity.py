@@ -416,3 +416,30 @@ def test_gpu_coverage_prefilter_matches_oracle_random(K, thr, seed):
     assert [st["cardinality_upper_bound"], st["key_bits"], st["distinct_keys"], st["kept"]] == want
     assert np.array_equal(keep, want_keep)
     assert _kept_reads(c) == [r for r, f in zip(reads, want_keep) if f]
+
+
+@pytest.mark.parametrize("case", ["k21", "k55"])
+def test_million_reads_coverage_prefilter(case):
+    """the coverage pre-filter on the 1 M-read synthetic set: cardinality bound, key width, number of survivors and the SHA-256 of the
+    verdicts as the unmodified reference produced them (tests/golden/make_golden_1m_cov.py), then the count of the SURVIVORS against a
+    count of the same reads handed over directly"""
+    import hashlib
+    import json
+    import os
+    from gpu_util import ctx
+    from spades_b200.kmer_index import DeBruijnReadKMerSplitter, KMerDiskCounter
+    from spades_b200.packing import pack_fixed
+    from spades_b200.reads_io import CovFilteringWrap
+    r = json.load(open(os.path.join(G.GOLDEN_DIR, "syn1M_sha256.json")))["reads"]
+    cs = json.load(open(os.path.join(G.GOLDEN_DIR, "syn1M_covfilter.json")))["cases"][case]
+    codes = synthetic_reads(r["n"], r["len"], r["genome_len"], r["err"], seed=r["seed"], as_codes=True)
+    c = ctx()
+    c.set_reads(*pack_fixed(codes))
+    keep, st = CovFilteringWrap(c, cs["k"] + 1, cs["threshold"], apply=True)
+    assert st["cardinality_upper_bound"] == cs["cardinality_upper_bound"] and st["key_bits"] == cs["key_bits"] and st["kept"] == cs["kept"]
+    assert hashlib.sha256(keep.tobytes()).hexdigest() == cs["sha256_keep"]
+    a = KMerDiskCounter(c, DeBruijnReadKMerSplitter(cs["k"] + 1)).Count(16)
+    ka, ca = a.kmers().copy(), a.counts().copy(); a.free()
+    c.set_reads(*pack_fixed(codes[keep.astype(bool)]))
+    b = KMerDiskCounter(c, DeBruijnReadKMerSplitter(cs["k"] + 1)).Count(16)
+    assert np.array_equal(ka, b.kmers()) and np.array_equal(ca, b.counts()); b.free()

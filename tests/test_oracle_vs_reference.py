@@ -59,3 +59,30 @@ def test_oracle_vs_live_reference_early_tip_clipper(k, B, n, L, glen, err, seed,
     art, r = oracle_artifacts(reads, k, B, early_tc=L - k)
     assert G.check_graph(g, art) == []
     assert r["tc"]["removed"] > 0
+
+
+@pytest.mark.parametrize("k,thr,seed,T", [(21, 2, 51, 1), (20, 3, 52, 8), (55, 2, 53, 3), (63, 4, 54, 8), (69, 2, 55, 2), (127, 3, 56, 8), (11, 6, 57, 8)])
+def test_oracle_vs_live_reference_coverage_prefilter(k, thr, seed, T):
+    """SURVEY 8f-3: the CoverageFilter phase of the unmodified reference (HLL bound -> qf::cqf -> median filter, filled by T racing
+    threads) against the oracle's restatement: the cardinality bound, the key width, the verdict for every read and the rolling hash
+    itself, for k+1 below, at and above 64 (rotation by (k+1) mod 64)"""
+    from spades_b200.packing import pack_reads, revcomp
+    rng = np.random.default_rng(seed)
+    reads = synthetic_reads(2500, 150, 4000, 0.01, seed=seed) + synthetic_reads(400, 150, 40000, 0.02, seed=seed + 1)
+    x = "".join("ACGT"[i] for i in rng.integers(0, 4, 90))
+    reads += [x + revcomp(x)] * 3 + ["A" * 150, "AC" * 70, "ACGTACGT"]
+    with tempfile.TemporaryDirectory() as d:
+        rf = os.path.join(d, "reads.txt")
+        open(rf, "w").write("\n".join(reads) + "\n")
+        env = dict(os.environ); env["PROBE_COV_THR"] = str(thr)
+        subprocess.check_call([PROBE, "covfilter", rf, str(k), "4", str(T), os.path.join(d, "out")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                              env=env, timeout=600)
+        card, bits, mask, _ = [int(v) for v in open(os.path.join(d, "out", "covfilter.txt")).read().split()]
+        keep_ref = np.array([int(v) for v in open(os.path.join(d, "out", "keep.txt")).read().split()], dtype=np.uint8)
+        hashes = np.fromfile(os.path.join(d, "out", "hashes.bin"), dtype=np.uint64)
+    words, offs, lens = pack_reads(reads)
+    keep, st = O.cov_filter(words, offs, lens, k + 1, thr)
+    assert st[0] == card and st[1] == bits and (1 << bits) - 1 == mask
+    assert np.array_equal(keep, keep_ref)
+    hh = [O.cyclic_hash(words[int(offs[i]):], j, k + 1) for i in range(64) for j in range(max(0, len(reads[i]) - k))]
+    assert np.array_equal(np.array(hh, dtype=np.uint64), hashes)
