@@ -797,19 +797,10 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
                 }
             }
         } else {
-            // contiguous segment (second-level splits; the multi-GPU path, whose pull kernel delivers partitions in one piece): four
-            // independent loads in flight per thread, as in the gather above
-            uint64_t i = threadIdx.x;
-            for (; i + 3 * (uint64_t)kRThreads < s.len; i += 4 * (uint64_t)kRThreads) {
-                const Kmer<NW> k0 = load_rec<NW>(src + i * NW), k1 = load_rec<NW>(src + (i + kRThreads) * NW);
-                const Kmer<NW> k2 = load_rec<NW>(src + (i + 2 * kRThreads) * NW), k3 = load_rec<NW>(src + (i + 3 * kRThreads) * NW);
-                atomicAdd(&hist[key_bits<NW>(k0, K, (int)s.bits, r)], 1u);
-                atomicAdd(&hist[key_bits<NW>(k1, K, (int)s.bits, r)], 1u);
-                atomicAdd(&hist[key_bits<NW>(k2, K, (int)s.bits, r)], 1u);
-                atomicAdd(&hist[key_bits<NW>(k3, K, (int)s.bits, r)], 1u);
-            }
-            for (; i < s.len; i += kRThreads) {
-                const Kmer<NW> k = load_rec<NW>(src + i * NW);
+            // (Four loads in flight for the contiguous form too -- second-level splits, the multi-GPU path -- were measured: 57 instead of
+            // 32 registers halve its residency, no gain at 2 GPUs (200.9 vs 200.6 ms) and +15 ms on one (the second-level splits). Not kept.)
+            for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) {
+                Kmer<NW> k = load_rec<NW>(src + i * NW);
                 atomicAdd(&hist[key_bits<NW>(k, K, (int)s.bits, r)], 1u);
             }
         }
@@ -878,13 +869,7 @@ __global__ void __launch_bounds__(kRThreads) refine_k(const Seg *__restrict__ se
                 for (; i < n; i += 32) put(load_rec<NW>(ps + (uint64_t)i * NW));
             }
         } else {
-            uint64_t i = threadIdx.x;
-            for (; i + 3 * (uint64_t)kRThreads < s.len; i += 4 * (uint64_t)kRThreads) {
-                const Kmer<NW> k0 = load_rec<NW>(src + i * NW), k1 = load_rec<NW>(src + (i + kRThreads) * NW);
-                const Kmer<NW> k2 = load_rec<NW>(src + (i + 2 * kRThreads) * NW), k3 = load_rec<NW>(src + (i + 3 * kRThreads) * NW);
-                put(k0); put(k1); put(k2); put(k3);
-            }
-            for (; i < s.len; i += kRThreads) put(load_rec<NW>(src + i * NW));
+            for (uint64_t i = threadIdx.x; i < s.len; i += blockDim.x) put(load_rec<NW>(src + i * NW));
         }
         __syncthreads();
         if constexpr (PAIR && NW == 2) {

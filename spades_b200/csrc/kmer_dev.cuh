@@ -349,7 +349,24 @@ struct LevelHasher {
 // w0[63..0] w1[63..0] ... with the last word contributing only its 2K-64(NW-1) valid low bits.
 // get_bits(k, pos, r) returns T[pos .. pos+r) as an integer (bits past the end read as 0). r <= 32.
 template <int NW>
+SG_HD uint32_t key_bits_generic(const Kmer<NW> &k, int K, int pos, int r);
+template <int NW>
 SG_HD uint32_t key_bits(const Kmer<NW> &k, int K, int pos, int r) {
+    if (NW == 2) {
+        // two words: left-align the second one, take 64 bits of the 128-bit string at `pos`, keep the top r. Branch-free apart from the
+        // (segment-uniform) pos < 64 test; the generic loop below costs ~35 instructions with data-dependent branches.
+        if (r <= 0) return 0u;
+        const int lastbits = 2 * K - 64;                                   // 2..64
+        const uint64_t w1l = k.w[1] << (64 - lastbits);
+        uint64_t x;
+        if (pos < 64) x = (k.w[0] << pos) | ((w1l >> 1) >> (63 - pos));      // pos == 0: the second term is w1l >> 64 == 0
+        else x = pos < 128 ? (w1l << (pos - 64)) : 0;
+        return (uint32_t)(x >> (64 - r));
+    }
+    return key_bits_generic<NW>(k, K, pos, r);
+}
+template <int NW>
+SG_HD uint32_t key_bits_generic(const Kmer<NW> &k, int K, int pos, int r) {
     const int lastbits = 2 * K - 64 * (NW - 1);
     uint64_t acc = 0;
     int got = 0;
