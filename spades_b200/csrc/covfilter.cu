@@ -85,12 +85,14 @@ struct CovTable {
     unsigned long long *e;
     uint64_t cap;
     uint64_t key_mask;
+    unsigned *overflow;         // set when a probe sequence visited every slot (cannot happen while the HLL bound holds; checked on the host)
     __device__ __forceinline__ uint64_t slot_of(uint64_t key) const { return __umul64hi(key * 0x9E3779B97F4A7C15ULL, cap); }
     // CQFProcessor::ProcessKmer: nothing once the count has reached the threshold
     __device__ __forceinline__ void add(uint64_t key, unsigned thr) const {
         const unsigned long long tag = (key + 1) << 16;
         uint64_t s = slot_of(key);
-        for (;;) {
+        for (uint64_t probes = 0;; ++probes) {
+            if (probes > cap) { *overflow = 1u; return; }
             unsigned long long cur = e[s];
             if (cur == 0) {
                 const unsigned long long old = atomicCAS(&e[s], 0ull, tag | 1ull);
@@ -111,12 +113,13 @@ struct CovTable {
     __device__ __forceinline__ unsigned count(uint64_t key) const {
         const unsigned long long tag = (key + 1) << 16;
         uint64_t s = slot_of(key);
-        for (;;) {
+        for (uint64_t probes = 0; probes <= cap; ++probes) {
             const unsigned long long cur = e[s];
             if (cur == 0) return 0;
             if ((cur & ~0xffffull) == tag) return (unsigned)(cur & 0xffffull);
             if (++s == cap) s = 0;
         }
+        return 0;
     }
 };
 
@@ -233,7 +236,10 @@ void cov_filter(Ctx *ctx, int K, unsigned thr, int apply, uint8_t *keep_out, uin
     DArr<uint8_t> keep(ctx, (size_t)n + 1);
     DArr<uint32_t> keep_words(ctx, (size_t)n + 1), flag(ctx, (size_t)n + 1);
     DArr<unsigned long long> d_cnt(ctx, 1);
+    DArr<unsigned> d_ovf(ctx, 1);
     SG_CUDA(cudaMemsetAsync(d_cnt.p, 0, 8, st));
+    SG_CUDA(cudaMemsetAsync(d_ovf.p, 0, 4, st));
+    t.overflow = d_ovf.p;
     if (n) {
         cov_fill_k<<<div_up(n, T), T, 0, st>>>(ctx->d_words, ctx->d_offs, ctx->d_lens, n, K, t, thr);
         cov_filter_k<<<div_up(n, T), T, 0, st>>>(ctx->d_words, ctx->d_offs, ctx->d_lens, n, K, t, thr, keep.p, keep_words.p);
@@ -252,9 +258,12 @@ void cov_filter(Ctx *ctx, int K, unsigned thr, int apply, uint8_t *keep_out, uin
     SG_CUDA(cudaMemcpyAsync(&kept, new_idx.p + n, 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(&kept_words, new_off.p + n, 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(&distinct, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    unsigned overflow = 0;
+    SG_CUDA(cudaMemcpyAsync(&overflow, d_ovf.p, 4, cudaMemcpyDeviceToHost, st));
     if (keep_out && n) SG_CUDA(cudaMemcpyAsync(keep_out, keep.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaStreamSynchronize(st));
+    SG_CHECK(!overflow, 6, "coverage filter: more distinct keys than the cardinality bound allows (table full)");
     if (stats) { stats[0] = maxn; stats[1] = key_bits; stats[2] = distinct; stats[3] = kept; }
     if (!apply) return;
     // 3. the surviving reads become the context's read set (what CovFilteringWrap does to the streams)
