@@ -1,6 +1,7 @@
 // host_par.h -- the host halves of the graph phase (link records, GFA text, unitig packing) on the host threads.
 #pragma once
 #include <stddef.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <memory>
@@ -27,10 +28,12 @@ template <class T> using raw_vector = std::vector<T, default_init_alloc<T>>;
 
 // Config 3 has ~10^8 edges and a 10-25 GB GFA: everything below runs on the host threads in contiguous chunks (the text of a chunk
 // depends only on its own edges / vertices), the chunks are emitted in order.
+// SGPU_HOST_THREADS caps the count (1 = the sequential code path; tests compare the two)
 inline int host_threads_for(size_t n) {
     if (n < (size_t)1 << 15) return 1;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
+    if (const char *e = getenv("SGPU_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) hw = std::min<unsigned>(hw, (unsigned)v); }
     return (int)std::min<size_t>(std::min<unsigned>(hw, 64u), n >> 13);
 }
 template <class F>
