@@ -46,7 +46,7 @@ def test_construction_phase_subclass_compiles_against_the_reference():
         pytest.skip("needs /root/reference to build")
     assert os.path.exists(obj), "run __graft_entry__.build()"
     syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
-    assert "KMerCountingGpu::run" in syms and "GpuKMerDiskCounterT<" in syms
+    assert "KMerCountingGpu::run" in syms and "CoverageFilterGpu::run" in syms and "GpuKMerDiskCounterT<" in syms
 
 
 @needs_tool
